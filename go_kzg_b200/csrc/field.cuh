@@ -1,0 +1,345 @@
+// field.cuh -- Montgomery arithmetic over the two BLS12-381 primes on 32-bit limbs.
+//
+// One element per lane: Fr = 8 x u32 (R = 2^256), Fp = 12 x u32 (R = 2^384).
+// The multiplication is an interleaved (CIOS-style) Montgomery product organised as two
+// accumulators ("even"- and "odd"-aligned 64-bit product columns) so that every
+// lo/hi product pair lands on a contiguous carry chain: mad.lo.cc / madc.hi.cc.  ptxas
+// pairs those into IMAD.WIDE + carry predicates on sm_100a.
+//
+// Everything is __host__ __device__: on the device the carry primitives are inline PTX,
+// on the host the same algorithm runs against an explicit emulated carry flag, so the
+// exact code the kernels execute is unit-tested on the CPU (level-1 API, tests -m "not gpu").
+//
+// Replaces (semantics): kilic Fr/Fe arithmetic reached through bls/bignum_kilic.go:95-115
+// and bls/bls_kilic.go:41-56 of the reference.
+#pragma once
+#include <stdint.h>
+#include "constants.cuh"
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#define HDNI __host__ __device__ __noinline__
+#else
+#define HD inline
+#define HDNI
+#endif
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------
+// carry-chain primitives.  `cf` is the emulated CC.CF on the host; unused on the device.
+// ---------------------------------------------------------------------------------------
+HD uint32_t add_cc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    uint64_t s = (uint64_t)a + b; cf = (uint32_t)(s >> 32); return (uint32_t)s;
+#endif
+}
+HD uint32_t addc_cc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    uint64_t s = (uint64_t)a + b + cf; cf = (uint32_t)(s >> 32); return (uint32_t)s;
+#endif
+}
+HD uint32_t addc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    return a + b + cf;
+#endif
+}
+HD uint32_t sub_cc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    uint64_t s = (uint64_t)a - b; cf = (uint32_t)(s >> 63); return (uint32_t)s;
+#endif
+}
+HD uint32_t subc_cc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    uint64_t s = (uint64_t)a - b - cf; cf = (uint32_t)(s >> 63); return (uint32_t)s;
+#endif
+}
+HD uint32_t subc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    return a - b - cf;
+#endif
+}
+HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+HD uint32_t mul_hi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+#else
+    uint64_t s = (uint64_t)(a * b) + c; cf = (uint32_t)(s >> 32); return (uint32_t)s;
+#endif
+}
+HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+#else
+    uint64_t s = (uint64_t)(a * b) + c + cf; cf = (uint32_t)(s >> 32); return (uint32_t)s;
+#endif
+}
+HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+#else
+    uint64_t s = (((uint64_t)a * b) >> 32) + c + cf; cf = (uint32_t)(s >> 32); return (uint32_t)s;
+#endif
+}
+HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32) + c + cf;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// field parameters
+// ---------------------------------------------------------------------------------------
+struct FpParams {
+    static constexpr int N = B200_FP_LIMBS;
+    static constexpr uint32_t INV = B200_FP_INV32;
+    static HD constexpr uint32_t mod(int i) { constexpr uint32_t t[N] = B200_FP_MOD; return t[i]; }
+    static HD constexpr uint32_t one(int i) { constexpr uint32_t t[N] = B200_FP_ONE; return t[i]; }
+    static HD constexpr uint32_t r2(int i) { constexpr uint32_t t[N] = B200_FP_R2; return t[i]; }
+    static HD constexpr uint32_t modm2(int i) { constexpr uint32_t t[N] = B200_FP_MODM2; return t[i]; }
+};
+struct FrParams {
+    static constexpr int N = B200_FR_LIMBS;
+    static constexpr uint32_t INV = B200_FR_INV32;
+    static HD constexpr uint32_t mod(int i) { constexpr uint32_t t[N] = B200_FR_MOD; return t[i]; }
+    static HD constexpr uint32_t one(int i) { constexpr uint32_t t[N] = B200_FR_ONE; return t[i]; }
+    static HD constexpr uint32_t r2(int i) { constexpr uint32_t t[N] = B200_FR_R2; return t[i]; }
+    static HD constexpr uint32_t modm2(int i) { constexpr uint32_t t[N] = B200_FR_MODM2; return t[i]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// Field element (value semantics; limbs little-endian). Montgomery or canonical content is
+// the caller's business: add/sub are representation agnostic, mul divides by R.
+// ---------------------------------------------------------------------------------------
+template <class P>
+struct Fe {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    static HD Fe zero() { Fe r; for (int i = 0; i < N; i++) r.l[i] = 0; return r; }
+    static HD Fe one() { Fe r; for (int i = 0; i < N; i++) r.l[i] = P::one(i); return r; }   // R mod p
+    static HD Fe r2() { Fe r; for (int i = 0; i < N; i++) r.l[i] = P::r2(i); return r; }
+    static HD Fe modulus() { Fe r; for (int i = 0; i < N; i++) r.l[i] = P::mod(i); return r; }
+
+    HD bool is_zero() const { uint32_t a = 0; for (int i = 0; i < N; i++) a |= l[i]; return a == 0; }
+    HD bool operator==(const Fe& o) const { uint32_t a = 0; for (int i = 0; i < N; i++) a |= l[i] ^ o.l[i]; return a == 0; }
+    HD bool operator!=(const Fe& o) const { return !(*this == o); }
+};
+
+// r = (a >= p) ? a - p : a     (a < 2p)
+template <class P>
+HD void fe_reduce_once(Fe<P>& a) {
+    constexpr int N = P::N;
+    uint32_t t[N], cf = 0;
+    t[0] = sub_cc(a.l[0], P::mod(0), cf);
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = subc_cc(a.l[i], P::mod(i), cf);
+    uint32_t borrow = subc(0u, 0u, cf);   // 0xffffffff if a < p
+#pragma unroll
+    for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t[i];
+}
+
+template <class P>
+HD Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    Fe<P> r; uint32_t cf = 0;
+    r.l[0] = add_cc(a.l[0], b.l[0], cf);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i], cf);
+    r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1], cf);   // both primes leave a spare top bit
+    fe_reduce_once(r);
+    return r;
+}
+
+template <class P>
+HD Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    Fe<P> r; uint32_t cf = 0;
+    r.l[0] = sub_cc(a.l[0], b.l[0], cf);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i], cf);
+    uint32_t borrow = subc(0u, 0u, cf);   // all ones if a < b
+    uint32_t c2 = 0;
+    r.l[0] = add_cc(r.l[0], P::mod(0) & borrow, c2);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], P::mod(i) & borrow, c2);
+    r.l[N - 1] = addc(r.l[N - 1], P::mod(N - 1) & borrow, c2);
+    return r;
+}
+
+template <class P>
+HD Fe<P> fe_neg(const Fe<P>& a) {
+    if (a.is_zero()) return a;
+    return fe_sub(Fe<P>::zero(), a);
+}
+template <class P>
+HD Fe<P> fe_dbl(const Fe<P>& a) { return fe_add(a, a); }
+
+// ---------------------------------------------------------------------------------------
+// Montgomery product, portable form (64-bit accumulation).  Cross-check for the PTX form.
+// ---------------------------------------------------------------------------------------
+template <class P>
+HD Fe<P> fe_mul_portable(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    uint32_t t[N + 2];
+    for (int i = 0; i < N + 2; i++) t[i] = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < N; j++) {
+            uint64_t s = (uint64_t)a.l[j] * b.l[i] + t[j] + carry;
+            t[j] = (uint32_t)s; carry = s >> 32;
+        }
+        uint64_t s = (uint64_t)t[N] + carry;
+        t[N] = (uint32_t)s; t[N + 1] = (uint32_t)(s >> 32);
+        uint32_t m = t[0] * P::INV;
+        s = (uint64_t)m * P::mod(0) + t[0];
+        carry = s >> 32;
+        for (int j = 1; j < N; j++) {
+            s = (uint64_t)m * P::mod(j) + t[j] + carry;
+            t[j - 1] = (uint32_t)s; carry = s >> 32;
+        }
+        s = (uint64_t)t[N] + carry;
+        t[N - 1] = (uint32_t)s;
+        t[N] = t[N + 1] + (uint32_t)(s >> 32);
+    }
+    Fe<P> r;
+    for (int i = 0; i < N; i++) r.l[i] = t[i];
+    fe_reduce_once(r);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Montgomery product, even/odd carry-chain form (the hot routine).
+//
+// T = X + W*Y (W = 2^32): X[k] sits at word k, Y[k] at word k+1.  One row adds a*b_i, then
+// m*p with m = X[0]*INV, which clears word 0; the shift by one word is realised by swapping
+// the roles of the two arrays for the next row (the old X, minus its two lowest words,
+// becomes the new Y).  T < W^(N+1) throughout, so the carry out of an X chain is absorbed
+// by Y[N-1] and the carry out of a Y chain is zero.
+// ---------------------------------------------------------------------------------------
+template <class P, bool FIRST>
+HD void mont_row(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+    constexpr int N = P::N;
+    uint32_t cf = 0;
+    if (FIRST) {
+        // X = even products, Y = odd products (both arrays start at zero)
+#pragma unroll
+        for (int j = 0; j < N; j += 2) { X[j] = mul_lo(a[j], bi); X[j + 1] = mul_hi(a[j], bi); }
+#pragma unroll
+        for (int j = 1; j < N; j += 2) { Y[j - 1] = mul_lo(a[j], bi); Y[j] = mul_hi(a[j], bi); }
+    } else {
+        // here X is the previous row's Y (already word-aligned) and Y the previous row's X,
+        // whose word 1 is still pending at word 0 and whose words 2.. become Y'[0..].
+        X[0] = add_cc(X[0], Y[1], cf);
+#pragma unroll
+        for (int j = 1; j < N - 1; j += 2) {
+            Y[j - 1] = madc_lo_cc(a[j], bi, Y[j + 1], cf);
+            Y[j] = madc_hi_cc(a[j], bi, Y[j + 2], cf);
+        }
+        Y[N - 2] = madc_lo_cc(a[N - 1], bi, 0u, cf);
+        Y[N - 1] = madc_hi(a[N - 1], bi, 0u, cf);
+        X[0] = mad_lo_cc(a[0], bi, X[0], cf);
+        X[1] = madc_hi_cc(a[0], bi, X[1], cf);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            X[j] = madc_lo_cc(a[j], bi, X[j], cf);
+            X[j + 1] = madc_hi_cc(a[j], bi, X[j + 1], cf);
+        }
+        Y[N - 1] = addc(Y[N - 1], 0u, cf);
+    }
+    uint32_t m = X[0] * P::INV;
+    X[0] = mad_lo_cc(m, P::mod(0), X[0], cf);
+    X[1] = madc_hi_cc(m, P::mod(0), X[1], cf);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(m, P::mod(j), X[j], cf);
+        X[j + 1] = madc_hi_cc(m, P::mod(j), X[j + 1], cf);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0u, cf);
+    Y[0] = mad_lo_cc(m, P::mod(1), Y[0], cf);
+    Y[1] = madc_hi_cc(m, P::mod(1), Y[1], cf);
+#pragma unroll
+    for (int j = 3; j < N; j += 2) {
+        Y[j - 1] = madc_lo_cc(m, P::mod(j), Y[j - 1], cf);
+        Y[j] = madc_hi_cc(m, P::mod(j), Y[j], cf);
+    }
+}
+
+template <class P>
+HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t ev[N], od[N];
+    mont_row<P, true>(ev, od, a.l, b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_row<P, false>(od, ev, a.l, b.l[i]);
+        if (i + 1 < N) mont_row<P, false>(ev, od, a.l, b.l[i + 1]);
+    }
+    // last row had X = od (od[0] == 0 now): result word k = od[k+1] + ev[k]
+    Fe<P> r; uint32_t cf = 0;
+    r.l[0] = add_cc(od[1], ev[0], cf);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r.l[k] = addc_cc(od[k + 1], ev[k], cf);
+    r.l[N - 1] = addc(ev[N - 1], 0u, cf);
+    fe_reduce_once(r);
+    return r;
+}
+
+template <class P>
+HD Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul(a, a); }
+
+// canonical <-> Montgomery
+template <class P>
+HD Fe<P> fe_to_mont(const Fe<P>& a) { return fe_mul(a, Fe<P>::r2()); }
+template <class P>
+HD Fe<P> fe_from_mont(const Fe<P>& a) {
+    Fe<P> o = Fe<P>::zero(); o.l[0] = 1;
+    return fe_mul(a, o);
+}
+
+// a^e, e given as NE 32-bit limbs (not constant time; exponents here are public)
+template <class P, int NE>
+HD Fe<P> fe_pow(const Fe<P>& a, const uint32_t (&e)[NE]) {
+    Fe<P> acc = Fe<P>::one();
+    bool started = false;
+    for (int i = NE * 32 - 1; i >= 0; i--) {
+        if (started) acc = fe_sqr(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) { acc = started ? fe_mul(acc, a) : a; started = true; }
+    }
+    return acc;
+}
+// Fermat inverse (0 -> 0, as kilic's RedInverse does for bls/bignum_kilic.go:113)
+template <class P>
+HD Fe<P> fe_inv(const Fe<P>& a) {
+    uint32_t e[P::N];
+    for (int i = 0; i < P::N; i++) e[i] = P::modm2(i);
+    if (a.is_zero()) return a;
+    return fe_pow<P, P::N>(a, e);
+}
+
+typedef Fe<FpParams> Fp;
+typedef Fe<FrParams> Fr;
+
+}  // namespace b200

@@ -1,0 +1,196 @@
+// g1.cuh -- BLS12-381 G1 in Jacobian coordinates over the Montgomery Fp of field.cuh.
+//
+// Group law is complete by case analysis (infinity, P == Q, P == -Q): FK20 zero-pads half of
+// every G1 transform with infinity (fk20_single.go:48-50,163-166; kzg.go:61) and structured
+// inputs do hit the doubling / cancellation branches.
+//
+// Replaces (semantics): kilic PointG1 Add/Sub/Double/MulScalar reached through
+// bls/bls_kilic.go:41-65 (MulG1/AddG1/SubG1/NegG1).
+#pragma once
+#include "field.cuh"
+
+namespace b200 {
+
+struct G1J {   // Jacobian, Montgomery coordinates; infinity <=> z == 0
+    Fp x, y, z;
+    static HD G1J infinity() { G1J r; r.x = Fp::zero(); r.y = Fp::zero(); r.z = Fp::zero(); return r; }
+    HD bool is_inf() const { return z.is_zero(); }
+};
+struct G1A {   // affine, Montgomery coordinates; infinity <=> (0,0) (not on y^2 = x^3 + 4)
+    Fp x, y;
+    HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+
+HD Fp fp_const_beta() { Fp r; constexpr uint32_t t[12] = B200_GLV_BETA; for (int i = 0; i < 12; i++) r.l[i] = t[i]; return r; }
+HD Fp fp_const_four() { Fp r; constexpr uint32_t t[12] = B200_FP_FOUR; for (int i = 0; i < 12; i++) r.l[i] = t[i]; return r; }
+HD G1J g1_generator() {
+    G1J g;
+    constexpr uint32_t gx[12] = B200_G1_GEN_X; constexpr uint32_t gy[12] = B200_G1_GEN_Y;
+    for (int i = 0; i < 12; i++) { g.x.l[i] = gx[i]; g.y.l[i] = gy[i]; }
+    g.z = Fp::one();
+    return g;
+}
+
+HD G1J g1_neg(const G1J& p) { G1J r = p; r.y = fe_neg(p.y); return r; }
+
+// 2P: 3M + 4S (a = 0)
+HD G1J g1_dbl(const G1J& p) {
+    if (p.is_inf()) return p;
+    Fp a = fe_sqr(p.x);
+    Fp b = fe_sqr(p.y);
+    Fp c = fe_sqr(b);
+    Fp d = fe_mul(p.x, b);
+    d = fe_dbl(fe_dbl(d));            // 4 X Y^2
+    Fp e = fe_add(fe_dbl(a), a);      // 3 X^2
+    Fp f = fe_sqr(e);
+    G1J r;
+    r.z = fe_dbl(fe_mul(p.y, p.z));
+    r.x = fe_sub(f, fe_dbl(d));
+    Fp c8 = fe_dbl(fe_dbl(fe_dbl(c)));
+    r.y = fe_sub(fe_mul(e, fe_sub(d, r.x)), c8);
+    return r;
+}
+
+// P + Q, general Jacobian (12M + 4S)
+HD G1J g1_add(const G1J& p, const G1J& q) {
+    if (p.is_inf()) return q;
+    if (q.is_inf()) return p;
+    Fp z1z1 = fe_sqr(p.z), z2z2 = fe_sqr(q.z);
+    Fp u1 = fe_mul(p.x, z2z2), u2 = fe_mul(q.x, z1z1);
+    Fp s1 = fe_mul(fe_mul(p.y, q.z), z2z2), s2 = fe_mul(fe_mul(q.y, p.z), z1z1);
+    if (u1 == u2) {
+        if (s1 == s2) return g1_dbl(p);
+        return G1J::infinity();
+    }
+    Fp h = fe_sub(u2, u1), rr = fe_sub(s2, s1);
+    Fp hh = fe_sqr(h), hhh = fe_mul(h, hh), v = fe_mul(u1, hh);
+    G1J r;
+    r.x = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
+    r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(s1, hhh));
+    r.z = fe_mul(fe_mul(p.z, q.z), h);
+    return r;
+}
+HD G1J g1_sub(const G1J& p, const G1J& q) { return g1_add(p, g1_neg(q)); }
+
+// P + Q with Q affine (8M + 3S)
+HD G1J g1_add_mixed(const G1J& p, const G1A& q) {
+    if (q.is_inf()) return p;
+    if (p.is_inf()) { G1J r; r.x = q.x; r.y = q.y; r.z = Fp::one(); return r; }
+    Fp z1z1 = fe_sqr(p.z);
+    Fp u2 = fe_mul(q.x, z1z1), s2 = fe_mul(fe_mul(q.y, p.z), z1z1);
+    if (p.x == u2) {
+        if (p.y == s2) return g1_dbl(p);
+        return G1J::infinity();
+    }
+    Fp h = fe_sub(u2, p.x), rr = fe_sub(s2, p.y);
+    Fp hh = fe_sqr(h), hhh = fe_mul(h, hh), v = fe_mul(p.x, hh);
+    G1J r;
+    r.x = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
+    r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(p.y, hhh));
+    r.z = fe_mul(p.z, h);
+    return r;
+}
+
+// (x + t, x - t) sharing the common subexpressions of the two additions (18 mults instead
+// of 32): the radix-2 butterfly of fft_g1.go:52-54.
+HD void g1_add_sub(const G1J& x, const G1J& t, G1J& sum, G1J& diff) {
+    if (t.is_inf()) { sum = x; diff = x; return; }
+    if (x.is_inf()) { sum = t; diff = g1_neg(t); return; }
+    Fp z1z1 = fe_sqr(x.z), z2z2 = fe_sqr(t.z);
+    Fp u1 = fe_mul(x.x, z2z2), u2 = fe_mul(t.x, z1z1);
+    Fp s1 = fe_mul(fe_mul(x.y, t.z), z2z2), s2 = fe_mul(fe_mul(t.y, x.z), z1z1);
+    if (u1 == u2) {   // t == +-x: rare, take the generic path
+        sum = g1_add(x, t);
+        diff = g1_add(x, g1_neg(t));
+        return;
+    }
+    Fp h = fe_sub(u2, u1);
+    Fp hh = fe_sqr(h), hhh = fe_mul(h, hh), v = fe_mul(u1, hh);
+    Fp z3 = fe_mul(fe_mul(x.z, t.z), h);
+    Fp s1hhh = fe_mul(s1, hhh);
+    Fp v2 = fe_dbl(v);
+    Fp rp = fe_sub(s2, s1);                       // x + t
+    Fp rm = fe_sub(fe_neg(s2), s1);               // x + (-t)
+    sum.x = fe_sub(fe_sub(fe_sqr(rp), hhh), v2);
+    sum.y = fe_sub(fe_mul(rp, fe_sub(v, sum.x)), s1hhh);
+    sum.z = z3;
+    diff.x = fe_sub(fe_sub(fe_sqr(rm), hhh), v2);
+    diff.y = fe_sub(fe_mul(rm, fe_sub(v, diff.x)), s1hhh);
+    diff.z = z3;
+}
+
+// endomorphism used by the GLV split k = k1 + k2 z^2:  z^2 (x, y) = (beta x, -y)
+HD G1J g1_endo(const G1J& p) { G1J r; r.x = fe_mul(p.x, fp_const_beta()); r.y = fe_neg(p.y); r.z = p.z; return r; }
+
+HD bool g1_equal(const G1J& a, const G1J& b) {   // bls/bls_kilic.go:106 EqualG1
+    if (a.is_inf() || b.is_inf()) return a.is_inf() && b.is_inf();
+    Fp za = fe_sqr(a.z), zb = fe_sqr(b.z);
+    if (fe_mul(a.x, zb) != fe_mul(b.x, za)) return false;
+    return fe_mul(a.y, fe_mul(zb, b.z)) == fe_mul(b.y, fe_mul(za, a.z));
+}
+
+// ---------------------------------------------------------------------------------------
+// scalar multiplication
+// ---------------------------------------------------------------------------------------
+// k * P, k canonical 8 x u32, fixed 4-bit windows (per-lane scalars: every lane executes the
+// same double/add schedule, only the table index differs).  Used for MulG1 with a
+// variable scalar (fk20_single.go:72-74 ToeplitzPart2, bls/bls_kilic.go:41).
+HD G1J g1_mul_window4(const G1J& p, const uint32_t* k) {
+    G1J tab[16];
+    tab[0] = G1J::infinity();
+    tab[1] = p;
+    for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? g1_add(tab[i - 1], p) : g1_dbl(tab[i >> 1]);
+    G1J acc = G1J::infinity();
+    for (int w = 63; w >= 0; w--) {
+        if (w != 63) { acc = g1_dbl(acc); acc = g1_dbl(acc); acc = g1_dbl(acc); acc = g1_dbl(acc); }
+        uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (d) acc = g1_add(acc, tab[d]);
+    }
+    return acc;
+}
+
+// Twiddle "program": a fixed scalar pre-split on the host as k = k1 + k2 z^2 (GLV) and
+// recoded in width-4 NAF (odd digits in [-7, 7]).  All lanes of a warp that share a twiddle
+// run the same schedule, so the digit tests are branch-uniform.
+#define B200_WNAF_LEN 132   // >= 129 digits per half scalar, padded
+struct ScalarProgram {
+    int8_t d1[B200_WNAF_LEN];   // wNAF digits of k1, index = bit position
+    int8_t d2[B200_WNAF_LEN];   // wNAF digits of k2 (applied to the endomorphism image)
+    int16_t top;                // highest non-zero position (-1: scalar is zero)
+    int16_t is_one;             // scalar == 1 (skip the multiplication)
+    int16_t pad[2];
+};
+
+HD G1J g1_mul_program(const G1J& p, const ScalarProgram* prog) {
+    int top = prog->top;
+    if (top < 0 || p.is_inf()) return G1J::infinity();
+    if (prog->is_one) return p;
+    // odd multiples 1P, 3P, 5P, 7P
+    G1J tab[4];
+    tab[0] = p;
+    G1J p2 = g1_dbl(p);
+    tab[1] = g1_add(p2, p);
+    tab[2] = g1_add(tab[1], p2);
+    tab[3] = g1_add(tab[2], p2);
+    const Fp beta = fp_const_beta();
+    G1J acc = G1J::infinity();
+    for (int i = top; i >= 0; i--) {
+        acc = g1_dbl(acc);
+        int a = prog->d1[i];
+        if (a) {
+            G1J t = tab[(a < 0 ? -a : a) >> 1];
+            if (a < 0) t.y = fe_neg(t.y);
+            acc = g1_add(acc, t);
+        }
+        int b = prog->d2[i];
+        if (b) {
+            G1J t = tab[(b < 0 ? -b : b) >> 1];
+            t.x = fe_mul(t.x, beta);
+            if (b > 0) t.y = fe_neg(t.y);    // z^2 (x,y) = (beta x, -y)
+            acc = g1_add(acc, t);
+        }
+    }
+    return acc;
+}
+
+}  // namespace b200

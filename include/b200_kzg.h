@@ -1,0 +1,161 @@
+/*
+ * b200_kzg.h -- C ABI of the B200-native KZG / FFT engine (libb200kzg.so).
+ *
+ * This is the drop-in boundary for protolambda/go-kzg's hot path: a new `bls/` build tag
+ * (`bignum_b200`) binds these symbols over cgo and keeps the Go
+ * FFTSettings / KZGSettings / FK20SingleSettings / FK20MultiSettings API unchanged.
+ * Every entry point cites the reference interface (file:line under /root/reference) it
+ * replaces.  No torch types, plain pointers and sizes only.
+ *
+ * Encodings (ours to choose: bls.Fr / bls.G1Point are opaque outside package bls):
+ *   Fr       4 x uint64 little-endian limbs, canonical residue in [0, r)   (== FrTo32 bytes)
+ *   G1       Jacobian X, Y, Z, each 6 x uint64 little-endian canonical limbs in [0, p);
+ *            point at infinity <=> Z == 0, so the all-zero value is infinity (Go zero value).
+ *   G1 compressed: 48 bytes, ZCash/IETF form (bls/bls_kilic.go:114-121).
+ * Arrays are contiguous ([]bls.Fr / []bls.G1Point pass as &s[0] without copying).
+ *
+ * Ownership: the caller allocates all inputs and outputs; the library never keeps a caller
+ * pointer after return.  Device tables live in the opaque handles.  Handles are immutable
+ * after creation and may be used from any thread; each call sets its CUDA device itself.
+ *
+ * Errors: every function returns a b200_status.  The Go shim maps them back to the
+ * reference's error/panic split.  There is NO CPU fallback: without a
+ * usable CUDA device every compute entry point returns B200_ERR_CUDA / B200_ERR_NO_DEVICE.
+ */
+#ifndef B200_KZG_H
+#define B200_KZG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B200_OK = 0,
+    B200_ERR_TOO_LARGE = 1,     /* "got %d values but only have %d roots of unity" fft_fr.go:57-59,78-80; fft_g1.go:60-62 */
+    B200_ERR_NOT_POW2 = 2,      /* "not a power of two" fft_fr.go:81-83; fft_g1.go:63-65; kzg.go:47,77 */
+    B200_ERR_LEN_MISMATCH = 3,  /* kzg.go:22-24; fk20_single.go:60-62; bls/bls_kilic.go:133-135 */
+    B200_ERR_BAD_INPUT = 4,     /* e.g. "second half should be zeroed" fk20_single.go:150-154; bad point encoding */
+    B200_ERR_CUDA = 5,          /* CUDA runtime failure (see b200_last_cuda_error) */
+    B200_ERR_NO_DEVICE = 6,     /* no CUDA device / library built without one */
+    B200_ERR_TOO_SMALL = 7,     /* kzg.go:25-27,50-52; das_extension.go:72-74 */
+    B200_ERR_RECOVERY = 8,      /* recover_from_samples.go:103-107 reconstructed data mismatch */
+    B200_ERR_ZERO_EVAL = 9      /* recover_from_samples.go:54-58 "bad zero eval" */
+} b200_status;
+
+const char* b200_strerror(int status);
+const char* b200_last_cuda_error(void);
+int b200_device_count(void);
+/* Selects the CUDA device used by handles created afterwards on this thread (default 0). */
+int b200_set_device(int device);
+
+typedef struct b200_fs b200_fs; /* FFTSettings          fft.go:34-42   */
+typedef struct b200_ks b200_ks; /* KZGSettings          kzg.go:11-19   */
+typedef struct b200_fk b200_fk; /* FK20Single/MultiSettings kzg.go:38-41,66-71 */
+
+/* ------------------------------------------------------------------ level 1: package bls ---
+ * Host-side scalar operations so that the Go facade compiles and behaves (API completeness;
+ * none of these is on the hot path -- the hot path crosses cgo at batch granularity below). */
+void b200_fr_add(uint64_t dst[4], const uint64_t a[4], const uint64_t b[4]); /* bls/bignum_kilic.go:99  AddModFr */
+void b200_fr_sub(uint64_t dst[4], const uint64_t a[4], const uint64_t b[4]); /* bls/bignum_kilic.go:95  SubModFr */
+void b200_fr_mul(uint64_t dst[4], const uint64_t a[4], const uint64_t b[4]); /* bls/bignum_kilic.go:109 MulModFr */
+void b200_fr_inv(uint64_t dst[4], const uint64_t a[4]);                      /* bls/bignum_kilic.go:113 InvModFr */
+void b200_fr_div(uint64_t dst[4], const uint64_t a[4], const uint64_t b[4]); /* bls/bignum_kilic.go:103 DivModFr */
+void b200_fr_batch_inv(uint64_t* vals, size_t n);                            /* bls/bignum_kilic.go:117 BatchInvModFr (in place) */
+int b200_fr_valid(const uint8_t le32[32]);                                   /* bls/bignum_all.go:12-35 ValidFr */
+void b200_fr_root_of_unity(unsigned scale, uint64_t out[4]);                 /* bls/globals.go:27-60 Scale2RootOfUnity */
+void b200_g1_generator(uint64_t out[18]);                                    /* bls/bls_kilic.go:23 GenG1 */
+void b200_g1_add(uint64_t dst[18], const uint64_t a[18], const uint64_t b[18]);     /* bls/bls_kilic.go:47 AddG1 */
+void b200_g1_sub(uint64_t dst[18], const uint64_t a[18], const uint64_t b[18]);     /* bls/bls_kilic.go:51 SubG1 */
+void b200_g1_neg(uint64_t dst[18]);                                                 /* bls/bls_kilic.go:63 NegG1 (in place) */
+void b200_g1_mul(uint64_t dst[18], const uint64_t a[18], const uint64_t k[4]);      /* bls/bls_kilic.go:41 MulG1 */
+int b200_g1_equal(const uint64_t a[18], const uint64_t b[18]);                      /* bls/bls_kilic.go:106 EqualG1 */
+void b200_g1_to_compressed(uint8_t out[48], const uint64_t p[18]);                  /* bls/bls_kilic.go:114 ToCompressedG1 */
+int b200_g1_from_compressed(uint64_t out[18], const uint8_t in[48]);                /* bls/bls_kilic.go:118 FromCompressedG1 */
+void b200_g1_to_compressed_many(uint8_t* out, const uint64_t* pts, size_t n);
+int b200_g1_from_compressed_many(uint64_t* out, const uint8_t* in, size_t n);
+
+/* Device MSM.  bls/bls_kilic.go:132-150 LinCombG1: sum_i scalars[i] * points[i]; n == 0 gives
+ * infinity (bls/bls_test.go:69-77).  Pippenger, 8-bit windows. */
+int b200_g1_lincomb(const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t out[18]);
+/* Device batch MulG1: out[i] = scalars[i] * points[i] (the loop at fk20_single.go:72-74). */
+int b200_g1_mul_many(const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t* out);
+
+/* ------------------------------------------------------------------ FFTSettings ------------ */
+int b200_fft_settings_new(uint8_t max_scale, b200_fs** out);  /* fft.go:44-61 NewFFTSettings */
+void b200_fft_settings_free(b200_fs* fs);
+uint64_t b200_fs_max_width(const b200_fs* fs);
+/* ExpandedRootsOfUnity (reverse == 0) or ReverseRootsOfUnity: max_width + 1 entries (fft.go:21-32) */
+int b200_fs_roots(const b200_fs* fs, int reverse, uint64_t* out);
+
+/* fft_fr.go:55-74 FFT: n <= MaxWidth values, zero-padded to the next power of two;
+ * out holds next_pow2(n) entries, natural order in and out. */
+int b200_fft_fr(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out);
+/* `batch` independent transforms of identical length n (contiguous). */
+int b200_fft_fr_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out);
+/* fft_g1.go:58-94 FFTG1: n must be a power of two <= MaxWidth. */
+int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out);
+int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out);
+/* das_extension.go:71-84 DASFFTExtension: in place; requires 2 n <= MaxWidth (and, as in the
+ * reference, is only meaningful for MaxWidth == 2 n). */
+int b200_das_fft_extension(b200_fs* fs, uint64_t* vals, size_t n);
+int b200_das_fft_extension_batch(b200_fs* fs, uint64_t* vals, size_t n, size_t batch);
+/* zero_poly.go:116-217 ZeroPolyViaMultiplication -> (zeroEval[length], zeroPoly[length]) */
+int b200_zero_poly_via_multiplication(b200_fs* fs, const uint64_t* missing_indices, size_t n_missing, size_t length,
+                                      uint64_t* zero_eval, uint64_t* zero_poly);
+/* recover_from_samples.go:42-109 RecoverPolyFromSamples with ZeroPolyViaMultiplication;
+ * samples is []*bls.Fr flattened by the shim: present[i] == 0 <=> samples[i] == nil. */
+int b200_recover_poly_from_samples(b200_fs* fs, const uint64_t* samples, const uint8_t* present, size_t n, uint64_t* out);
+int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t* samples, const uint8_t* present, size_t n,
+                                         size_t batch, uint64_t* out);
+
+/* ------------------------------------------------------------------ KZGSettings ------------ */
+/* kzg.go:21-36 NewKZGSettings: n_g1 != n_g2 -> LEN_MISMATCH; n_g1 < MaxWidth -> TOO_SMALL.
+ * The G2 half stays on the caller's CPU backend (verification only); only its length is checked. */
+int b200_kzg_settings_new(b200_fs* fs, const uint64_t* secret_g1, size_t n_g1, size_t n_g2, b200_ks** out);
+void b200_kzg_settings_free(b200_ks* ks);
+/* kzg_single_proofs.go:17-19 CommitToPoly = LinCombG1(SecretG1[:n], coeffs) */
+int b200_commit_to_poly(b200_ks* ks, const uint64_t* coeffs, size_t n, uint64_t out[18]);
+int b200_commit_to_poly_batch(b200_ks* ks, const uint64_t* coeffs, size_t n, size_t batch, uint64_t* out);
+
+/* ------------------------------------------------------------------ FK20 ------------------- */
+/* kzg.go:43-64 NewFK20SingleSettings(ks, n2) */
+int b200_fk20_single_settings_new(b200_ks* ks, size_t n2, b200_fk** out);
+/* kzg.go:73-116 NewFK20MultiSettings(ks, n2, chunkLen) */
+int b200_fk20_multi_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out);
+void b200_fk20_settings_free(b200_fk* fk);
+/* copy of xExtFFT (file `file`, n2 / chunk_len points) -- for tests */
+int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out);
+/* fk20_single.go:122-134 FK20Single: n coefficients -> n proofs, natural order */
+int b200_fk20_single(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proofs);
+/* fk20_single.go:139-172 FK20SingleDAOptimized: n2 coefficients with zero upper half -> n2 proofs */
+int b200_fk20_single_da_optimized(b200_fk* fk, const uint64_t* poly, size_t n2, uint64_t* proofs);
+/* fk20_single.go:176-196 DAUsingFK20: n coefficients -> 2n proofs in reverse bit order */
+int b200_da_using_fk20(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proofs);
+/* fk20_multi.go:58-109 FK20MultiDAOptimized: n2 coefficients (upper half zero) -> 2k proofs */
+int b200_fk20_multi_da_optimized(b200_fk* fk, const uint64_t* poly, size_t n2, uint64_t* proofs);
+/* fk20_multi.go:113-133 DAUsingFK20Multi: n coefficients -> 2k proofs in reverse bit order */
+int b200_da_using_fk20_multi(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proofs);
+
+/* Headline unit of work, batched: for each of `batch` polynomials of n coefficients,
+ * commitment = CommitToPoly(poly) and proofs = FK20Single(poly).  Host buffers; the copies
+ * are inside the call. */
+int b200_commit_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint64_t* commitments,
+                           uint64_t* proofs);
+/* Same with DEVICE buffers (inputs resident in HBM), asynchronous on `cuda_stream`
+ * (a cudaStream_t, may be NULL for the default stream). */
+int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments,
+                               void* d_proofs, void* cuda_stream);
+/* Number of kernels the last batch call on this handle launched (bench.py gpu_launches). */
+uint64_t b200_fk20_last_launch_count(const b200_fk* fk);
+
+/* Self-test hooks (tests/): run the device field/curve primitives against the portable
+ * host forms on `n` pseudo-random operands; returns the mismatch count in *mismatches. */
+int b200_selftest_field(size_t n, uint64_t seed, uint64_t* mismatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_KZG_H */
