@@ -1,0 +1,56 @@
+"""Builds libb200kzg.so (hand-written sm_100a CUDA + the C ABI of include/b200_kzg.h) in-tree.
+
+nvcc cross-compiles without a GPU; the three translation units compile in parallel.  The built
+library lands in go_kzg_b200/lib/ (git-ignored, but it travels to the GPU box with gpurun)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "lib", "obj")
+LIB = os.path.join(HERE, "lib", "libb200kzg.so")
+UNITS = ["api.cu", "kernels_fr.cu", "kernels_g1.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+
+
+def _deps():
+    out = []
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".cu", ".cuh", ".h")):
+                out.append(os.path.join(root, f))
+    return out
+
+
+def _compile(unit: str, verbose: bool) -> str:
+    obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+    cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, unit), "-o", obj]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed on " + unit)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    newest = max(os.path.getmtime(p) for p in _deps())
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(lambda u: _compile(u, verbose), UNITS))
+    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,734 @@
+// api.cu -- the C ABI of libb200kzg.so (include/b200_kzg.h): handles, host-side level-1
+// operations of package bls, and the orchestration of the device pipelines (Fr NTT, G1 FFT,
+// LinCombG1, FK20 single / multi).  Every compute entry point runs on the GPU; there is no CPU
+// fallback (a missing device is an error).
+#include <cuda_runtime.h>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+#include "../../include/b200_kzg.h"
+#include "hostutil.cuh"
+#include "kernels.h"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_cuda_err;
+static thread_local int g_device = 0;
+
+#define CK(expr)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e__);             \
+            return e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? B200_ERR_NO_DEVICE : B200_ERR_CUDA; \
+        }                                                                                 \
+    } while (0)
+#define CKS(expr)                       \
+    do {                                \
+        int s__ = (expr);               \
+        if (s__ != B200_OK) return s__; \
+    } while (0)
+
+extern "C" const char* b200_strerror(int status) {
+    switch (status) {
+        case B200_OK: return "ok";
+        case B200_ERR_TOO_LARGE: return "more values than roots of unity";
+        case B200_ERR_NOT_POW2: return "not a power of two";
+        case B200_ERR_LEN_MISMATCH: return "length mismatch";
+        case B200_ERR_BAD_INPUT: return "bad input";
+        case B200_ERR_CUDA: return "CUDA error";
+        case B200_ERR_NO_DEVICE: return "no CUDA device";
+        case B200_ERR_TOO_SMALL: return "too small";
+        case B200_ERR_RECOVERY: return "recovered data does not match the known samples";
+        case B200_ERR_ZERO_EVAL: return "bad zero eval";
+    }
+    return "unknown status";
+}
+extern "C" const char* b200_last_cuda_error(void) { return g_cuda_err.c_str(); }
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int b200_set_device(int device) {
+    int n = b200_device_count();
+    if (n == 0) return B200_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return B200_ERR_BAD_INPUT;
+    g_device = device;
+    return B200_OK;
+}
+
+// sticky-error-free check after a batch of launches
+static int check_launches() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_cuda_err = std::string("kernel launch: ") + cudaGetErrorString(e); return B200_ERR_CUDA; }
+    return B200_OK;
+}
+
+// RAII stream-ordered device buffer
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        if (bytes == 0) bytes = 16;
+        CK(cudaMallocAsync(&p, bytes, s));
+        return B200_OK;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline bool is_pow2(uint64_t v) { return v && !(v & (v - 1)); }   // bls/globals.go:72
+static inline unsigned log2u(uint64_t v) { unsigned l = 0; while (((uint64_t)1 << l) < v) l++; return l; }
+static inline uint64_t next_pow2(uint64_t v) { if (v == 0) return 1; return (uint64_t)1 << log2u(v); }   // fft.go:11-16
+
+// ------------------------------------------------------------------------------ level 1 (host)
+extern "C" void b200_fr_add(uint64_t* dst, const uint64_t* a, const uint64_t* b) { fr_store_canon(dst, fe_add(fr_load_canon(a), fr_load_canon(b))); }
+extern "C" void b200_fr_sub(uint64_t* dst, const uint64_t* a, const uint64_t* b) { fr_store_canon(dst, fe_sub(fr_load_canon(a), fr_load_canon(b))); }
+extern "C" void b200_fr_mul(uint64_t* dst, const uint64_t* a, const uint64_t* b) {
+    // canonical x canonical: (a R)(b) / R = a b
+    fr_store_canon(dst, fe_mul(fe_to_mont(fr_load_canon(a)), fr_load_canon(b)));
+}
+extern "C" void b200_fr_inv(uint64_t* dst, const uint64_t* a) { fr_to_abi_from_mont(dst, fe_inv(fr_from_abi_mont(a))); }
+extern "C" void b200_fr_div(uint64_t* dst, const uint64_t* a, const uint64_t* b) {   // bls/bignum_kilic.go:103-107
+    Fr bi = fe_inv(fr_from_abi_mont(b));
+    fr_store_canon(dst, fe_mul(bi, fr_load_canon(a)));
+}
+extern "C" void b200_fr_batch_inv(uint64_t* vals, size_t n) {   // Montgomery's trick; zeros stay zero
+    if (!n) return;
+    std::vector<Fr> v(n), pre(n);
+    Fr acc = Fr::one();
+    for (size_t i = 0; i < n; i++) {
+        v[i] = fr_from_abi_mont(vals + 4 * i);
+        pre[i] = acc;
+        if (!v[i].is_zero()) acc = fe_mul(acc, v[i]);
+    }
+    acc = fe_inv(acc);
+    for (size_t i = n; i-- > 0;) {
+        if (v[i].is_zero()) { fr_store_canon(vals + 4 * i, Fr::zero()); continue; }
+        Fr inv = fe_mul(acc, pre[i]);
+        acc = fe_mul(acc, v[i]);
+        fr_to_abi_from_mont(vals + 4 * i, inv);
+    }
+}
+extern "C" int b200_fr_valid(const uint8_t* le32) {
+    uint64_t l[4];
+    memcpy(l, le32, 32);
+    return fr_canon_valid(l) ? 1 : 0;
+}
+extern "C" void b200_fr_root_of_unity(unsigned scale, uint64_t* out) {
+    if (scale > 31) { memset(out, 0, 32); return; }
+    fr_store_canon(out, fr_scale2_root_canon(scale));
+}
+extern "C" void b200_g1_generator(uint64_t* out) { g1_to_abi(out, g1_generator()); }
+extern "C" void b200_g1_add(uint64_t* dst, const uint64_t* a, const uint64_t* b) { g1_to_abi(dst, g1_add(g1_from_abi(a), g1_from_abi(b))); }
+extern "C" void b200_g1_sub(uint64_t* dst, const uint64_t* a, const uint64_t* b) { g1_to_abi(dst, g1_sub(g1_from_abi(a), g1_from_abi(b))); }
+extern "C" void b200_g1_neg(uint64_t* dst) { g1_to_abi(dst, g1_neg(g1_from_abi(dst))); }
+extern "C" void b200_g1_mul(uint64_t* dst, const uint64_t* a, const uint64_t* k) {
+    Fr s = fr_load_canon(k);
+    g1_to_abi(dst, g1_mul_simple(g1_from_abi(a), s.l));
+}
+extern "C" int b200_g1_equal(const uint64_t* a, const uint64_t* b) { return g1_equal(g1_from_abi(a), g1_from_abi(b)) ? 1 : 0; }
+extern "C" void b200_g1_to_compressed(uint8_t* out, const uint64_t* p) { g1_compress(out, g1_from_abi(p)); }
+extern "C" int b200_g1_from_compressed(uint64_t* out, const uint8_t* in) {
+    G1J p;
+    int rc = g1_decompress(p, in);
+    if (rc) return B200_ERR_BAD_INPUT;
+    g1_to_abi(out, p);
+    return B200_OK;
+}
+extern "C" void b200_g1_to_compressed_many(uint8_t* out, const uint64_t* pts, size_t n) {
+    for (size_t i = 0; i < n; i++) b200_g1_to_compressed(out + 48 * i, pts + 18 * i);
+}
+extern "C" int b200_g1_from_compressed_many(uint64_t* out, const uint8_t* in, size_t n) {
+    for (size_t i = 0; i < n; i++) CKS(b200_g1_from_compressed(out + 18 * i, in + 48 * i));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------ FFTSettings
+struct b200_fs {
+    int device = 0;
+    unsigned max_scale = 0;
+    uint64_t max_width = 0;
+    std::vector<Fr> h_expanded;   // Montgomery, max_width + 1
+    FrDomain dom;
+    std::mutex mu;
+    // twiddle programs for the G1 FFT: [inverse][mode], max_width / 2 entries each, built lazily
+    ScalarProgram* progs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+};
+
+static Fr fr_inv_of_u64(uint64_t v) { return fe_inv(fr_from_u64(v)); }   // Montgomery in, Montgomery out
+
+extern "C" int b200_fft_settings_new(uint8_t max_scale, b200_fs** out) {
+    *out = nullptr;
+    if (max_scale > 31) return B200_ERR_TOO_LARGE;
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    CK(cudaSetDevice(g_device));
+    b200_fs* fs = new (std::nothrow) b200_fs();
+    if (!fs) return B200_ERR_CUDA;
+    fs->device = g_device;
+    fs->max_scale = max_scale;
+    fs->max_width = (uint64_t)1 << max_scale;
+    const uint64_t W = fs->max_width;
+    // fft.go:21-32 expandRootOfUnity: 1, w, w^2, ..., w^W = 1
+    Fr w = fe_to_mont(fr_scale2_root_canon(max_scale));
+    fs->h_expanded.resize(W + 1);
+    fs->h_expanded[0] = Fr::one();
+    for (uint64_t i = 1; i <= W; i++) fs->h_expanded[i] = fe_mul(fs->h_expanded[i - 1], w);
+    std::vector<Fr> rev(W + 1), twf(W ? W : 1), twi(W ? W : 1);
+    for (uint64_t i = 0; i <= W; i++) rev[i] = fs->h_expanded[W - i];
+    twf[0] = twi[0] = Fr::one();
+    for (uint64_t n = 2; n <= W; n <<= 1) {
+        uint64_t stride = W / n;
+        for (uint64_t j = 0; j < n / 2; j++) {
+            twf[n / 2 + j] = fs->h_expanded[j * stride];
+            twi[n / 2 + j] = rev[j * stride];
+        }
+    }
+    FrDomain& d = fs->dom;
+    d.max_scale = max_scale; d.max_width = W;
+    auto up = [&](Fr** dst, const std::vector<Fr>& src) -> int {
+        CK(cudaMalloc(dst, src.size() * sizeof(Fr)));
+        CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Fr), cudaMemcpyHostToDevice));
+        return B200_OK;
+    };
+    int rc = up(&d.expanded, fs->h_expanded);
+    if (!rc) rc = up(&d.reverse, rev);
+    if (!rc) rc = up(&d.tw_fwd, twf);
+    if (!rc) rc = up(&d.tw_inv, twi);
+    if (rc) { b200_fft_settings_free(fs); return rc; }
+    *out = fs;
+    return B200_OK;
+}
+extern "C" void b200_fft_settings_free(b200_fs* fs) {
+    if (!fs) return;
+    cudaSetDevice(fs->device);
+    cudaFree(fs->dom.expanded); cudaFree(fs->dom.reverse); cudaFree(fs->dom.tw_fwd); cudaFree(fs->dom.tw_inv);
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) cudaFree(fs->progs[a][b]);
+    delete fs;
+}
+extern "C" uint64_t b200_fs_max_width(const b200_fs* fs) { return fs->max_width; }
+extern "C" int b200_fs_roots(const b200_fs* fs, int reverse, uint64_t* out) {
+    const uint64_t W = fs->max_width;
+    for (uint64_t i = 0; i <= W; i++) fr_to_abi_from_mont(out + 4 * i, fs->h_expanded[reverse ? W - i : i]);
+    return B200_OK;
+}
+
+// twiddle programs w^(+-j), j < max_width / 2, in the given recoding mode
+static int fs_programs(b200_fs* fs, int inverse, int mode, const ScalarProgram** out) {
+    std::lock_guard<std::mutex> lk(fs->mu);
+    if (!fs->progs[inverse][mode]) {
+        const uint64_t W = fs->max_width, half = W / 2 ? W / 2 : 1;
+        std::vector<ScalarProgram> h(half);
+        for (uint64_t j = 0; j < half; j++) {
+            Fr k = fe_from_mont(fs->h_expanded[inverse ? (W - j) % (W ? W : 1) : j]);
+            if (W == 0) k = fe_from_mont(Fr::one());
+            make_scalar_program(&h[j], k, mode);
+        }
+        ScalarProgram* d = nullptr;
+        CK(cudaMalloc(&d, half * sizeof(ScalarProgram)));
+        CK(cudaMemcpy(d, h.data(), half * sizeof(ScalarProgram), cudaMemcpyHostToDevice));
+        fs->progs[inverse][mode] = d;
+    }
+    *out = fs->progs[inverse][mode];
+    return B200_OK;
+}
+// lanes of a warp share the twiddle when the batch fills whole warps -> sparse (wNAF) recoding
+static inline int program_mode_for_batch(size_t batch) { return batch % 32 == 0 ? 1 : 0; }
+
+// ------------------------------------------------------------------------------ Fr FFT
+static int dev_fr_fft(b200_fs* fs, const Fr* d_in, Fr* d_out, unsigned logn, size_t batch, bool inverse, cudaStream_t st) {
+    DevBuf tmp;
+    if (logn > 12) CKS(tmp.alloc(((size_t)batch << logn) * sizeof(Fr), st));
+    Fr scale;
+    if (inverse) scale = fr_inv_of_u64((uint64_t)1 << logn);
+    launch_fr_ntt(fs->dom, d_in, d_out, tmp.as<Fr>(), logn, batch, inverse, inverse ? &scale : nullptr, st);
+    return check_launches();
+}
+
+extern "C" int b200_fft_fr_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out) {
+    if (n > fs->max_width) return B200_ERR_TOO_LARGE;              // fft_fr.go:57-59
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fs->device));
+    const uint64_t np = next_pow2(n);                              // fft_fr.go:60
+    const unsigned logn = log2u(np);
+    cudaStream_t st = nullptr;
+    DevBuf raw, buf;
+    CKS(raw.alloc(batch * np * 32, st));
+    CKS(buf.alloc(batch * np * sizeof(Fr), st));
+    if (np != n) CK(cudaMemsetAsync(raw.p, 0, batch * np * 32, st));   // zero padding fft_fr.go:66-68
+    if (n) CK(cudaMemcpy2DAsync(raw.p, np * 32, vals, n * 32, n * 32, batch, cudaMemcpyHostToDevice, st));
+    launch_fr_to_mont(raw.as<uint64_t>(), buf.as<Fr>(), batch * np, st);
+    CKS(dev_fr_fft(fs, buf.as<Fr>(), buf.as<Fr>(), logn, batch, inverse != 0, st));
+    launch_fr_from_mont(buf.as<Fr>(), raw.as<uint64_t>(), batch * np, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, batch * np * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+extern "C" int b200_fft_fr(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out) {
+    return b200_fft_fr_batch(fs, vals, n, 1, inverse, out);
+}
+
+// ------------------------------------------------------------------------------ DAS extension
+extern "C" int b200_das_fft_extension_batch(b200_fs* fs, uint64_t* vals, size_t n, size_t batch) {
+    if (n * 2 > fs->max_width) return B200_ERR_TOO_SMALL;   // das_extension.go:72-74
+    if (n < 2 || !is_pow2(n)) return B200_ERR_BAD_INPUT;    // das_extension.go:22-24 "bad usage"
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fs->device));
+    cudaStream_t st = nullptr;
+    DevBuf raw, buf;
+    CKS(raw.alloc(batch * n * 32, st)); CKS(buf.alloc(batch * n * sizeof(Fr), st));
+    CK(cudaMemcpyAsync(raw.p, vals, batch * n * 32, cudaMemcpyHostToDevice, st));
+    launch_fr_to_mont(raw.as<uint64_t>(), buf.as<Fr>(), batch * n, st);
+    launch_das_fft_extension(fs->dom, buf.as<Fr>(), log2u(n), batch, fr_inv_of_u64(n), st);
+    launch_fr_from_mont(buf.as<Fr>(), raw.as<uint64_t>(), batch * n, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(vals, raw.p, batch * n * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+extern "C" int b200_das_fft_extension(b200_fs* fs, uint64_t* vals, size_t n) { return b200_das_fft_extension_batch(fs, vals, n, 1); }
+
+// ------------------------------------------------------------------------------ recovery (next milestone)
+extern "C" int b200_zero_poly_via_multiplication(b200_fs*, const uint64_t*, size_t, size_t, uint64_t*, uint64_t*) {
+    g_cuda_err = "ZeroPolyViaMultiplication: device path not built yet";
+    return B200_ERR_CUDA;
+}
+extern "C" int b200_recover_poly_from_samples_batch(b200_fs*, const uint64_t*, const uint8_t*, size_t, size_t, uint64_t*) {
+    g_cuda_err = "RecoverPolyFromSamples: device path not built yet";
+    return B200_ERR_CUDA;
+}
+extern "C" int b200_recover_poly_from_samples(b200_fs* fs, const uint64_t* s, const uint8_t* p, size_t n, uint64_t* out) {
+    return b200_recover_poly_from_samples_batch(fs, s, p, n, 1, out);
+}
+
+// ------------------------------------------------------------------------------ G1 FFT
+// In-place transform of `batch` vectors of n = 2^logn points (element i of blob b at
+// data[b * bstride + i * estride]).  dif: natural order in, bit-reversed out; otherwise (DIT)
+// bit-reversed in, natural out.  No 1/n scaling here.
+static int dev_g1_fft_stages(b200_fs* fs, G1J* data, unsigned logn, size_t batch, size_t estride, size_t bstride,
+                             bool inverse, bool dif, cudaStream_t st) {
+    if (logn == 0) return B200_OK;
+    const ScalarProgram* progs;
+    CKS(fs_programs(fs, inverse ? 1 : 0, program_mode_for_batch(batch), &progs));
+    const size_t n = (size_t)1 << logn, halfw = fs->max_width / 2;
+    if (dif) {
+        for (size_t m = n / 2; m >= 1; m >>= 1)
+            launch_g1_fft_stage(data, n / 2, batch, m, estride, bstride, true, progs, halfw / m, st);
+    } else {
+        for (size_t m = 1; m <= n / 2; m <<= 1)
+            launch_g1_fft_stage(data, n / 2, batch, m, estride, bstride, false, progs, halfw / m, st);
+    }
+    return check_launches();
+}
+
+extern "C" int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out) {
+    if (n > fs->max_width) return B200_ERR_TOO_LARGE;     // fft_g1.go:60-62
+    if (!is_pow2(n)) return B200_ERR_NOT_POW2;            // fft_g1.go:63-65
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fs->device));
+    const unsigned logn = log2u(n);
+    cudaStream_t st = nullptr;
+    DevBuf raw, buf;
+    CKS(raw.alloc(batch * n * 144, st));
+    CKS(buf.alloc(batch * n * sizeof(G1J), st));
+    CK(cudaMemcpyAsync(raw.p, vals, batch * n * 144, cudaMemcpyHostToDevice, st));
+    launch_g1_from_abi(raw.as<uint64_t>(), buf.as<G1J>(), batch * n, st);
+    CKS(dev_g1_fft_stages(fs, buf.as<G1J>(), logn, batch, 1, n, inverse != 0, true, st));
+    DevBuf prog;
+    if (inverse) {   // fft_g1.go:81-84: every output times n^-1
+        ScalarProgram sp;
+        make_scalar_program(&sp, fe_from_mont(fr_inv_of_u64(n)), 1);
+        CKS(prog.alloc(sizeof(ScalarProgram), st));
+        CK(cudaMemcpyAsync(prog.p, &sp, sizeof sp, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // sp lives on this stack frame
+        launch_g1_mul_programs(buf.as<G1J>(), n, batch, 1, n, prog.as<ScalarProgram>(), 0, 0, logn, st);
+    }
+    launch_g1_to_abi(buf.as<G1J>(), raw.as<uint64_t>(), n, batch, 1, n, 1, logn, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, batch * n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+extern "C" int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out) {
+    return b200_fft_g1_batch(fs, vals, n, 1, inverse, out);
+}
+
+// ------------------------------------------------------------------------------ LinCombG1
+// sum_i k[b][i] * pts[i] for each blob b: per-term scalar multiplication, then a fold tree.
+// d_k canonical ([batch][n]); result of blob b is left at work[b * n].
+static int dev_lincomb(const G1J* d_pts, size_t pts_bstride, const Fr* d_k, int k_is_mont, G1J* work, size_t n,
+                       size_t batch, cudaStream_t st) {
+    launch_g1_mul_var(d_pts, pts_bstride, d_k, k_is_mont, work, n, n, batch, st);
+    for (size_t cnt = n; cnt > 1;) {
+        size_t half = (cnt + 1) / 2;
+        launch_g1_fold(work, n, half, cnt, batch, st);
+        cnt = half;
+    }
+    return check_launches();
+}
+
+extern "C" int b200_g1_lincomb(const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t* out) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    if (n == 0) { memset(out, 0, 144); return B200_OK; }     // bls/bls_test.go:69-77: empty sum is infinity
+    CK(cudaSetDevice(g_device));
+    cudaStream_t st = nullptr;
+    DevBuf raw, pts, k, work;
+    CKS(raw.alloc(n * 144, st)); CKS(pts.alloc(n * sizeof(G1J), st)); CKS(k.alloc(n * 32, st)); CKS(work.alloc(n * sizeof(G1J), st));
+    CK(cudaMemcpyAsync(raw.p, points, n * 144, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    launch_g1_from_abi(raw.as<uint64_t>(), pts.as<G1J>(), n, st);
+    CKS(dev_lincomb(pts.as<G1J>(), 0, k.as<Fr>(), 0, work.as<G1J>(), n, 1, st));
+    launch_g1_to_abi(work.as<G1J>(), raw.as<uint64_t>(), 1, 1, 1, n, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_g1_mul_many(const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t* out) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    if (n == 0) return B200_OK;
+    CK(cudaSetDevice(g_device));
+    cudaStream_t st = nullptr;
+    DevBuf raw, pts, k;
+    CKS(raw.alloc(n * 144, st)); CKS(pts.alloc(n * sizeof(G1J), st)); CKS(k.alloc(n * 32, st));
+    CK(cudaMemcpyAsync(raw.p, points, n * 144, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    launch_g1_from_abi(raw.as<uint64_t>(), pts.as<G1J>(), n, st);
+    // batch = n, one element each: per-lane scalars
+    launch_g1_mul_var(pts.as<G1J>(), 1, k.as<Fr>(), 0, pts.as<G1J>(), 1, 1, n, st);
+    launch_g1_to_abi(pts.as<G1J>(), raw.as<uint64_t>(), n, 1, 1, n, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------ KZGSettings
+struct b200_ks {
+    b200_fs* fs = nullptr;
+    size_t n_g1 = 0;
+    G1J* d_secret_g1 = nullptr;   // Montgomery Jacobian
+};
+
+extern "C" int b200_kzg_settings_new(b200_fs* fs, const uint64_t* secret_g1, size_t n_g1, size_t n_g2, b200_ks** out) {
+    *out = nullptr;
+    if (n_g1 != n_g2) return B200_ERR_LEN_MISMATCH;      // kzg.go:22-24
+    if (n_g1 < fs->max_width) return B200_ERR_TOO_SMALL;  // kzg.go:25-27
+    CK(cudaSetDevice(fs->device));
+    b200_ks* ks = new (std::nothrow) b200_ks();
+    if (!ks) return B200_ERR_CUDA;
+    ks->fs = fs; ks->n_g1 = n_g1;
+    cudaStream_t st = nullptr;
+    DevBuf raw;
+    int rc = raw.alloc(n_g1 * 144, st);
+    if (!rc && cudaMalloc(&ks->d_secret_g1, (n_g1 ? n_g1 : 1) * sizeof(G1J)) != cudaSuccess) rc = B200_ERR_CUDA;
+    if (rc) { delete ks; return rc; }
+    if (n_g1) {
+        cudaMemcpyAsync(raw.p, secret_g1, n_g1 * 144, cudaMemcpyHostToDevice, st);
+        launch_g1_from_abi(raw.as<uint64_t>(), ks->d_secret_g1, n_g1, st);
+    }
+    rc = check_launches();
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = B200_ERR_CUDA;
+    if (rc) { b200_kzg_settings_free(ks); return rc; }
+    *out = ks;
+    return B200_OK;
+}
+extern "C" void b200_kzg_settings_free(b200_ks* ks) {
+    if (!ks) return;
+    cudaSetDevice(ks->fs->device);
+    cudaFree(ks->d_secret_g1);
+    delete ks;
+}
+
+extern "C" int b200_commit_to_poly_batch(b200_ks* ks, const uint64_t* coeffs, size_t n, size_t batch, uint64_t* out) {
+    if (n > ks->n_g1) return B200_ERR_LEN_MISMATCH;   // SecretG1[:n] would panic (kzg_single_proofs.go:18)
+    if (batch == 0) return B200_OK;
+    if (n == 0) { memset(out, 0, batch * 144); return B200_OK; }
+    CK(cudaSetDevice(ks->fs->device));
+    cudaStream_t st = nullptr;
+    DevBuf k, work, res;
+    CKS(k.alloc(batch * n * 32, st)); CKS(work.alloc(batch * n * sizeof(G1J), st)); CKS(res.alloc(batch * 144, st));
+    CK(cudaMemcpyAsync(k.p, coeffs, batch * n * 32, cudaMemcpyHostToDevice, st));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st));
+    launch_g1_to_abi(work.as<G1J>(), res.as<uint64_t>(), 1, batch, 1, n, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, res.p, batch * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+extern "C" int b200_commit_to_poly(b200_ks* ks, const uint64_t* coeffs, size_t n, uint64_t* out) {
+    return b200_commit_to_poly_batch(ks, coeffs, n, 1, out);
+}
+
+// ------------------------------------------------------------------------------ FK20
+struct b200_fk {
+    b200_ks* ks = nullptr;
+    size_t n2 = 0, chunk_len = 1;
+    G1J* d_x_ext_fft = nullptr;   // [chunk_len][n2 / chunk_len], natural order (kzg.go:62,110-114)
+    unsigned long long last_launches = 0;
+};
+
+// kzg.go:43-64 / 73-116 + fk20_single.go:40-56 toeplitzPart1
+static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out) {
+    *out = nullptr;
+    b200_fs* fs = ks->fs;
+    if (n2 > fs->max_width) return B200_ERR_TOO_LARGE;       // kzg.go:44-46 / 74-76
+    if (!is_pow2(n2)) return B200_ERR_NOT_POW2;              // kzg.go:47-49 / 77-79
+    if (n2 < 2) return B200_ERR_TOO_SMALL;                   // kzg.go:50-52 / 80-82
+    if (chunk_len > n2 / 2) return B200_ERR_TOO_LARGE;       // kzg.go:83-85
+    if (!is_pow2(chunk_len)) return B200_ERR_NOT_POW2;       // kzg.go:86-91
+    CK(cudaSetDevice(fs->device));
+    const size_t n = n2 / 2, l = chunk_len, k = n / l, k2 = 2 * k;
+    const unsigned logk2 = log2u(k2);
+    b200_fk* fk = new (std::nothrow) b200_fk();
+    if (!fk) return B200_ERR_CUDA;
+    fk->ks = ks; fk->n2 = n2; fk->chunk_len = l;
+    cudaStream_t st = nullptr;
+    int rc = B200_OK;
+    do {
+        if (cudaMalloc(&fk->d_x_ext_fft, l * k2 * sizeof(G1J)) != cudaSuccess) { rc = B200_ERR_CUDA; break; }
+        DevBuf work;
+        if ((rc = work.alloc(l * k2 * sizeof(G1J), st))) break;
+        launch_g1_fill_infinity(work.as<G1J>(), l * k2, st);
+        // file `off`: x[i] = SecretG1[n - l - 1 - off - i l], i < k - 1; x[k-1 .. 2k-1] = infinity
+        launch_fk20_gather_x(ks->d_secret_g1, work.as<G1J>(), n, l, st);
+        // FFT_G1 of every file (forward), natural order result
+        if ((rc = dev_g1_fft_stages(fs, work.as<G1J>(), logk2, l, 1, k2, false, true, st))) break;
+        launch_g1_copy(fk->d_x_ext_fft, 1, k2, work.as<G1J>(), 1, k2, k2, l, 1, logk2, st);
+        if ((rc = check_launches())) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "sync in fk20 settings"; rc = B200_ERR_CUDA; break; }
+    } while (0);
+    if (rc) { b200_fk20_settings_free(fk); return rc; }
+    *out = fk;
+    return B200_OK;
+}
+extern "C" int b200_fk20_single_settings_new(b200_ks* ks, size_t n2, b200_fk** out) { return fk20_settings_new(ks, n2, 1, out); }
+extern "C" int b200_fk20_multi_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out) {
+    if (chunk_len < 1) { *out = nullptr; return B200_ERR_TOO_SMALL; }   // kzg.go:89-91
+    return fk20_settings_new(ks, n2, chunk_len, out);
+}
+extern "C" void b200_fk20_settings_free(b200_fk* fk) {
+    if (!fk) return;
+    cudaSetDevice(fk->ks->fs->device);
+    cudaFree(fk->d_x_ext_fft);
+    delete fk;
+}
+extern "C" int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out) {
+    if (file >= fk->chunk_len) return B200_ERR_BAD_INPUT;
+    CK(cudaSetDevice(fk->ks->fs->device));
+    const size_t k2 = fk->n2 / fk->chunk_len;
+    cudaStream_t st = nullptr;
+    DevBuf raw;
+    CKS(raw.alloc(k2 * 144, st));
+    launch_g1_to_abi(fk->d_x_ext_fft + file * k2, raw.as<uint64_t>(), k2, 1, 1, k2, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, k2 * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+extern "C" uint64_t b200_fk20_last_launch_count(const b200_fk* fk) { return fk->last_launches; }
+
+// The FK20 pipeline on device buffers, for `batch` polynomials of n coefficients (canonical):
+//   c      = toeplitz coefficients (per chunk offset)                      fk20_single.go:89-119
+//   c^     = NTT(c) / 2k            (the 1/2k of the later inverse G1 transform folded in here)
+//   hExt^  = sum over offsets of c^ (.) xExtFFT[offset]                     fk20_single.go:59-77, fk20_multi.go:80-91
+//   h      = IFFT_G1(hExt^)[:k]     decimation in frequency: natural in, bit-reversed out, so
+//                                   h[m] (m < k) lands on even slot 2 rev_k(m)
+//   proofs = FFT_G1(h)              (mode 0: k points, the even slots *are* the bit-reversed input of a DIT)
+//          | FFT_G1(h ++ 0^k)       (mode 1/2: 2k points; odd slots are cleared first)
+// mode 0: FK20Single (natural order); 1: *DAOptimized (natural order, 2k proofs); 2: DAUsing* (reverse bit order)
+static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch, int mode, uint64_t* d_proofs, cudaStream_t st) {
+    b200_fs* fs = fk->ks->fs;
+    const size_t l = fk->chunk_len, k = n / l, k2 = 2 * k;
+    const unsigned logk2 = log2u(k2);
+    DevBuf c, h, tmp;
+    CKS(c.alloc(batch * l * k2 * sizeof(Fr), st));
+    CKS(h.alloc(batch * l * k2 * sizeof(G1J), st));
+    if (l == 1) launch_toeplitz_coeffs(d_polys, c.as<Fr>(), n, batch, st);
+    else launch_toeplitz_coeffs_strided(d_polys, c.as<Fr>(), n, l, batch, st);
+    if (logk2 > 12) CKS(tmp.alloc(batch * l * k2 * sizeof(Fr), st));
+    Fr scale = fr_inv_of_u64(k2);
+    launch_fr_ntt(fs->dom, c.as<Fr>(), c.as<Fr>(), tmp.as<Fr>(), logk2, batch * l, false, &scale, st);
+    launch_g1_mul_var(fk->d_x_ext_fft, 0, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
+    for (size_t cnt = l; cnt > 1; cnt /= 2) launch_g1_fold(h.as<G1J>(), l * k2, (cnt / 2) * k2, cnt * k2, batch, st);
+    CKS(check_launches());
+    const size_t bstride = l * k2;
+    CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, true, true, st));
+    if (mode == 0) {
+        CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2 - 1, batch, 2, bstride, false, false, st));
+        launch_g1_to_abi(h.as<G1J>(), d_proofs, k, batch, 2, bstride, 0, 0, st);
+    } else {
+        // clear the odd slots (the discarded upper half of the inverse transform): h ++ 0^k
+        static G1J* d_inf = nullptr;   // one infinity element per process (never freed)
+        if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }
+        launch_g1_copy(h.as<G1J>() + 1, 2, bstride, d_inf, 0, 0, k, batch, 0, 0, st);
+        CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, false, false, st));
+        launch_g1_to_abi(h.as<G1J>(), d_proofs, k2, batch, 1, bstride, mode == 2 ? 1 : 0, logk2, st);
+    }
+    return check_launches();
+}
+
+// host-buffer front end shared by the five FK20 entry points
+static int host_fk20(b200_fk* fk, const uint64_t* poly, size_t n, int mode, uint64_t* proofs) {
+    CK(cudaSetDevice(fk->ks->fs->device));
+    const size_t n_out = mode == 0 ? n / fk->chunk_len : 2 * n / fk->chunk_len;
+    cudaStream_t st = nullptr;
+    DevBuf dp, dout;
+    CKS(dp.alloc(n * 32, st)); CKS(dout.alloc(n_out * 144, st));
+    CK(cudaMemcpyAsync(dp.p, poly, n * 32, cudaMemcpyHostToDevice, st));
+    unsigned long long before = g_launch_count;
+    CKS(dev_fk20(fk, dp.as<uint64_t>(), n, 1, mode, dout.as<uint64_t>(), st));
+    fk->last_launches = g_launch_count - before;
+    CK(cudaMemcpyAsync(proofs, dout.p, n_out * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+static bool upper_half_zero(const uint64_t* poly, size_t n2) {
+    for (size_t i = (n2 / 2) * 4; i < n2 * 4; i++) if (poly[i]) return false;
+    return true;
+}
+
+extern "C" int b200_fk20_single(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proofs) {
+    if (fk->chunk_len != 1) return B200_ERR_BAD_INPUT;
+    if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;   // fk20_single.go:60-62 (toeplitz coeffs vs xExtFFT)
+    return host_fk20(fk, poly, n, 0, proofs);
+}
+extern "C" int b200_fk20_single_da_optimized(b200_fk* fk, const uint64_t* poly, size_t n2, uint64_t* proofs) {
+    if (fk->chunk_len != 1) return B200_ERR_BAD_INPUT;
+    if (n2 > fk->ks->fs->max_width) return B200_ERR_TOO_LARGE;   // fk20_single.go:140-145
+    if (!is_pow2(n2)) return B200_ERR_NOT_POW2;                  // fk20_single.go:146-149
+    if (!upper_half_zero(poly, n2)) return B200_ERR_BAD_INPUT;   // fk20_single.go:150-154
+    if (n2 != fk->n2) return B200_ERR_LEN_MISMATCH;
+    return host_fk20(fk, poly, n2 / 2, 1, proofs);
+}
+extern "C" int b200_da_using_fk20(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proofs) {
+    if (fk->chunk_len != 1) return B200_ERR_BAD_INPUT;
+    if (n > fk->ks->fs->max_width / 2) return B200_ERR_TOO_LARGE;   // fk20_single.go:178-180
+    if (!is_pow2(n)) return B200_ERR_NOT_POW2;                      // fk20_single.go:181-183
+    if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
+    return host_fk20(fk, poly, n, 2, proofs);
+}
+extern "C" int b200_fk20_multi_da_optimized(b200_fk* fk, const uint64_t* poly, size_t n2, uint64_t* proofs) {
+    if (n2 > fk->ks->fs->max_width) return B200_ERR_TOO_LARGE;   // fk20_multi.go:60-63
+    if (!upper_half_zero(poly, n2)) return B200_ERR_BAD_INPUT;   // fk20_multi.go:65-69
+    if (n2 != fk->n2) return B200_ERR_LEN_MISMATCH;
+    return host_fk20(fk, poly, n2 / 2, 1, proofs);
+}
+extern "C" int b200_da_using_fk20_multi(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proofs) {
+    if (n > fk->ks->fs->max_width / 2) return B200_ERR_TOO_LARGE;   // fk20_multi.go:115-117
+    if (!is_pow2(n)) return B200_ERR_NOT_POW2;                      // fk20_multi.go:118-120
+    if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
+    return host_fk20(fk, poly, n, 2, proofs);
+}
+
+// ------------------------------------------------------------------------------ headline unit
+extern "C" int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments,
+                                          void* d_proofs, void* cuda_stream) {
+    if (fk->chunk_len != 1) return B200_ERR_BAD_INPUT;
+    if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
+    if (n > fk->ks->n_g1) return B200_ERR_LEN_MISMATCH;
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fk->ks->fs->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    unsigned long long before = g_launch_count;
+    {
+        DevBuf work;
+        CKS(work.alloc(batch * n * sizeof(G1J), st));
+        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st));
+        launch_g1_to_abi(work.as<G1J>(), (uint64_t*)d_commitments, 1, batch, 1, n, 0, 0, st);
+    }
+    CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 0, (uint64_t*)d_proofs, st));
+    fk->last_launches = g_launch_count - before;
+    return B200_OK;
+}
+extern "C" int b200_commit_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint64_t* commitments,
+                                      uint64_t* proofs) {
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fk->ks->fs->device));
+    cudaStream_t st = nullptr;
+    DevBuf dp, dc, dout;
+    CKS(dp.alloc(batch * n * 32, st)); CKS(dc.alloc(batch * 144, st)); CKS(dout.alloc(batch * n * 144, st));
+    CK(cudaMemcpyAsync(dp.p, polys, batch * n * 32, cudaMemcpyHostToDevice, st));
+    CKS(b200_commit_fk20_batch_dev(fk, dp.p, n, batch, dc.p, dout.p, st));
+    CK(cudaMemcpyAsync(commitments, dc.p, batch * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(proofs, dout.p, batch * n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------ profiling
+namespace b200 {
+bool g_prof_on = false;
+struct ProfRec { int cat; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof_recs;
+void prof_begin_event(int cat, cudaStream_t st) {
+    ProfRec r; r.cat = cat;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    g_prof_recs.push_back(r);
+}
+void prof_end_event(cudaStream_t st) { cudaEventRecord(g_prof_recs.back().e1, st); }
+}  // namespace b200
+extern "C" int b200_profile_begin(void) {
+    for (auto& r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof_recs.clear();
+    g_prof_on = true;
+    return B200_OK;
+}
+extern "C" int b200_profile_end(double* ms_per_class, uint64_t* launches_per_class) {
+    g_prof_on = false;
+    CK(cudaDeviceSynchronize());
+    for (int c = 0; c < PROF_NCAT; c++) { ms_per_class[c] = 0; launches_per_class[c] = 0; }
+    for (auto& r : g_prof_recs) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        ms_per_class[r.cat] += ms; launches_per_class[r.cat]++;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    g_prof_recs.clear();
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------ self test / probes
+extern "C" int b200_selftest_field(size_t n, uint64_t seed, uint64_t* mismatches) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    CK(cudaSetDevice(g_device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    CK(cudaMemset(d, 0, 8));
+    launch_selftest(n, seed, d, nullptr);
+    int rc = check_launches();
+    unsigned long long h = 0;
+    if (!rc && cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { g_cuda_err = cudaGetErrorString(cudaGetLastError()); rc = B200_ERR_CUDA; }
+    cudaFree(d);
+    *mismatches = h;
+    return rc;
+}
+// Fp multiplication throughput probe: `threads` lanes x `iters` x 2 dependent Montgomery products;
+// returns the elapsed milliseconds (integer-pipe roofline denominator for the G1 kernels).
+extern "C" int b200_probe_fp_mul(size_t threads, int iters, float* ms) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    CK(cudaSetDevice(g_device));
+    uint32_t* d = nullptr;
+    CK(cudaMalloc(&d, 128));
+    uint32_t h[32];
+    for (int i = 0; i < 32; i++) h[i] = 0x9E3779B9u * (i + 1);
+    CK(cudaMemcpy(d, h, 128, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    launch_fp_mul_probe(d, threads, 8, nullptr);   // warm-up
+    CK(cudaEventRecord(e0, nullptr));
+    launch_fp_mul_probe(d, threads, iters, nullptr);
+    CK(cudaEventRecord(e1, nullptr));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return check_launches();
+}

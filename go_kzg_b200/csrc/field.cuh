@@ -342,4 +342,28 @@ HD Fe<P> fe_inv(const Fe<P>& a) {
 typedef Fe<FpParams> Fp;
 typedef Fe<FrParams> Fr;
 
+#ifdef __CUDACC__
+// 16-byte vector load/store of field elements and points (all device arrays are 16 B aligned:
+// sizeof(Fr) = 32, sizeof(G1A) = 96, sizeof(G1J) = 144).
+template <class T>
+__device__ __forceinline__ T ld_vec(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16 B multiple");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void st_vec(T* p, const T& v) {
+    static_assert(sizeof(T) % 16 == 0, "16 B multiple");
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+#endif
+
 }  // namespace b200

@@ -132,65 +132,27 @@ HD bool g1_equal(const G1J& a, const G1J& b) {   // bls/bls_kilic.go:106 EqualG1
 // ---------------------------------------------------------------------------------------
 // scalar multiplication
 // ---------------------------------------------------------------------------------------
-// k * P, k canonical 8 x u32, fixed 4-bit windows (per-lane scalars: every lane executes the
-// same double/add schedule, only the table index differs).  Used for MulG1 with a
-// variable scalar (fk20_single.go:72-74 ToeplitzPart2, bls/bls_kilic.go:41).
-HD G1J g1_mul_window4(const G1J& p, const uint32_t* k) {
-    G1J tab[16];
-    tab[0] = G1J::infinity();
-    tab[1] = p;
-    for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? g1_add(tab[i - 1], p) : g1_dbl(tab[i >> 1]);
+// k * P by plain double-and-add, k canonical 8 x u32 (host level-1 API: bls/bls_kilic.go:41 MulG1).
+HD G1J g1_mul_simple(const G1J& p, const uint32_t* k) {
     G1J acc = G1J::infinity();
-    for (int w = 63; w >= 0; w--) {
-        if (w != 63) { acc = g1_dbl(acc); acc = g1_dbl(acc); acc = g1_dbl(acc); acc = g1_dbl(acc); }
-        uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
-        if (d) acc = g1_add(acc, tab[d]);
+    bool started = false;
+    for (int i = 255; i >= 0; i--) {
+        if (started) acc = g1_dbl(acc);
+        if ((k[i >> 5] >> (i & 31)) & 1u) { acc = started ? g1_add(acc, p) : p; started = true; }
     }
     return acc;
 }
 
-// Twiddle "program": a fixed scalar pre-split on the host as k = k1 + k2 z^2 (GLV) and
-// recoded in width-4 NAF (odd digits in [-7, 7]).  All lanes of a warp that share a twiddle
-// run the same schedule, so the digit tests are branch-uniform.
-#define B200_WNAF_LEN 132   // >= 129 digits per half scalar, padded
+// Scalar "program": a fixed scalar pre-split on the host as k = k1 + k2 z^2 (GLV) with both
+// halves recoded into signed digits indexed by bit position (see g1_dev.cuh for the two modes).
+#define B200_WNAF_LEN 132   // >= 130 digit positions per half scalar, padded to 4
 struct ScalarProgram {
-    int8_t d1[B200_WNAF_LEN];   // wNAF digits of k1, index = bit position
-    int8_t d2[B200_WNAF_LEN];   // wNAF digits of k2 (applied to the endomorphism image)
+    int8_t d1[B200_WNAF_LEN];   // digits of k1
+    int8_t d2[B200_WNAF_LEN];   // digits of k2 (applied to the endomorphism image)
     int16_t top;                // highest non-zero position (-1: scalar is zero)
-    int16_t is_one;             // scalar == 1 (skip the multiplication)
+    int8_t is_one;              // scalar == 1 (skip the multiplication)
+    int8_t mode;                // 0 fixed 4-bit windows, 1 width-5 NAF
     int16_t pad[2];
 };
-
-HD G1J g1_mul_program(const G1J& p, const ScalarProgram* prog) {
-    int top = prog->top;
-    if (top < 0 || p.is_inf()) return G1J::infinity();
-    if (prog->is_one) return p;
-    // odd multiples 1P, 3P, 5P, 7P
-    G1J tab[4];
-    tab[0] = p;
-    G1J p2 = g1_dbl(p);
-    tab[1] = g1_add(p2, p);
-    tab[2] = g1_add(tab[1], p2);
-    tab[3] = g1_add(tab[2], p2);
-    const Fp beta = fp_const_beta();
-    G1J acc = G1J::infinity();
-    for (int i = top; i >= 0; i--) {
-        acc = g1_dbl(acc);
-        int a = prog->d1[i];
-        if (a) {
-            G1J t = tab[(a < 0 ? -a : a) >> 1];
-            if (a < 0) t.y = fe_neg(t.y);
-            acc = g1_add(acc, t);
-        }
-        int b = prog->d2[i];
-        if (b) {
-            G1J t = tab[(b < 0 ? -b : b) >> 1];
-            t.x = fe_mul(t.x, beta);
-            if (b > 0) t.y = fe_neg(t.y);    // z^2 (x,y) = (beta x, -y)
-            acc = g1_add(acc, t);
-        }
-    }
-    return acc;
-}
 
 }  // namespace b200

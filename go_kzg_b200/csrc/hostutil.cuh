@@ -34,22 +34,33 @@ inline void g1_to_abi(uint64_t* p, const G1J& a) {
     memcpy(p, x.l, 48); memcpy(p + 6, y.l, 48); memcpy(p + 12, z.l, 48);
 }
 
-// ---- fixed-scalar recoding: k = k1 + k2 z^2, both halves in width-4 NAF -----------------
-inline void wnaf4_128(unsigned __int128 v, int8_t* out /* B200_WNAF_LEN */) {
+// ---- fixed-scalar recoding: k = k1 + k2 z^2, both halves as signed digit strings ----------
+// mode 1: width-5 NAF (odd digits in [-15, 15]); mode 0: fixed 4-bit signed windows.
+inline void wnaf5_128(unsigned __int128 v, int8_t* out /* B200_WNAF_LEN */) {
     memset(out, 0, B200_WNAF_LEN);
     int i = 0;
     while (v != 0) {
         int d = 0;
         if (v & 1) {
-            d = (int)(v & 15);
-            if (d >= 8) d -= 16;
+            d = (int)(v & 31);
+            if (d >= 16) d -= 32;
             if (d >= 0) v -= (unsigned)d; else v += (unsigned)(-d);
         }
         out[i++] = (int8_t)d;
         v >>= 1;
     }
 }
-inline void make_scalar_program(ScalarProgram* sp, const Fr& k_canon) {
+inline void window4_128(unsigned __int128 v, int8_t* out /* B200_WNAF_LEN */) {
+    memset(out, 0, B200_WNAF_LEN);
+    unsigned carry = 0;
+    for (int w = 0; w < 33; w++) {
+        unsigned d = (w < 32 ? (unsigned)((v >> (4 * w)) & 15) : 0u) + carry;
+        int dd;
+        if (d > 8) { dd = (int)d - 16; carry = 1; } else { dd = (int)d; carry = 0; }
+        out[4 * w] = (int8_t)dd;
+    }
+}
+inline void glv_split(const Fr& k_canon, unsigned __int128& k1, unsigned __int128& k2) {
     constexpr uint32_t z2l[4] = B200_GLV_Z2;
     unsigned __int128 z2 = 0;
     for (int i = 3; i >= 0; i--) z2 = (z2 << 32) | z2l[i];
@@ -60,14 +71,20 @@ inline void make_scalar_program(ScalarProgram* sp, const Fr& k_canon) {
         quo <<= 1;
         if (top || rem >= z2) { rem -= z2; quo |= 1; }
     }
-    wnaf4_128(rem, sp->d1);
-    wnaf4_128(quo, sp->d2);
+    k1 = rem; k2 = quo;
+}
+inline void make_scalar_program(ScalarProgram* sp, const Fr& k_canon, int mode) {
+    unsigned __int128 k1, k2;
+    glv_split(k_canon, k1, k2);
+    if (mode == 1) { wnaf5_128(k1, sp->d1); wnaf5_128(k2, sp->d2); }
+    else { window4_128(k1, sp->d1); window4_128(k2, sp->d2); }
     int top = -1;
     for (int i = 0; i < B200_WNAF_LEN; i++) if (sp->d1[i] || sp->d2[i]) top = i;
     sp->top = (int16_t)top;
     bool one = k_canon.l[0] == 1;
     for (int i = 1; i < 8; i++) one = one && k_canon.l[i] == 0;
     sp->is_one = one ? 1 : 0;
+    sp->mode = (int8_t)mode;
     sp->pad[0] = sp->pad[1] = 0;
 }
 

@@ -1,0 +1,92 @@
+// kernels.h -- launcher interface between the C-ABI translation unit (api.cu) and the kernel
+// translation units (kernels_fr.cu, kernels_g1.cu).  Internal; the public boundary is
+// include/b200_kzg.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "g1.cuh"
+
+namespace b200 {
+
+// every launcher bumps this (gpu_launches in bench.py)
+extern unsigned long long g_launch_count;
+
+// Optional per-kernel-class device timing (bench.py's roofline): when enabled, every launcher
+// brackets its launches with CUDA events on the launching stream.
+enum ProfCat { PROF_FR_NTT = 0, PROF_G1_FFT_STAGE, PROF_G1_MUL, PROF_G1_FOLD, PROF_MISC, PROF_NCAT };
+extern bool g_prof_on;
+void prof_begin_event(int cat, cudaStream_t st);
+void prof_end_event(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(int cat, cudaStream_t s) : st(s), on(g_prof_on) { if (on) prof_begin_event(cat, st); }
+    ~ProfScope() { if (on) prof_end_event(st); }
+};
+
+// ---------------------------------------------------------------- Fr
+// Device-side FFTSettings tables (fft.go:34-42), Montgomery form.
+struct FrDomain {
+    unsigned max_scale = 0;
+    uint64_t max_width = 0;
+    Fr* expanded = nullptr;   // [max_width + 1]  w^i
+    Fr* reverse = nullptr;    // [max_width + 1]  w^-i
+    // compact per-scale half tables: scale s (n = 2^s) lives at offset n/2, length n/2:
+    // tw_fwd[n/2 + j] = w_n^j, tw_inv[n/2 + j] = w_n^-j  (j < n/2); contiguous so one bulk copy
+    // stages a transform's twiddles in shared memory.
+    Fr* tw_fwd = nullptr;     // [max_width]
+    Fr* tw_inv = nullptr;     // [max_width]
+};
+
+void launch_fr_to_mont(const uint64_t* in_canon, Fr* out, size_t n, cudaStream_t st);
+void launch_fr_from_mont(const Fr* in, uint64_t* out_canon, size_t n, cudaStream_t st);
+// out[b][i] = scale * NTT(in[b][:])[i]; natural order in and out; n = 2^logn <= max_width; tmp
+// holds batch * n elements (used when the transform takes two passes); in may equal out.
+// `scale` (Montgomery) is multiplied into every output (n^-1 for the inverse transform).
+void launch_fr_ntt(const FrDomain& dom, const Fr* in, Fr* out, Fr* tmp, unsigned logn, size_t batch, bool inverse,
+                   const Fr* scale_or_null, cudaStream_t st);
+// das_extension.go:71-84 in place on Montgomery values [batch][2^logn]; inv_n = (2^logn)^-1 (Montgomery)
+void launch_das_fft_extension(const FrDomain& dom, Fr* vals, unsigned logn, size_t batch, const Fr& inv_n, cudaStream_t st);
+// fk20_single.go:106-119 toeplitzCoeffsStep over a batch: poly[b][n] canonical -> out[b][2n] Montgomery
+void launch_toeplitz_coeffs(const uint64_t* polys_canon, Fr* out, size_t n, size_t batch, cudaStream_t st);
+// fk20_single.go:89-103 toeplitzCoeffsStepStrided for every offset: out[b][off][2k] Montgomery
+void launch_toeplitz_coeffs_strided(const uint64_t* polys_canon, Fr* out, size_t n, size_t chunk_len, size_t batch,
+                                    cudaStream_t st);
+// pointwise helpers on Montgomery arrays
+void launch_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n, cudaStream_t st);   // dst = a * b
+
+// ---------------------------------------------------------------- G1
+void launch_g1_from_abi(const uint64_t* in, G1J* out, size_t n, cudaStream_t st);
+// out[b * n + i] = in[b * bstride + idx(i) * estride], idx = bit reversal over logn bits if bitrev
+void launch_g1_to_abi(const G1J* in, uint64_t* out, size_t n, size_t batch, size_t estride, size_t bstride, int bitrev,
+                      unsigned logn, cudaStream_t st);
+void launch_g1_fill_infinity(G1J* p, size_t n, cudaStream_t st);
+// one radix-2 stage over batch transforms of 2 * n_half points each; element i of blob b lives at
+// data[b * bstride + i * estride]; m = half block length of this stage.  DIT: (x0 + w x1, x0 - w x1),
+// DIF: (x0 + x1, w (x0 - x1)), w = progs[j * prog_stride] for position j inside the block.
+void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
+                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st);
+// out[b * out_bstride + i] = k[b * n + i] * pts[b * pts_bstride + i]   (pts_bstride = 0: shared bases)
+void launch_g1_mul_var(const G1J* pts, size_t pts_bstride, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride,
+                       size_t n, size_t batch, cudaStream_t st);
+// out[b * bstride + i * estride] = progs[idx(i) * prog_stride] * same element (in place)
+void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,
+                            const ScalarProgram* progs, size_t prog_stride, int bitrev, unsigned logn, cudaStream_t st);
+// data[b * bstride + i] += data[b * bstride + i + half]  for i < cnt - half
+void launch_g1_fold(G1J* data, size_t bstride, size_t half, size_t cnt, size_t batch, cudaStream_t st);
+// dst[b*dst_bstride + i*dst_estride] += src[b*src_bstride + i*src_estride]
+void launch_g1_add_arrays(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J* src, size_t src_estride,
+                          size_t src_bstride, size_t n, size_t batch, cudaStream_t st);
+// dst[b*dst_bstride + i*dst_estride] = src[b*src_bstride + idx(i)*src_estride]
+void launch_g1_copy(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J* src, size_t src_estride,
+                    size_t src_bstride, size_t n, size_t batch, int bitrev, unsigned logn, cudaStream_t st);
+// kzg.go:57-61 / 103-109: work[off * 2k + i] = S[n - l - 1 - off - i l] for i < k - 1 (k = n / l);
+// the rest of work (pre-filled) stays infinity
+void launch_fk20_gather_x(const G1J* secret_g1, G1J* work, size_t n, size_t l, cudaStream_t st);
+// self test: device field + group law against portable forms; returns mismatches
+void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, cudaStream_t st);
+// throughput probe: `iters` dependent Fp multiplications per thread
+void launch_fp_mul_probe(uint32_t* d_buf, size_t threads, int iters, cudaStream_t st);
+
+}  // namespace b200

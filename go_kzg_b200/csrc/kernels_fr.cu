@@ -1,0 +1,349 @@
+// kernels_fr.cu -- scalar-field kernels: radix-2 Cooley-Tukey NTT over Fr (fft_fr.go:30-105),
+// Toeplitz coefficient gathers (fk20_single.go:89-119), pointwise helpers.
+//
+// NTT design: natural order in, natural order out, exactly the reference's transform.  A
+// transform of n = 2^logn points runs as one pass (n <= 4096: the whole vector lives in shared
+// memory, 32 B per element) or as two passes of a 4-step decomposition n = n1 * n2 (columns of
+// length n1 with a twiddle correction, then rows of length n2).  Inside a pass a CTA owns `cols`
+// independent sub-transforms: data is gathered with the bit reversal folded into the *global*
+// read (32 B elements = whole sectors), the half-table of twiddles w_M^j is staged to shared
+// memory with one bulk async copy (cp.async.bulk + mbarrier, TMA's 1-D form), and log2(M)
+// butterfly stages run out of shared memory with 128-bit accesses, one butterfly per lane.
+#include "field.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+static inline unsigned grid_for(size_t total, unsigned block) { return (unsigned)((total + block - 1) / block); }
+__device__ __forceinline__ uint32_t brev_bits(uint32_t v, unsigned logn) { return logn ? (__brev(v) >> (32 - logn)) : 0u; }
+
+// ------------------------------------------------------------------------------ conversions
+__global__ void k_fr_to_mont(const uint64_t* __restrict__ in, Fr* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr a = ld_vec(reinterpret_cast<const Fr*>(in) + i);
+    st_vec(out + i, fe_to_mont(a));
+}
+__global__ void k_fr_from_mont(const Fr* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_vec(reinterpret_cast<Fr*>(out) + i, fe_from_mont(ld_vec(in + i)));
+}
+void launch_fr_to_mont(const uint64_t* in, Fr* out, size_t n, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n) return;
+    k_fr_to_mont<<<grid_for(n, 256), 256, 0, st>>>(in, out, n); g_launch_count++;
+}
+void launch_fr_from_mont(const Fr* in, uint64_t* out, size_t n, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n) return;
+    k_fr_from_mont<<<grid_for(n, 256), 256, 0, st>>>(in, out, n); g_launch_count++;
+}
+
+__global__ void k_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_vec(dst + i, fe_mul(ld_vec(a + i), ld_vec(b + i)));
+}
+void launch_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n) return;
+    k_fr_mul_arrays<<<grid_for(n, 256), 256, 0, st>>>(dst, a, b, n); g_launch_count++;
+}
+
+// ------------------------------------------------------------------------------ NTT pass
+struct NttPass {
+    const Fr* in;
+    Fr* out;
+    size_t n;             // points per transform
+    unsigned logm;        // sub-transform length M = 2^logm
+    unsigned cols;        // sub-transforms per CTA (power of two)
+    size_t in_estride, in_cstride;     // element e of column c: in[b n + e in_estride + c in_cstride]
+    size_t out_kstride, out_cstride;   // output k of column c: out[b n + k out_kstride + c out_cstride]
+    const Fr* tw;         // M/2 twiddles w_M^j (forward or inverse), contiguous
+    const Fr* big;        // w_N^i table (expanded or reverse roots), or null: no correction
+    size_t big_stride;    // max_width / n
+    int c_fast;           // gather order of the global read (1: column index fastest)
+    int has_scale;
+    Fr scale;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok = 0;
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(phase)
+            : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_fr_ntt_pass(NttPass P) {
+    extern __shared__ uint4 smem_raw[];
+    __shared__ uint64_t bar;
+    const unsigned M = 1u << P.logm, C = P.cols;
+    Fr* s = reinterpret_cast<Fr*>(smem_raw);    // [M][C]
+    Fr* tws = s + (size_t)M * C;                // [M/2]
+    const unsigned tid = threadIdx.x, T = blockDim.x;
+    const size_t c0 = (size_t)blockIdx.x * C;
+    const Fr* in = P.in + (size_t)blockIdx.y * P.n;
+    Fr* out = P.out + (size_t)blockIdx.y * P.n;
+
+    const uint32_t tw_bytes = (M / 2) * (uint32_t)sizeof(Fr);
+    if (tid == 0 && tw_bytes) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&bar, tw_bytes);
+        bulk_g2s(tws, P.tw, tw_bytes, &bar);
+    }
+    // gather with the bit reversal on the global side: s[p][c] = x[rev(p)][c]
+    const unsigned total = M * C;
+    for (unsigned idx = tid; idx < total; idx += T) {
+        unsigned p, c;
+        if (P.c_fast) { c = idx % C; p = idx / C; } else { p = idx % M; c = idx / M; }
+        unsigned e = brev_bits(p, P.logm);
+        st_vec(s + (size_t)p * C + c, ld_vec(in + (size_t)e * P.in_estride + (c0 + c) * P.in_cstride));
+    }
+    __syncthreads();
+    if (tw_bytes) mbar_wait(&bar, 0);   // every thread observes the completed phase (acquire)
+
+    const unsigned nbf = (M / 2) * C;
+    for (unsigned m = 1; m < M; m <<= 1) {
+        const unsigned tstride = (M / 2) / m;
+        for (unsigned bf = tid; bf < nbf; bf += T) {
+            unsigned c = bf % C, q = bf / C;
+            unsigned j = q & (m - 1);
+            unsigned i0 = 2 * q - j, i1 = i0 + m;
+            Fr* a0 = s + (size_t)i0 * C + c;
+            Fr* a1 = s + (size_t)i1 * C + c;
+            Fr x1 = ld_vec(a1);
+            if (j) x1 = fe_mul(x1, ld_vec(tws + (size_t)j * tstride));
+            Fr x0 = ld_vec(a0);
+            st_vec(a0, fe_add(x0, x1));
+            st_vec(a1, fe_sub(x0, x1));
+        }
+        __syncthreads();
+    }
+    for (unsigned idx = tid; idx < total; idx += T) {
+        unsigned c = idx % C, k = idx / C;
+        Fr v = ld_vec(s + (size_t)k * C + c);
+        if (P.big) {
+            size_t ti = (size_t)k * (c0 + c);
+            if (ti) v = fe_mul(v, ld_vec(P.big + ti * P.big_stride));
+        }
+        if (P.has_scale) v = fe_mul(v, P.scale);
+        st_vec(out + (size_t)k * P.out_kstride + (c0 + c) * P.out_cstride, v);
+    }
+}
+
+static void run_pass(NttPass& P, size_t ngroups, size_t batch, cudaStream_t st) {
+    const size_t M = (size_t)1 << P.logm;
+    size_t smem = M * P.cols * sizeof(Fr) + (M / 2) * sizeof(Fr);
+    size_t work = M * P.cols / 2;
+    unsigned threads = work >= 1024 ? 1024 : (work < 32 ? 32 : (unsigned)work);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_fr_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    dim3 grid((unsigned)ngroups, (unsigned)batch);
+    k_fr_ntt_pass<<<grid, threads, smem, st>>>(P);
+    g_launch_count++;
+}
+
+void launch_fr_ntt(const FrDomain& dom, const Fr* in, Fr* out, Fr* tmp, unsigned logn, size_t batch, bool inverse,
+                   const Fr* scale_or_null, cudaStream_t st) {
+    ProfScope prof_scope(PROF_FR_NTT, st);
+    if (!batch) return;
+    const size_t n = (size_t)1 << logn;
+    const Fr* twbase = inverse ? dom.tw_inv : dom.tw_fwd;
+    const Fr* big = inverse ? dom.reverse : dom.expanded;
+    NttPass P;
+    P.n = n;
+    P.has_scale = 0;
+    if (logn <= 12) {
+        P.in = in; P.out = out; P.logm = logn; P.cols = 1;
+        P.in_estride = 1; P.in_cstride = 0; P.out_kstride = 1; P.out_cstride = 0;
+        P.tw = twbase + n / 2; P.big = nullptr; P.big_stride = 0; P.c_fast = 0;
+        if (scale_or_null) { P.has_scale = 1; P.scale = *scale_or_null; }
+        run_pass(P, 1, batch, st);
+        return;
+    }
+    const unsigned log1 = (logn + 1) / 2, log2 = logn - log1;
+    const size_t n1 = (size_t)1 << log1, n2 = (size_t)1 << log2;
+    // pass 1: columns (length n1, stride n2), times w_n^(n2 k1), left in place at [k1][n2]
+    {
+        unsigned cols = (unsigned)(4096 / n1); if (cols > 8) cols = 8; if (cols > n2) cols = (unsigned)n2;
+        P.in = in; P.out = tmp; P.logm = log1; P.cols = cols;
+        P.in_estride = n2; P.in_cstride = 1; P.out_kstride = n2; P.out_cstride = 1;
+        P.tw = twbase + n1 / 2; P.big = big; P.big_stride = dom.max_width / n; P.c_fast = 1;
+        run_pass(P, n2 / cols, batch, st);
+    }
+    // pass 2: rows (length n2, contiguous), output k2 of row k1 lands at k1 + n1 k2
+    {
+        unsigned cols = (unsigned)(4096 / n2); if (cols > 8) cols = 8; if (cols > n1) cols = (unsigned)n1;
+        P.in = tmp; P.out = out; P.logm = log2; P.cols = cols;
+        P.in_estride = 1; P.in_cstride = n2; P.out_kstride = n1; P.out_cstride = 1;
+        P.tw = twbase + n2 / 2; P.big = nullptr; P.big_stride = 0; P.c_fast = 0;
+        if (scale_or_null) { P.has_scale = 1; P.scale = *scale_or_null; }
+        run_pass(P, n1 / cols, batch, st);
+    }
+}
+
+// ------------------------------------------------------------------------------ DAS extension
+// das_extension.go:7-66 as an in-place butterfly network over n = 2^logn values.  Root indices
+// are relative to the settings' full domain exactly as in the reference (domainStride starts at
+// 1 whatever n is).
+//   descent, block length L = n .. 4 (stride s = n / L):  (a0, a1) <- (a0 + a1, (a0 - a1) Rev[2 i s])
+//   base,    L = 2 (s = n / 2):                            x = a0 + a1, t = (a0 - a1) Exp[s]; (x + t, x - t)
+//   ascent,  L = 4 .. n:                                   (a0, a1) <- (a0 + a1 Exp[(1 + 2 i) s], a0 - a1 Exp[..])
+//   finally every value times n^-1                         das_extension.go:78-83
+// Blocks of up to DAS_BLOCK values run entirely in shared memory; longer levels are single
+// global-memory passes.
+#define DAS_LOG_BLOCK 12
+template <bool ASCENT>
+__global__ void k_das_level(Fr* vals, size_t n, size_t L, const Fr* __restrict__ roots, int has_scale, Fr scale) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Fr* v = vals + (size_t)blockIdx.y * n;
+    if (t >= n / 2) return;
+    size_t hh = L / 2, i = t % hh, base = (t / hh) * L, s = n / L;
+    Fr a0 = ld_vec(v + base + i), a1 = ld_vec(v + base + hh + i);
+    if (!ASCENT) {
+        Fr d = fe_mul(fe_sub(a0, a1), ld_vec(roots + 2 * i * s));
+        st_vec(v + base + i, fe_add(a0, a1));
+        st_vec(v + base + hh + i, d);
+    } else {
+        Fr yr = fe_mul(a1, ld_vec(roots + (1 + 2 * i) * s));
+        Fr r0 = fe_add(a0, yr), r1 = fe_sub(a0, yr);
+        if (has_scale) { r0 = fe_mul(r0, scale); r1 = fe_mul(r1, scale); }
+        st_vec(v + base + i, r0);
+        st_vec(v + base + hh + i, r1);
+    }
+}
+// one CTA = one block of B = 2^logb consecutive values (all levels L <= B)
+__global__ void __launch_bounds__(1024) k_das_block(Fr* vals, size_t n, unsigned logb, const Fr* __restrict__ expanded,
+                                                    const Fr* __restrict__ reverse, int has_scale, Fr scale) {
+    extern __shared__ uint4 smem_raw[];
+    Fr* s = reinterpret_cast<Fr*>(smem_raw);
+    const unsigned B = 1u << logb, tid = threadIdx.x, T = blockDim.x;
+    Fr* v = vals + (size_t)blockIdx.y * n + (size_t)blockIdx.x * B;
+    for (unsigned i = tid; i < B; i += T) st_vec(s + i, ld_vec(v + i));
+    __syncthreads();
+    for (unsigned L = B; L >= 4; L >>= 1) {
+        const unsigned hh = L / 2;
+        const size_t st = n / L;
+        for (unsigned t = tid; t < B / 2; t += T) {
+            unsigned i = t % hh, base = (t / hh) * L;
+            Fr a0 = ld_vec(s + base + i), a1 = ld_vec(s + base + hh + i);
+            Fr d = fe_mul(fe_sub(a0, a1), ld_vec(reverse + 2 * (size_t)i * st));
+            st_vec(s + base + i, fe_add(a0, a1));
+            st_vec(s + base + hh + i, d);
+        }
+        __syncthreads();
+    }
+    if (B >= 2) {
+        const Fr w = ld_vec(expanded + n / 2);
+        for (unsigned t = tid; t < B / 2; t += T) {
+            Fr a0 = ld_vec(s + 2 * t), a1 = ld_vec(s + 2 * t + 1);
+            Fr x = fe_add(a0, a1), y = fe_mul(fe_sub(a0, a1), w);
+            st_vec(s + 2 * t, fe_add(x, y));
+            st_vec(s + 2 * t + 1, fe_sub(x, y));
+        }
+        __syncthreads();
+    }
+    for (unsigned L = 4; L <= B; L <<= 1) {
+        const unsigned hh = L / 2;
+        const size_t st = n / L;
+        for (unsigned t = tid; t < B / 2; t += T) {
+            unsigned i = t % hh, base = (t / hh) * L;
+            Fr a0 = ld_vec(s + base + i), a1 = ld_vec(s + base + hh + i);
+            Fr yr = fe_mul(a1, ld_vec(expanded + (1 + 2 * (size_t)i) * st));
+            st_vec(s + base + i, fe_add(a0, yr));
+            st_vec(s + base + hh + i, fe_sub(a0, yr));
+        }
+        __syncthreads();
+    }
+    for (unsigned i = tid; i < B; i += T) {
+        Fr x = ld_vec(s + i);
+        if (has_scale) x = fe_mul(x, scale);
+        st_vec(v + i, x);
+    }
+}
+void launch_das_fft_extension(const FrDomain& dom, Fr* vals, unsigned logn, size_t batch, const Fr& inv_n, cudaStream_t st) {
+    ProfScope prof_scope(PROF_FR_NTT, st);
+    if (!batch) return;
+    const size_t n = (size_t)1 << logn;
+    if (logn == 0) return;   // the reference panics ("bad usage") before this point; caller checks
+    const unsigned logb = logn < DAS_LOG_BLOCK ? logn : DAS_LOG_BLOCK;
+    const size_t B = (size_t)1 << logb;
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(k_das_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
+    dim3 lgrid((unsigned)((n / 2 + 255) / 256), (unsigned)batch);
+    for (size_t L = n; L > B; L >>= 1) { k_das_level<false><<<lgrid, 256, 0, st>>>(vals, n, L, dom.reverse, 0, inv_n); g_launch_count++; }
+    unsigned threads = B / 2 >= 1024 ? 1024 : (B / 2 < 32 ? 32 : (unsigned)(B / 2));
+    k_das_block<<<dim3((unsigned)(n / B), (unsigned)batch), threads, B * sizeof(Fr), st>>>(vals, n, logb, dom.expanded, dom.reverse,
+                                                                                    B == n ? 1 : 0, inv_n);
+    g_launch_count++;
+    for (size_t L = 2 * B; L <= n; L <<= 1) { k_das_level<true><<<lgrid, 256, 0, st>>>(vals, n, L, dom.expanded, L == n ? 1 : 0, inv_n); g_launch_count++; }
+}
+
+// ------------------------------------------------------------------------------ Toeplitz gathers
+// fk20_single.go:106-119: [p[n-1], 0 x (n+1), p[1..n-2]]
+__global__ void k_toeplitz_coeffs(const uint64_t* __restrict__ polys, Fr* __restrict__ out, size_t n, size_t batch) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n2 = 2 * n;
+    if (t >= n2 * batch) return;
+    size_t b = t / n2, i = t % n2;
+    const Fr* p = reinterpret_cast<const Fr*>(polys) + b * n;
+    Fr v = Fr::zero();
+    if (i == 0) v = fe_to_mont(ld_vec(p + (n - 1)));
+    else if (i >= n + 2) v = fe_to_mont(ld_vec(p + (i - n - 1)));
+    st_vec(out + t, v);
+}
+void launch_toeplitz_coeffs(const uint64_t* polys, Fr* out, size_t n, size_t batch, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n || !batch) return;
+    k_toeplitz_coeffs<<<grid_for(2 * n * batch, 256), 256, 0, st>>>(polys, out, n, batch); g_launch_count++;
+}
+// fk20_single.go:89-103 for every offset: out[b][off][2k]
+__global__ void k_toeplitz_coeffs_strided(const uint64_t* __restrict__ polys, Fr* __restrict__ out, size_t n, size_t l,
+                                          size_t batch) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t k = n / l, k2 = 2 * k;
+    if (t >= k2 * l * batch) return;
+    size_t i = t % k2, off = (t / k2) % l, b = t / (k2 * l);
+    const Fr* p = reinterpret_cast<const Fr*>(polys) + b * n;
+    Fr v = Fr::zero();
+    if (i == 0) v = fe_to_mont(ld_vec(p + (n - 1 - off)));
+    else if (i >= k + 2) v = fe_to_mont(ld_vec(p + (2 * l - off - 1 + (i - k - 2) * l)));
+    st_vec(out + t, v);
+}
+void launch_toeplitz_coeffs_strided(const uint64_t* polys, Fr* out, size_t n, size_t chunk_len, size_t batch,
+                                    cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n || !batch) return;
+    size_t total = 2 * (n / chunk_len) * chunk_len * batch;
+    k_toeplitz_coeffs_strided<<<grid_for(total, 256), 256, 0, st>>>(polys, out, n, chunk_len, batch); g_launch_count++;
+}
+
+}  // namespace b200

@@ -1,0 +1,414 @@
+"""ctypes mirror of the reference's Go API over the C ABI of libb200kzg.so.
+
+Encodings (include/b200_kzg.h): Fr = (n, 4) uint64 little-endian canonical limbs;
+G1 = (n, 18) uint64 Jacobian canonical limbs, Z == 0 <=> infinity; compressed G1 = (n, 48) uint8.
+
+Error behaviour follows the reference: functions that return `error` in Go raise KZGError,
+functions that `panic` in Go raise KZGPanic; CUDA problems raise B200Error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+R_MOD = 52435875175126190479447740508185965837690552500527637822603658699938581184513
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libb200kzg.so")
+
+OK, TOO_LARGE, NOT_POW2, LEN_MISMATCH, BAD_INPUT, ERR_CUDA, NO_DEVICE, TOO_SMALL, RECOVERY, ZERO_EVAL = range(10)
+
+
+class B200Error(RuntimeError):
+    """CUDA / device failure inside the library (no CPU fallback exists)."""
+
+
+class KZGError(ValueError):
+    """The reference returns an `error` for this condition."""
+
+    def __init__(self, status, msg):
+        super().__init__(msg)
+        self.status = status
+
+
+class KZGPanic(Exception):
+    """The reference panics on this condition."""
+
+    def __init__(self, status, msg):
+        super().__init__(msg)
+        self.status = status
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads libb200kzg.so (built by go_kzg_b200/build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise B200Error("libb200kzg.so is not built: run `python -m go_kzg_b200.build` "
+                        "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(_LIB_PATH)
+    vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+    L.b200_strerror.restype = C.c_char_p
+    L.b200_strerror.argtypes = [i32]
+    L.b200_last_cuda_error.restype = C.c_char_p
+    L.b200_device_count.restype = i32
+    L.b200_set_device.argtypes = [i32]
+    for name in ("b200_fr_add", "b200_fr_sub", "b200_fr_mul", "b200_fr_div", "b200_g1_add", "b200_g1_sub", "b200_g1_mul"):
+        getattr(L, name).argtypes = [vp, vp, vp]
+        getattr(L, name).restype = None
+    L.b200_fr_inv.argtypes = [vp, vp]
+    L.b200_fr_inv.restype = None
+    L.b200_fr_batch_inv.argtypes = [vp, sz]
+    L.b200_fr_batch_inv.restype = None
+    L.b200_fr_valid.argtypes = [vp]
+    L.b200_fr_root_of_unity.argtypes = [C.c_uint, vp]
+    L.b200_fr_root_of_unity.restype = None
+    L.b200_g1_generator.argtypes = [vp]
+    L.b200_g1_generator.restype = None
+    L.b200_g1_neg.argtypes = [vp]
+    L.b200_g1_neg.restype = None
+    L.b200_g1_equal.argtypes = [vp, vp]
+    L.b200_g1_to_compressed.argtypes = [vp, vp]
+    L.b200_g1_to_compressed.restype = None
+    L.b200_g1_from_compressed.argtypes = [vp, vp]
+    L.b200_g1_to_compressed_many.argtypes = [vp, vp, sz]
+    L.b200_g1_to_compressed_many.restype = None
+    L.b200_g1_from_compressed_many.argtypes = [vp, vp, sz]
+    L.b200_g1_lincomb.argtypes = [vp, vp, sz, vp]
+    L.b200_g1_mul_many.argtypes = [vp, vp, sz, vp]
+    L.b200_fft_settings_new.argtypes = [C.c_uint8, C.POINTER(vp)]
+    L.b200_fft_settings_free.argtypes = [vp]
+    L.b200_fft_settings_free.restype = None
+    L.b200_fs_max_width.argtypes = [vp]
+    L.b200_fs_max_width.restype = u64
+    L.b200_fs_roots.argtypes = [vp, i32, vp]
+    L.b200_fft_fr.argtypes = [vp, vp, sz, i32, vp]
+    L.b200_fft_fr_batch.argtypes = [vp, vp, sz, sz, i32, vp]
+    L.b200_fft_g1.argtypes = [vp, vp, sz, i32, vp]
+    L.b200_fft_g1_batch.argtypes = [vp, vp, sz, sz, i32, vp]
+    L.b200_das_fft_extension.argtypes = [vp, vp, sz]
+    L.b200_das_fft_extension_batch.argtypes = [vp, vp, sz, sz]
+    L.b200_zero_poly_via_multiplication.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.b200_recover_poly_from_samples.argtypes = [vp, vp, vp, sz, vp]
+    L.b200_recover_poly_from_samples_batch.argtypes = [vp, vp, vp, sz, sz, vp]
+    L.b200_kzg_settings_new.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
+    L.b200_kzg_settings_free.argtypes = [vp]
+    L.b200_kzg_settings_free.restype = None
+    L.b200_commit_to_poly.argtypes = [vp, vp, sz, vp]
+    L.b200_commit_to_poly_batch.argtypes = [vp, vp, sz, sz, vp]
+    L.b200_fk20_single_settings_new.argtypes = [vp, sz, C.POINTER(vp)]
+    L.b200_fk20_multi_settings_new.argtypes = [vp, sz, sz, C.POINTER(vp)]
+    L.b200_fk20_settings_free.argtypes = [vp]
+    L.b200_fk20_settings_free.restype = None
+    L.b200_fk20_x_ext_fft.argtypes = [vp, sz, vp]
+    L.b200_fk20_single.argtypes = [vp, vp, sz, vp]
+    L.b200_fk20_single_da_optimized.argtypes = [vp, vp, sz, vp]
+    L.b200_da_using_fk20.argtypes = [vp, vp, sz, vp]
+    L.b200_fk20_multi_da_optimized.argtypes = [vp, vp, sz, vp]
+    L.b200_da_using_fk20_multi.argtypes = [vp, vp, sz, vp]
+    L.b200_commit_fk20_batch.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.b200_commit_fk20_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+    L.b200_fk20_last_launch_count.argtypes = [vp]
+    L.b200_fk20_last_launch_count.restype = u64
+    L.b200_selftest_field.argtypes = [sz, u64, C.POINTER(u64)]
+    L.b200_probe_fp_mul.argtypes = [sz, i32, C.POINTER(C.c_float)]
+    L.b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(u64)]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _fr(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+
+
+def _g1(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 18)
+
+
+def _raise(status: int, errors=(), what: str = ""):
+    """status -> exception, following the reference's error/panic split for this call."""
+    if status == OK:
+        return
+    msg = "%s: %s" % (what, lib().b200_strerror(status).decode())
+    if status in (ERR_CUDA, NO_DEVICE):
+        raise B200Error(msg + " [" + lib().b200_last_cuda_error().decode() + "]")
+    if status in errors:
+        raise KZGError(status, msg)
+    raise KZGPanic(status, msg)
+
+
+# ------------------------------------------------------------------------------- conversions
+def fr_from_ints(vals) -> np.ndarray:
+    out = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        v = int(v)
+        for j in range(4):
+            out[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def fr_to_ints(a) -> list:
+    a = _fr(a)
+    return [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
+
+
+def g1_to_compressed(pts) -> np.ndarray:
+    """bls/bls_kilic.go:114 ToCompressedG1 over an array (host side)."""
+    pts = _g1(pts)
+    out = np.zeros((pts.shape[0], 48), dtype=np.uint8)
+    lib().b200_g1_to_compressed_many(_p(out), _p(pts), pts.shape[0])
+    return out
+
+
+def g1_from_compressed(b) -> np.ndarray:
+    """bls/bls_kilic.go:118 FromCompressedG1 over an array (host side); error on bad encodings."""
+    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 48)
+    out = np.zeros((b.shape[0], 18), dtype=np.uint64)
+    _raise(lib().b200_g1_from_compressed_many(_p(out), _p(b), b.shape[0]), errors=(BAD_INPUT,), what="FromCompressedG1")
+    return out
+
+
+def lincomb_g1(points, scalars) -> np.ndarray:
+    """bls/bls_kilic.go:132-150 LinCombG1 (device MSM); panics on a length mismatch."""
+    pts, sc = _g1(points), _fr(scalars)
+    if pts.shape[0] != sc.shape[0]:
+        raise KZGPanic(LEN_MISMATCH, "got %d numbers and %d points" % (sc.shape[0], pts.shape[0]))
+    out = np.zeros(18, dtype=np.uint64)
+    _raise(lib().b200_g1_lincomb(_p(pts), _p(sc), pts.shape[0], _p(out)), what="LinCombG1")
+    return out
+
+
+def g1_mul_many(points, scalars) -> np.ndarray:
+    pts, sc = _g1(points), _fr(scalars)
+    assert pts.shape[0] == sc.shape[0]
+    out = np.zeros_like(pts)
+    _raise(lib().b200_g1_mul_many(_p(pts), _p(sc), pts.shape[0], _p(out)), what="MulG1 batch")
+    return out
+
+
+# ------------------------------------------------------------------------------- settings
+class FFTSettings:
+    """fft.go:34-61.  Holds the device-side domain tables."""
+
+    def __init__(self, max_scale: int):
+        h = C.c_void_p()
+        _raise(lib().b200_fft_settings_new(max_scale, C.byref(h)), what="NewFFTSettings")
+        self.h = h
+        self.max_scale = max_scale
+        self.max_width = 1 << max_scale
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_fft_settings_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def expanded_roots_of_unity(self, reverse: bool = False) -> np.ndarray:
+        out = np.zeros((self.max_width + 1, 4), dtype=np.uint64)
+        _raise(lib().b200_fs_roots(self.h, int(reverse), _p(out)))
+        return out
+
+    def fft(self, vals, inv: bool = False) -> np.ndarray:
+        """fft_fr.go:55-74 FFT (zero-pads to the next power of two); error if too large."""
+        v = _fr(vals)
+        n = v.shape[0]
+        npow = 1 if n == 0 else 1 << (n - 1).bit_length()
+        out = np.zeros((npow, 4), dtype=np.uint64)
+        _raise(lib().b200_fft_fr(self.h, _p(v), n, int(inv), _p(out)), errors=(TOO_LARGE, NOT_POW2), what="FFT")
+        return out
+
+    def fft_batch(self, vals, inv: bool = False) -> np.ndarray:
+        v = np.ascontiguousarray(vals, dtype=np.uint64)
+        batch, n = v.shape[0], v.shape[1]
+        npow = 1 if n == 0 else 1 << (n - 1).bit_length()
+        out = np.zeros((batch, npow, 4), dtype=np.uint64)
+        _raise(lib().b200_fft_fr_batch(self.h, _p(v), n, batch, int(inv), _p(out)), errors=(TOO_LARGE, NOT_POW2), what="FFT")
+        return out
+
+    def fft_g1(self, vals, inv: bool = False) -> np.ndarray:
+        """fft_g1.go:58-94 FFTG1; error if too large or not a power of two."""
+        v = _g1(vals)
+        out = np.zeros_like(v)
+        _raise(lib().b200_fft_g1(self.h, _p(v), v.shape[0], int(inv), _p(out)), errors=(TOO_LARGE, NOT_POW2), what="FFTG1")
+        return out
+
+    def fft_g1_batch(self, vals, inv: bool = False) -> np.ndarray:
+        v = np.ascontiguousarray(vals, dtype=np.uint64)
+        batch, n = v.shape[0], v.shape[1]
+        out = np.zeros_like(v)
+        _raise(lib().b200_fft_g1_batch(self.h, _p(v), n, batch, int(inv), _p(out)), errors=(TOO_LARGE, NOT_POW2), what="FFTG1")
+        return out
+
+    def das_fft_extension(self, vals) -> np.ndarray:
+        """das_extension.go:71-84 DASFFTExtension (the reference works in place; a copy is returned)."""
+        v = _fr(vals).copy()
+        _raise(lib().b200_das_fft_extension(self.h, _p(v), v.shape[0]), what="DASFFTExtension")
+        return v
+
+    def das_fft_extension_batch(self, vals) -> np.ndarray:
+        v = np.ascontiguousarray(vals, dtype=np.uint64).copy()
+        _raise(lib().b200_das_fft_extension_batch(self.h, _p(v), v.shape[1], v.shape[0]), what="DASFFTExtension")
+        return v
+
+    def zero_poly_via_multiplication(self, missing_indices, length: int):
+        """zero_poly.go:116-217 -> (zeroEval, zeroPoly)"""
+        m = np.ascontiguousarray(np.asarray(missing_indices, dtype=np.uint64))
+        ze = np.zeros((length, 4), dtype=np.uint64)
+        zp = np.zeros((length, 4), dtype=np.uint64)
+        _raise(lib().b200_zero_poly_via_multiplication(self.h, _p(m), m.shape[0], length, _p(ze), _p(zp)),
+               what="ZeroPolyViaMultiplication")
+        return ze, zp
+
+    def recover_poly_from_samples(self, samples, present) -> np.ndarray:
+        """recover_from_samples.go:42-109; samples[i] is ignored where present[i] == 0 (nil)."""
+        s = _fr(samples)
+        pr = np.ascontiguousarray(present, dtype=np.uint8)
+        out = np.zeros_like(s)
+        _raise(lib().b200_recover_poly_from_samples(self.h, _p(s), _p(pr), s.shape[0], _p(out)),
+               errors=(TOO_LARGE, NOT_POW2, RECOVERY), what="RecoverPolyFromSamples")
+        return out
+
+    def recover_poly_from_samples_batch(self, samples, present) -> np.ndarray:
+        s = np.ascontiguousarray(samples, dtype=np.uint64)
+        pr = np.ascontiguousarray(present, dtype=np.uint8)
+        out = np.zeros_like(s)
+        _raise(lib().b200_recover_poly_from_samples_batch(self.h, _p(s), _p(pr), s.shape[1], s.shape[0], _p(out)),
+               errors=(TOO_LARGE, NOT_POW2, RECOVERY), what="RecoverPolyFromSamples")
+        return out
+
+
+class KZGSettings:
+    """kzg.go:11-36.  secret_g2 stays with the caller's CPU backend; only its length is checked."""
+
+    def __init__(self, fs: FFTSettings, secret_g1, secret_g2_len=None):
+        g = _g1(secret_g1)
+        h = C.c_void_p()
+        n2 = g.shape[0] if secret_g2_len is None else secret_g2_len
+        _raise(lib().b200_kzg_settings_new(fs.h, _p(g), g.shape[0], n2, C.byref(h)), what="NewKZGSettings")
+        self.h, self.fs = h, fs
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_kzg_settings_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def commit_to_poly(self, coeffs) -> np.ndarray:
+        """kzg_single_proofs.go:17-19"""
+        c = _fr(coeffs)
+        out = np.zeros(18, dtype=np.uint64)
+        _raise(lib().b200_commit_to_poly(self.h, _p(c), c.shape[0], _p(out)), what="CommitToPoly")
+        return out
+
+    def commit_to_poly_batch(self, coeffs) -> np.ndarray:
+        c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        out = np.zeros((c.shape[0], 18), dtype=np.uint64)
+        _raise(lib().b200_commit_to_poly_batch(self.h, _p(c), c.shape[1], c.shape[0], _p(out)), what="CommitToPoly")
+        return out
+
+
+class _FK20Base:
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_fk20_settings_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def x_ext_fft(self, file: int = 0) -> np.ndarray:
+        out = np.zeros((self.n2 // self.chunk_len, 18), dtype=np.uint64)
+        _raise(lib().b200_fk20_x_ext_fft(self.h, file, _p(out)))
+        return out
+
+    def last_launch_count(self) -> int:
+        return int(lib().b200_fk20_last_launch_count(self.h))
+
+
+class FK20SingleSettings(_FK20Base):
+    """kzg.go:38-64"""
+
+    def __init__(self, ks: KZGSettings, n2: int):
+        h = C.c_void_p()
+        _raise(lib().b200_fk20_single_settings_new(ks.h, n2, C.byref(h)), what="NewFK20SingleSettings")
+        self.h, self.ks, self.n2, self.chunk_len = h, ks, n2, 1
+
+    def fk20_single(self, poly) -> np.ndarray:
+        """fk20_single.go:122-134: n proofs, natural order"""
+        p = _fr(poly)
+        out = np.zeros((p.shape[0], 18), dtype=np.uint64)
+        _raise(lib().b200_fk20_single(self.h, _p(p), p.shape[0], _p(out)), what="FK20Single")
+        return out
+
+    def fk20_single_da_optimized(self, poly) -> np.ndarray:
+        """fk20_single.go:139-172"""
+        p = _fr(poly)
+        out = np.zeros((p.shape[0], 18), dtype=np.uint64)
+        _raise(lib().b200_fk20_single_da_optimized(self.h, _p(p), p.shape[0], _p(out)), what="FK20SingleDAOptimized")
+        return out
+
+    def da_using_fk20(self, poly) -> np.ndarray:
+        """fk20_single.go:176-196: 2n proofs in reverse bit order"""
+        p = _fr(poly)
+        out = np.zeros((2 * p.shape[0], 18), dtype=np.uint64)
+        _raise(lib().b200_da_using_fk20(self.h, _p(p), p.shape[0], _p(out)), what="DAUsingFK20")
+        return out
+
+    def commit_fk20_batch(self, polys):
+        """Headline unit: (CommitToPoly(p), FK20Single(p)) for every polynomial of the batch."""
+        p = np.ascontiguousarray(polys, dtype=np.uint64)
+        batch, n = p.shape[0], p.shape[1]
+        commits = np.zeros((batch, 18), dtype=np.uint64)
+        proofs = np.zeros((batch, n, 18), dtype=np.uint64)
+        _raise(lib().b200_commit_fk20_batch(self.h, _p(p), n, batch, _p(commits), _p(proofs)), what="commit+FK20Single")
+        return commits, proofs
+
+
+class FK20MultiSettings(_FK20Base):
+    """kzg.go:66-116"""
+
+    def __init__(self, ks: KZGSettings, n2: int, chunk_len: int):
+        h = C.c_void_p()
+        _raise(lib().b200_fk20_multi_settings_new(ks.h, n2, chunk_len, C.byref(h)), what="NewFK20MultiSettings")
+        self.h, self.ks, self.n2, self.chunk_len = h, ks, n2, chunk_len
+
+    def fk20_multi_da_optimized(self, poly) -> np.ndarray:
+        """fk20_multi.go:58-109: n2 coefficients (upper half zero) -> 2k proofs"""
+        p = _fr(poly)
+        out = np.zeros((p.shape[0] // self.chunk_len, 18), dtype=np.uint64)
+        _raise(lib().b200_fk20_multi_da_optimized(self.h, _p(p), p.shape[0], _p(out)), what="FK20MultiDAOptimized")
+        return out
+
+    def da_using_fk20_multi(self, poly) -> np.ndarray:
+        """fk20_multi.go:113-133: 2k proofs in reverse bit order"""
+        p = _fr(poly)
+        out = np.zeros((2 * p.shape[0] // self.chunk_len, 18), dtype=np.uint64)
+        _raise(lib().b200_da_using_fk20_multi(self.h, _p(p), p.shape[0], _p(out)), what="DAUsingFK20Multi")
+        return out

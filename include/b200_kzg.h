@@ -151,9 +151,19 @@ int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_
 /* Number of kernels the last batch call on this handle launched (bench.py gpu_launches). */
 uint64_t b200_fk20_last_launch_count(const b200_fk* fk);
 
+/* Per-kernel-class device timing for bench.py's roofline: between begin and end every launch is
+ * bracketed by CUDA events on its stream.  Classes: 0 Fr NTT, 1 G1 FFT butterfly stage,
+ * 2 G1 scalar multiplication, 3 G1 fold/add, 4 conversions and copies.  Not thread safe. */
+#define B200_PROFILE_CLASSES 5
+int b200_profile_begin(void);
+int b200_profile_end(double ms_per_class[B200_PROFILE_CLASSES], uint64_t launches_per_class[B200_PROFILE_CLASSES]);
+
 /* Self-test hooks (tests/): run the device field/curve primitives against the portable
  * host forms on `n` pseudo-random operands; returns the mismatch count in *mismatches. */
 int b200_selftest_field(size_t n, uint64_t seed, uint64_t* mismatches);
+/* Integer-pipe probe (bench.py's second roofline): `threads` lanes each run 2 * iters dependent
+ * 381-bit Montgomery multiplications; *ms receives the device time of that launch. */
+int b200_probe_fp_mul(size_t threads, int iters, float* ms);
 
 #ifdef __cplusplus
 }

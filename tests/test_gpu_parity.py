@@ -1,0 +1,314 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (python mirror of the Go API).
+
+Everything here needs a B200 (`-m gpu`).  G1 results are compared on their 48-byte compressed
+encodings (Jacobian limbs are representation dependent; the reference itself only compares
+projectively, bls/bls_kilic.go:106), Fr results on canonical limbs: bit-exact, no tolerance."""
+import random
+
+import numpy as np
+import pytest
+
+import go_kzg_b200 as kzg
+from kzg_test_util import blob_polys, random_fr_ints
+from oracle import cref, pyref
+
+pytestmark = pytest.mark.gpu
+R = pyref.R_MOD
+
+
+def cmp_g1(got, want):
+    assert np.array_equal(kzg.g1_to_compressed(got), cref.g1_compress(want))
+
+
+# ------------------------------------------------------------------------------ primitives
+def test_device_field_and_group_selftest():
+    import ctypes as C
+    bad = C.c_uint64(123)
+    assert kzg.lib().b200_selftest_field(4096, 7, C.byref(bad)) == 0
+    assert bad.value == 0
+
+
+# ------------------------------------------------------------------------------ Fr FFT
+def test_fft_fr_golden(goldens):
+    """fft_fr_test.go:32-71 TestInvFFT"""
+    g = goldens["inv_fft_scale4"]
+    fs = kzg.FFTSettings(4)
+    assert kzg.fr_to_ints(fs.fft(kzg.fr_from_ints(g["input"]), True)) == [int(v) for v in g["expected"]]
+
+
+def test_fs_roots_match_oracle():
+    fs, fo = kzg.FFTSettings(6), pyref.FFTSettings(6)
+    assert kzg.fr_to_ints(fs.expanded_roots_of_unity()) == fo.expanded
+    assert kzg.fr_to_ints(fs.expanded_roots_of_unity(True)) == fo.expanded[::-1]
+
+
+@pytest.mark.parametrize("scale", [0, 1, 2, 3, 5, 8, 10, 12, 13, 14, 15])
+def test_fft_fr_vs_oracle(scale):
+    n = 1 << scale
+    fs, fo = kzg.FFTSettings(max(scale, 4)), cref.FFTSettings(max(scale, 4))
+    v = kzg.fr_from_ints(random_fr_ints(n, scale))
+    for inv in (False, True):
+        assert np.array_equal(fs.fft(v, inv), fo.fft(v, inv))
+    back = fs.fft(fs.fft(v), True)                       # fft_fr_test.go:9-30 round trip
+    assert np.array_equal(back, v)
+
+
+def test_fft_fr_subsize_and_padding():
+    """smaller transforms reuse the big domain with stride MaxWidth / n (fft_fr.go:89,100);
+    non power-of-two inputs are zero padded (fft_fr.go:60-68)"""
+    fs, fo = kzg.FFTSettings(14), cref.FFTSettings(14)
+    for n in (1, 3, 16, 1000, 4097):
+        v = kzg.fr_from_ints(random_fr_ints(n, n))
+        for inv in (False, True):
+            assert np.array_equal(fs.fft(v, inv), fo.fft(v, inv))
+    with pytest.raises(kzg.KZGError):                    # fft_fr.go:57-59
+        kzg.FFTSettings(3).fft(kzg.fr_from_ints(list(range(9))))
+
+
+def test_fft_fr_batch():
+    fs, fo = kzg.FFTSettings(13), cref.FFTSettings(13)
+    v = np.stack([kzg.fr_from_ints(random_fr_ints(8192, 100 + b)) for b in range(3)])
+    out = fs.fft_batch(v)
+    for b in range(3):
+        assert np.array_equal(out[b], fo.fft(v[b]))
+
+
+# ------------------------------------------------------------------------------ DAS extension
+def test_das_ext_golden(goldens):
+    """das_extension_test.go:11-40"""
+    g = goldens["das_ext_scale4"]
+    fs = kzg.FFTSettings(4)
+    assert kzg.fr_to_ints(fs.das_fft_extension(kzg.fr_from_ints(g["input"]))) == [int(v) for v in g["expected"]]
+
+
+@pytest.mark.parametrize("scale", [2, 4, 7, 9, 13, 14, 15])
+def test_das_ext_vs_oracle(scale):
+    fs, fo = kzg.FFTSettings(scale), cref.FFTSettings(scale)
+    even = kzg.fr_from_ints(random_fr_ints(1 << (scale - 1), scale))
+    odd = fs.das_fft_extension(even)
+    assert np.array_equal(odd, fo.das_fft_extension(even))
+    # das_extension_test.go:42-86: the interleaved data has a zero upper half of coefficients
+    inter = np.empty((1 << scale, 4), dtype=np.uint64)
+    inter[0::2], inter[1::2] = even, odd
+    coeffs = fs.fft(inter, True)
+    assert not coeffs[(1 << scale) // 2:].any()
+
+
+def test_das_ext_oversized_domain_and_panic():
+    # MaxWidth > 2 n: the reference still indexes the full domain with stride 1 (das_extension.go:75)
+    fs, fo = kzg.FFTSettings(8), cref.FFTSettings(8)
+    v = kzg.fr_from_ints(random_fr_ints(32, 1))
+    assert np.array_equal(fs.das_fft_extension(v), fo.das_fft_extension(v))
+    with pytest.raises(kzg.KZGPanic):                    # das_extension.go:72-74
+        kzg.FFTSettings(3).das_fft_extension(kzg.fr_from_ints(list(range(8))))
+
+
+# ------------------------------------------------------------------------------ G1 FFT
+@pytest.mark.parametrize("n", [1, 2, 4, 16, 64])
+def test_fft_g1_vs_oracle(n):
+    rng = random.Random(n)
+    scale = max(n.bit_length() - 1, 1)
+    fs, fo = kzg.FFTSettings(scale + 1), cref.FFTSettings(scale + 1)   # sub-size: stride 2
+    ks = [rng.randrange(R) for _ in range(n)]
+    if n >= 4:
+        ks[1] = 0                   # infinity among the inputs
+        ks[3] = ks[2]               # equal points -> doubling branch inside butterflies
+    pts = cref.g1_mul_gen(ks)
+    for inv in (False, True):
+        cmp_g1(fs.fft_g1(pts, inv), fo.fft_g1(pts, inv))
+
+
+def test_fft_g1_constant_and_zero_vectors():
+    fs = kzg.FFTSettings(4)
+    P = cref.g1_mul_gen([5])[0]
+    same = np.stack([P] * 16)
+    out = fs.fft_g1(same)           # DFT of a constant: (16 P, inf, inf, ...)
+    want = np.zeros((16, 18), dtype=np.uint64)
+    want[0] = cref.g1_mul_gen([80])[0]
+    cmp_g1(out, want)
+    cmp_g1(fs.fft_g1(np.zeros((16, 18), dtype=np.uint64)), np.zeros((16, 18), dtype=np.uint64))
+
+
+def test_fft_g1_errors():
+    """fft_g1.go:60-65"""
+    fs = kzg.FFTSettings(3)
+    with pytest.raises(kzg.KZGError):
+        fs.fft_g1(np.zeros((16, 18), dtype=np.uint64))
+    with pytest.raises(kzg.KZGError):
+        fs.fft_g1(np.zeros((6, 18), dtype=np.uint64))
+
+
+def test_fft_g1_lagrange_kat(trusted_setup_bytes):
+    """eth/trusted_setup.json: FFTG1(setup_G1, inv) == setup_G1_lagrange, natural order, all
+    4096 points -- the reference's shipped G1-IFFT known-answer vector."""
+    s1, lag = trusted_setup_bytes
+    fs = kzg.FFTSettings(12)
+    out = fs.fft_g1(kzg.g1_from_compressed(s1), True)
+    assert np.array_equal(kzg.g1_to_compressed(out), lag)
+
+
+def test_fft_g1_batch_uses_shared_twiddle_programs():
+    """batch of 32 transforms: lanes = blobs, width-5 NAF twiddle programs"""
+    rng = random.Random(77)
+    fs, fo = kzg.FFTSettings(4), pyref.FFTSettings(4)
+    ks = [[rng.randrange(R) for _ in range(16)] for _ in range(32)]
+    pts = np.stack([cref.g1_mul_gen(k) for k in ks])
+    out = fs.fft_g1_batch(pts, False)
+    for b in (0, 7, 31):
+        cmp_g1(out[b], cref.g1_mul_gen(fo.fft(ks[b], False)))
+    out = fs.fft_g1_batch(pts, True)
+    for b in (0, 13, 31):
+        cmp_g1(out[b], cref.g1_mul_gen(fo.fft(ks[b], True)))
+
+
+# ------------------------------------------------------------------------------ LinCombG1 / commit
+def test_empty_lincomb_is_infinity():
+    """bls/bls_test.go:69-77 TestEmptyG1Lincomb"""
+    out = kzg.lincomb_g1(np.zeros((0, 18), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64))
+    assert not out.any()
+    with pytest.raises(kzg.KZGPanic):                    # bls/bls_kilic.go:133-135
+        kzg.lincomb_g1(np.zeros((2, 18), dtype=np.uint64), np.zeros((3, 4), dtype=np.uint64))
+
+
+@pytest.mark.parametrize("n", [1, 5, 31, 32, 200])
+def test_lincomb_vs_oracle(n):
+    rng = random.Random(n)
+    ks = [rng.randrange(R) for _ in range(n)]
+    ss = [rng.randrange(R) for _ in range(n)]
+    if n > 3:
+        ss[1], ks[2], ss[3] = 0, 0, R - 1
+    pts = cref.g1_mul_gen(ks)
+    out = kzg.lincomb_g1(pts, kzg.fr_from_ints(ss))
+    cmp_g1(out, cref.g1_mul_gen([sum(k * s for k, s in zip(ks, ss)) % R]))
+    cmp_g1(out, cref.lincomb_g1(pts, cref.fr_to_limbs(ss)))
+
+
+def test_mul_many_vs_oracle():
+    rng = random.Random(3)
+    ks = [rng.randrange(R) for _ in range(40)]
+    ss = [0, 1, 2, R - 1, 1 << 128, (1 << 128) - 1] + [rng.randrange(R) for _ in range(34)]
+    pts = cref.g1_mul_gen(ks)
+    pts[5] = 0
+    ks[5] = 0
+    out = kzg.g1_mul_many(pts, kzg.fr_from_ints(ss))
+    cmp_g1(out, cref.g1_mul_gen([k * s % R for k, s in zip(ks, ss)]))
+
+
+def test_commit_to_poly_trusted_setup(trusted_setup_bytes):
+    """config 2: CommitToPoly over eth/trusted_setup.json (secret 1337) == p(1337) G"""
+    s1, _ = trusted_setup_bytes
+    fs = kzg.FFTSettings(12)
+    ks = kzg.KZGSettings(fs, kzg.g1_from_compressed(s1))
+    coeffs = random_fr_ints(4096, 0xB2000000)
+    com = ks.commit_to_poly(kzg.fr_from_ints(coeffs))
+    cmp_g1(com, cref.g1_mul_gen([pyref.eval_poly(coeffs, 1337)]))
+    short = ks.commit_to_poly(kzg.fr_from_ints(coeffs[:100]))      # SecretG1[:len(coeffs)]
+    cmp_g1(short, cref.g1_mul_gen([pyref.eval_poly(coeffs[:100], 1337)]))
+
+
+def test_kzg_settings_checks():
+    """kzg.go:21-27 panics"""
+    fs = kzg.FFTSettings(4)
+    pts = cref.generate_setup_g1(5, 16)
+    with pytest.raises(kzg.KZGPanic):
+        kzg.KZGSettings(fs, pts, secret_g2_len=15)
+    with pytest.raises(kzg.KZGPanic):
+        kzg.KZGSettings(fs, pts[:8])
+
+
+# ------------------------------------------------------------------------------ FK20
+def test_fk20_single_reference_test_case(goldens):
+    """fk20_single_test.go:11-44 (secret, polynomial and sizes of the reference's own test);
+    every proof is checked, against the oracle and against the closed form."""
+    t = goldens["fk20_single_test"]
+    secret, poly, scale, n2 = int(t["secret"]), t["poly"], t["fft_scale"], t["n2"]
+    n = len(poly)
+    setup = cref.generate_setup_g1(secret, n2 + 1)
+    fs = kzg.FFTSettings(scale)
+    ks = kzg.KZGSettings(fs, setup)
+    fk = kzg.FK20SingleSettings(ks, n2)
+    fo = cref.FK20(scale, setup, n2)
+    cmp_g1(fk.x_ext_fft(), fo.x_ext_fft())
+    p = kzg.fr_from_ints(poly)
+    cmp_g1(ks.commit_to_poly(p), fo.commit(p))
+    proofs = fk.fk20_single(p)
+    cmp_g1(proofs, fo.fk20_single(p, da=False))
+    cmp_g1(proofs, cref.g1_mul_gen(pyref.fk20_single_exponents(poly, secret)))
+    da = fk.da_using_fk20(p)
+    cmp_g1(da, fo.fk20_single(p, da=True))
+    ext = np.concatenate([p, np.zeros_like(p)])
+    dao = fk.fk20_single_da_optimized(ext)
+    want = pyref.fk20_pipeline_exponents(pyref.FFTSettings(scale), poly, secret, True)
+    pyref.reverse_bit_order(want)                        # DAUsingFK20 minus its final permutation
+    cmp_g1(dao, cref.g1_mul_gen(want))
+    ext[n + 1, 0] = 1
+    with pytest.raises(kzg.KZGPanic):                    # fk20_single.go:150-154
+        fk.fk20_single_da_optimized(ext)
+    with pytest.raises(kzg.KZGPanic):                    # fk20_single.go:60-62
+        fk.fk20_single(p[: n // 2])
+
+
+def test_fk20_settings_panics():
+    """kzg.go:44-52, 74-91"""
+    fs = kzg.FFTSettings(4)
+    ks = kzg.KZGSettings(fs, cref.generate_setup_g1(5, 16))
+    for n2 in (32, 12, 1):
+        with pytest.raises(kzg.KZGPanic):
+            kzg.FK20SingleSettings(ks, n2)
+    for n2, l in ((16, 16), (16, 3), (16, 0)):
+        with pytest.raises(kzg.KZGPanic):
+            kzg.FK20MultiSettings(ks, n2, l)
+
+
+def test_fk20_multi_reference_test_case(goldens):
+    """fk20_multi_test.go:11-91: chunk 16 x 32 chunks, the reference's secret; all 64 coset
+    proofs against the oracle pipeline restated in the exponent."""
+    t = goldens["fk20_multi_test"]
+    secret, l, cc = int(t["secret"]), t["chunk_len"], t["chunk_count"]
+    n = l * cc
+    scale = (2 * n).bit_length() - 1
+    poly = random_fr_ints(n, 11)
+    setup = cref.generate_setup_g1(secret, 2 * n)
+    fs = kzg.FFTSettings(scale)
+    fk = kzg.FK20MultiSettings(kzg.KZGSettings(fs, setup), 2 * n, l)
+    got = fk.da_using_fk20_multi(kzg.fr_from_ints(poly))
+    want = pyref.fk20_multi_da_exponents(pyref.FFTSettings(scale), poly, secret, l)
+    cmp_g1(got, cref.g1_mul_gen(want))
+    fo = cref.FK20(scale, setup, 2 * n, l)
+    cmp_g1(fk.x_ext_fft(3), fo.x_ext_fft(3))
+    ext = kzg.fr_from_ints(poly + [0] * n)
+    nat = fk.fk20_multi_da_optimized(ext)
+    k2 = 2 * cc
+    rev = [pyref.reverse_bits_limited(k2, i) for i in range(k2)]
+    cmp_g1(nat[rev], cref.g1_mul_gen(want))
+
+
+def _setup_8192(trusted_setup_bytes):
+    s1, _ = trusted_setup_bytes
+    first = kzg.g1_from_compressed(s1)
+    rest = cref.g1_mul_gen([pow(1337, i, R) for i in range(4096, 8192)])
+    return np.concatenate([first, rest])
+
+
+def test_commit_fk20_batch_n4096(trusted_setup_bytes):
+    """configs 2 + 3 at full size: 32 blobs of 4096 coefficients over the trusted setup
+    (secret 1337, extended to 8192 points): commitments == p(s) G and all 4096 proofs of
+    sampled blobs == (p(s) - p(w^i)) / (s - w^i) G."""
+    fs = kzg.FFTSettings(13)
+    fk = kzg.FK20SingleSettings(kzg.KZGSettings(fs, _setup_8192(trusted_setup_bytes)), 8192)
+    batch = 32
+    polys = blob_polys(batch, 4096)
+    commits, proofs = fk.commit_fk20_batch(polys)
+    assert fk.last_launch_count() > 0
+    ints = [kzg.fr_to_ints(polys[b]) for b in range(batch)]
+    cmp_g1(commits, cref.g1_mul_gen([pyref.eval_poly(p, 1337) for p in ints]))
+    for b in (0, 17, 31):
+        cmp_g1(proofs[b], cref.g1_mul_gen(pyref.fk20_single_exponents(ints[b], 1337)))
+    # linearity (size independent): proofs(p0 + p1) == proofs(p0) + proofs(p1) at a few positions
+    psum = kzg.fr_from_ints([(a + b) % R for a, b in zip(ints[0], ints[1])])
+    single = fk.fk20_single(psum)           # batch of one: per-lane twiddle programs
+    L = kzg.lib()
+    for i in (0, 1, 2047, 4095):
+        s = np.zeros(18, dtype=np.uint64)
+        L.b200_g1_add(s.ctypes.data, proofs[0][i].ctypes.data, proofs[1][i].ctypes.data)
+        assert L.b200_g1_equal(s.ctypes.data, single[i].ctypes.data) == 1
