@@ -28,16 +28,29 @@ def _deps():
     return out
 
 
+def _check_ptxas(unit: str, log: str) -> None:
+    """Refuse builds in which a non-entry (ABI) device function spills: on sm_100a ptxas reports
+    such functions with a 0-byte stack frame and the spill slots landed in the caller's locals
+    (observed as silently wrong G1 butterflies).  Spills in entry functions are fine."""
+    lines = log.splitlines()
+    for i, ln in enumerate(lines):
+        if "Function properties for" in ln and i + 1 < len(lines):
+            name = ln.split("Function properties for")[1].strip()
+            props = lines[i + 1]
+            is_entry = any("Compiling entry function '%s'" % name in p for p in lines[max(0, i - 2):i])
+            if not is_entry and "0 bytes spill stores" not in props:
+                raise RuntimeError("%s: device function %s spills (%s)" % (unit, name, props.strip()))
+
+
 def _compile(unit: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
-    cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, unit), "-o", obj]
-    if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
+    cmd = [NVCC, *FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, unit), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
         raise RuntimeError("nvcc failed on " + unit)
+    _check_ptxas(unit, r.stdout + r.stderr)
     return obj
 
 

@@ -158,6 +158,7 @@ struct b200_fs {
     std::mutex mu;
     // twiddle programs for the G1 FFT: [inverse][mode], max_width / 2 entries each, built lazily
     ScalarProgram* progs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    Fr* d_shift[2] = {nullptr, nullptr};   // 5^-i and 5^i, i < max_width (recovery), built lazily
 };
 
 static Fr fr_inv_of_u64(uint64_t v) { return fe_inv(fr_from_u64(v)); }   // Montgomery in, Montgomery out
@@ -208,6 +209,7 @@ extern "C" void b200_fft_settings_free(b200_fs* fs) {
     cudaSetDevice(fs->device);
     cudaFree(fs->dom.expanded); cudaFree(fs->dom.reverse); cudaFree(fs->dom.tw_fwd); cudaFree(fs->dom.tw_inv);
     for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) cudaFree(fs->progs[a][b]);
+    cudaFree(fs->d_shift[0]); cudaFree(fs->d_shift[1]);
     delete fs;
 }
 extern "C" uint64_t b200_fs_max_width(const b200_fs* fs) { return fs->max_width; }
@@ -293,14 +295,159 @@ extern "C" int b200_das_fft_extension_batch(b200_fs* fs, uint64_t* vals, size_t 
 }
 extern "C" int b200_das_fft_extension(b200_fs* fs, uint64_t* vals, size_t n) { return b200_das_fft_extension_batch(fs, vals, n, 1); }
 
-// ------------------------------------------------------------------------------ recovery (next milestone)
-extern "C" int b200_zero_poly_via_multiplication(b200_fs*, const uint64_t*, size_t, size_t, uint64_t*, uint64_t*) {
-    g_cuda_err = "ZeroPolyViaMultiplication: device path not built yet";
-    return B200_ERR_CUDA;
+// ------------------------------------------------------------------------------ zero poly / recovery
+// Length bookkeeping of zero_poly.go:116-217 replayed on the host: the device computes the same
+// polynomial by another exact route, so the cases in which the reference *panics* (slice bounds,
+// "expected larger destination length", "expected output smaller or equal to input length") have
+// to be reproduced from the sizes alone.  Returns false where the reference would panic.
+static bool zero_poly_sizes_ok(size_t nmiss, size_t length) {
+    const size_t per_leaf = 63, per_leaf_poly = 64;
+    if (nmiss <= per_leaf) return nmiss + 1 <= length;           // zero_poly.go:133 make(len > cap) panics
+    size_t leaf_count = (nmiss + per_leaf - 1) / per_leaf;
+    size_t n = next_pow2(leaf_count * per_leaf_poly);
+    std::vector<size_t> len(leaf_count, per_leaf_poly);
+    size_t nleaves = leaf_count;
+    while (nleaves > 1) {
+        size_t reduced_count = (nleaves + 3) / 4, leaf_size = next_pow2(len[0]);
+        for (size_t i = 0; i < reduced_count; i++) {
+            size_t start = i * 4, end = start + 4, out_end = end * leaf_size;
+            if (out_end > n) out_end = n;
+            if (start * leaf_size > out_end) return false;         // zero_poly.go:190 slice bounds
+            size_t rlen = out_end - start * leaf_size;
+            if (end > nleaves) end = nleaves;
+            if (end > start + 1) {
+                size_t deg = 0;
+                for (size_t q = start; q < end; q++) deg += len[q] - 1;
+                if (!is_pow2(rlen) || deg + 1 > rlen) return false;   // zero_poly.go:60-76
+                rlen = deg + 1;
+            }
+            len[i] = rlen;
+        }
+        nleaves = reduced_count;
+    }
+    return len[0] <= length;                                       // zero_poly.go:207-209
 }
-extern "C" int b200_recover_poly_from_samples_batch(b200_fs*, const uint64_t*, const uint8_t*, size_t, size_t, uint64_t*) {
-    g_cuda_err = "RecoverPolyFromSamples: device path not built yet";
-    return B200_ERR_CUDA;
+
+// device side: zero_eval[b] and zero_poly[b] (Montgomery) for `batch` missing lists
+static int dev_zero_poly(b200_fs* fs, const std::vector<uint32_t>& h_missing, const std::vector<uint32_t>& h_nmiss, size_t pitch,
+                         size_t n, size_t batch, Fr* d_zero_eval, Fr* d_zero_poly, cudaStream_t st) {
+    size_t max_missing = 0;
+    for (size_t b = 0; b < batch; b++) if (h_nmiss[b] > max_missing) max_missing = h_nmiss[b];
+    DevBuf miss, cnt, partial;
+    CKS(miss.alloc(h_missing.size() * 4, st)); CKS(cnt.alloc(batch * 4, st));
+    CKS(partial.alloc(batch * zero_eval_segments(max_missing) * n * sizeof(Fr), st));
+    CK(cudaMemcpyAsync(miss.p, h_missing.data(), h_missing.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cnt.p, h_nmiss.data(), batch * 4, cudaMemcpyHostToDevice, st));
+    launch_zero_eval(fs->dom, n, batch, miss.as<uint32_t>(), cnt.as<uint32_t>(), pitch, max_missing, partial.as<Fr>(), d_zero_eval, st);
+    CKS(check_launches());
+    CKS(dev_fr_fft(fs, d_zero_eval, d_zero_poly, log2u(n), batch, true, st));
+    CK(cudaStreamSynchronize(st));   // h_missing / h_nmiss are the caller's stack vectors
+    return B200_OK;
+}
+
+extern "C" int b200_zero_poly_via_multiplication(b200_fs* fs, const uint64_t* missing, size_t n_missing, size_t length,
+                                                 uint64_t* zero_eval, uint64_t* zero_poly) {
+    if (n_missing == 0) {                                          // zero_poly.go:117-119
+        memset(zero_eval, 0, length * 32); memset(zero_poly, 0, length * 32);
+        return B200_OK;
+    }
+    if (length > fs->max_width) return B200_ERR_TOO_SMALL;         // zero_poly.go:120-122 "domain too small"
+    if (!is_pow2(length)) return B200_ERR_NOT_POW2;                // zero_poly.go:123-125
+    const uint64_t stride = fs->max_width / length;
+    std::vector<uint32_t> m(n_missing), cnt(1, (uint32_t)n_missing);
+    for (size_t i = 0; i < n_missing; i++) {
+        if (missing[i] * stride > fs->max_width) return B200_ERR_BAD_INPUT;   // root table index out of range
+        m[i] = (uint32_t)(missing[i] % length);                    // w^(length stride) == w^0
+    }
+    if (!zero_poly_sizes_ok(n_missing, length)) return B200_ERR_BAD_INPUT;
+    CK(cudaSetDevice(fs->device));
+    cudaStream_t st = nullptr;
+    DevBuf ze, zp, raw;
+    CKS(ze.alloc(length * sizeof(Fr), st)); CKS(zp.alloc(length * sizeof(Fr), st)); CKS(raw.alloc(2 * length * 32, st));
+    CKS(dev_zero_poly(fs, m, cnt, n_missing, length, 1, ze.as<Fr>(), zp.as<Fr>(), st));
+    launch_fr_from_mont(ze.as<Fr>(), raw.as<uint64_t>(), length, st);
+    launch_fr_from_mont(zp.as<Fr>(), raw.as<uint64_t>() + 4 * length, length, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(zero_eval, raw.p, length * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(zero_poly, raw.as<uint64_t>() + 4 * length, length * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// powers of the coset shift factor 5 (recover_from_samples.go:9-40): [0] = 5^-i, [1] = 5^i, i < max_width
+static int fs_shift_tables(b200_fs* fs, const Fr** inv_pows, const Fr** pows) {
+    std::lock_guard<std::mutex> lk(fs->mu);
+    if (!fs->d_shift[0]) {
+        const uint64_t W = fs->max_width;
+        std::vector<Fr> t(W);
+        for (int which = 0; which < 2; which++) {
+            Fr f = fr_from_u64(5);
+            if (which == 0) f = fe_inv(f);
+            Fr p = Fr::one();
+            for (uint64_t i = 0; i < W; i++) { t[i] = p; p = fe_mul(p, f); }
+            CK(cudaMalloc(&fs->d_shift[which], W * sizeof(Fr)));
+            CK(cudaMemcpy(fs->d_shift[which], t.data(), W * sizeof(Fr), cudaMemcpyHostToDevice));
+        }
+    }
+    *inv_pows = fs->d_shift[0]; *pows = fs->d_shift[1];
+    return B200_OK;
+}
+
+extern "C" int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t* samples, const uint8_t* present, size_t n,
+                                                    size_t batch, uint64_t* out) {
+    if (batch == 0) return B200_OK;
+    // missing index lists (recover_from_samples.go:45-50)
+    std::vector<uint32_t> miss(batch * n), cnt(batch);
+    for (size_t b = 0; b < batch; b++) {
+        uint32_t c = 0;
+        for (size_t i = 0; i < n; i++) if (!present[b * n + i]) miss[b * n + c++] = (uint32_t)i;
+        cnt[b] = c;
+    }
+    for (size_t b = 0; b < batch; b++) {
+        // nothing missing: zeroPolyFn returns all zeros and the sanity loop panics (recover_from_samples.go:54-58)
+        if (cnt[b] == 0) return n == 0 ? B200_OK : B200_ERR_ZERO_EVAL;
+    }
+    if (n > fs->max_width) return B200_ERR_TOO_SMALL;              // zero_poly.go:120-122
+    if (!is_pow2(n)) return B200_ERR_NOT_POW2;                     // zero_poly.go:123-125
+    for (size_t b = 0; b < batch; b++) if (!zero_poly_sizes_ok(cnt[b], n)) return B200_ERR_BAD_INPUT;
+    CK(cudaSetDevice(fs->device));
+    const Fr *shift_inv, *shift_fwd;
+    CKS(fs_shift_tables(fs, &shift_inv, &shift_fwd));
+    const unsigned logn = log2u(n);
+    const size_t total = batch * n;
+    cudaStream_t st = nullptr;
+    DevBuf raw, s, ze, zp, a, c, pres, flags;
+    CKS(raw.alloc(total * 32, st)); CKS(s.alloc(total * sizeof(Fr), st)); CKS(ze.alloc(total * sizeof(Fr), st));
+    CKS(zp.alloc(total * sizeof(Fr), st)); CKS(a.alloc(total * sizeof(Fr), st)); CKS(c.alloc(total * sizeof(Fr), st));
+    CKS(pres.alloc(total, st)); CKS(flags.alloc(batch * 4, st));
+    CK(cudaMemcpyAsync(raw.p, samples, total * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pres.p, present, total, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(flags.p, 0, batch * 4, st));
+    launch_fr_to_mont(raw.as<uint64_t>(), s.as<Fr>(), total, st);
+    CKS(dev_zero_poly(fs, miss, cnt, n, n, batch, ze.as<Fr>(), zp.as<Fr>(), st));
+    launch_fr_mul_masked(a.as<Fr>(), s.as<Fr>(), ze.as<Fr>(), pres.as<uint8_t>(), total, st);   // E = samples (.) zeroEval
+    CKS(dev_fr_fft(fs, a.as<Fr>(), a.as<Fr>(), logn, batch, true, st));                            // polyWithZero
+    launch_fr_mul_table(a.as<Fr>(), shift_inv, n, batch, st);                                      // ShiftPoly
+    launch_fr_mul_table(zp.as<Fr>(), shift_inv, n, batch, st);
+    CKS(dev_fr_fft(fs, a.as<Fr>(), a.as<Fr>(), logn, batch, false, st));                           // evalShiftedPolyWithZero
+    CKS(dev_fr_fft(fs, zp.as<Fr>(), c.as<Fr>(), logn, batch, false, st));                          // evalShiftedZeroPoly
+    launch_fr_div(a.as<Fr>(), c.as<Fr>(), total, st);                                              // :89-91
+    CKS(dev_fr_fft(fs, a.as<Fr>(), a.as<Fr>(), logn, batch, true, st));
+    launch_fr_mul_table(a.as<Fr>(), shift_fwd, n, batch, st);                                      // UnshiftPoly
+    CKS(dev_fr_fft(fs, a.as<Fr>(), a.as<Fr>(), logn, batch, false, st));                           // reconstructedData
+    launch_recover_check(a.as<Fr>(), s.as<Fr>(), ze.as<Fr>(), pres.as<uint8_t>(), n, batch, flags.as<uint32_t>(), st);
+    launch_fr_from_mont(a.as<Fr>(), raw.as<uint64_t>(), total, st);
+    CKS(check_launches());
+    std::vector<uint32_t> h_flags(batch);
+    CK(cudaMemcpyAsync(h_flags.data(), flags.p, batch * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t b = 0; b < batch; b++) {
+        if (h_flags[b] & 2) return B200_ERR_ZERO_EVAL;             // recover_from_samples.go:54-58 (panic)
+        if (h_flags[b] & 1) return B200_ERR_RECOVERY;              // recover_from_samples.go:103-107 (error)
+    }
+    CK(cudaMemcpyAsync(out, raw.p, total * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
 }
 extern "C" int b200_recover_poly_from_samples(b200_fs* fs, const uint64_t* s, const uint8_t* p, size_t n, uint64_t* out) {
     return b200_recover_poly_from_samples_batch(fs, s, p, n, 1, out);
@@ -411,6 +558,7 @@ extern "C" int b200_g1_mul_many(const uint64_t* points, const uint64_t* scalars,
 
 // ------------------------------------------------------------------------------ KZGSettings
 struct b200_ks {
+    int device = 0;
     b200_fs* fs = nullptr;
     size_t n_g1 = 0;
     G1J* d_secret_g1 = nullptr;   // Montgomery Jacobian
@@ -423,7 +571,7 @@ extern "C" int b200_kzg_settings_new(b200_fs* fs, const uint64_t* secret_g1, siz
     CK(cudaSetDevice(fs->device));
     b200_ks* ks = new (std::nothrow) b200_ks();
     if (!ks) return B200_ERR_CUDA;
-    ks->fs = fs; ks->n_g1 = n_g1;
+    ks->fs = fs; ks->n_g1 = n_g1; ks->device = fs->device;
     cudaStream_t st = nullptr;
     DevBuf raw;
     int rc = raw.alloc(n_g1 * 144, st);
@@ -441,7 +589,7 @@ extern "C" int b200_kzg_settings_new(b200_fs* fs, const uint64_t* secret_g1, siz
 }
 extern "C" void b200_kzg_settings_free(b200_ks* ks) {
     if (!ks) return;
-    cudaSetDevice(ks->fs->device);
+    cudaSetDevice(ks->device);
     cudaFree(ks->d_secret_g1);
     delete ks;
 }
@@ -468,6 +616,7 @@ extern "C" int b200_commit_to_poly(b200_ks* ks, const uint64_t* coeffs, size_t n
 
 // ------------------------------------------------------------------------------ FK20
 struct b200_fk {
+    int device = 0;
     b200_ks* ks = nullptr;
     size_t n2 = 0, chunk_len = 1;
     G1J* d_x_ext_fft = nullptr;   // [chunk_len][n2 / chunk_len], natural order (kzg.go:62,110-114)
@@ -488,7 +637,7 @@ static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk**
     const unsigned logk2 = log2u(k2);
     b200_fk* fk = new (std::nothrow) b200_fk();
     if (!fk) return B200_ERR_CUDA;
-    fk->ks = ks; fk->n2 = n2; fk->chunk_len = l;
+    fk->ks = ks; fk->n2 = n2; fk->chunk_len = l; fk->device = fs->device;
     cudaStream_t st = nullptr;
     int rc = B200_OK;
     do {
@@ -515,7 +664,7 @@ extern "C" int b200_fk20_multi_settings_new(b200_ks* ks, size_t n2, size_t chunk
 }
 extern "C" void b200_fk20_settings_free(b200_fk* fk) {
     if (!fk) return;
-    cudaSetDevice(fk->ks->fs->device);
+    cudaSetDevice(fk->device);
     cudaFree(fk->d_x_ext_fft);
     delete fk;
 }
@@ -700,14 +849,42 @@ extern "C" int b200_selftest_field(size_t n, uint64_t seed, uint64_t* mismatches
     if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
     CK(cudaSetDevice(g_device));
     unsigned long long* d = nullptr;
-    CK(cudaMalloc(&d, 8));
-    CK(cudaMemset(d, 0, 8));
-    launch_selftest(n, seed, d, nullptr);
+    CK(cudaMalloc(&d, 17 * 8));
+    CK(cudaMemset(d, 0, 17 * 8));
+    G1J* scratch = nullptr;
+    CK(cudaMalloc(&scratch, (n ? 4 * n : 1) * sizeof(G1J)));
+    launch_selftest(n, seed, d, scratch, nullptr);
     int rc = check_launches();
-    unsigned long long h = 0;
-    if (!rc && cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { g_cuda_err = cudaGetErrorString(cudaGetLastError()); rc = B200_ERR_CUDA; }
+    cudaDeviceSynchronize();
+    cudaFree(scratch);
+    {   // host-recoded programs (both modes) for pseudo-random scalars and a few structured ones
+        const size_t np = 256;
+        std::vector<ScalarProgram> progs(np);
+        std::vector<Fr> ks(np);
+        uint64_t s = seed ^ 0xD1B54A32D192ED03ULL;
+        for (size_t i = 0; i < np; i++) {
+            Fr k;
+            for (int j = 0; j < 8; j++) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; k.l[j] = (uint32_t)(s >> 32); }
+            k.l[7] &= 0x3fffffffu;
+            if (i < 32) k = fe_from_mont(fe_to_mont(fr_scale2_root_canon((unsigned)i)));   // the 2-adic roots of unity
+            if (i == 32) { k = Fr::zero(); k.l[0] = 1; }
+            if (i == 33) k = Fr::zero();
+            ks[i] = k;
+            make_scalar_program(&progs[i], k, (int)(i & 1));
+        }
+        ScalarProgram* dp = nullptr; Fr* dk = nullptr;
+        CK(cudaMalloc(&dp, np * sizeof(ScalarProgram))); CK(cudaMalloc(&dk, np * sizeof(Fr)));
+        CK(cudaMemcpy(dp, progs.data(), np * sizeof(ScalarProgram), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dk, ks.data(), np * sizeof(Fr), cudaMemcpyHostToDevice));
+        launch_selftest_programs(np, dp, dk, d, nullptr);
+        if (!rc) rc = check_launches();
+        cudaDeviceSynchronize();
+        cudaFree(dp); cudaFree(dk);
+    }
+    unsigned long long h[17] = {0};
+    if (!rc && cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) { g_cuda_err = cudaGetErrorString(cudaGetLastError()); rc = B200_ERR_CUDA; }
     cudaFree(d);
-    *mismatches = h;
+    for (int i = 0; i < 17; i++) mismatches[i] = h[i];
     return rc;
 }
 // Fp multiplication throughput probe: `threads` lanes x `iters` x 2 dependent Montgomery products;

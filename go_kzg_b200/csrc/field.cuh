@@ -133,7 +133,7 @@ struct FrParams {
 // the caller's business: add/sub are representation agnostic, mul divides by R.
 // ---------------------------------------------------------------------------------------
 template <class P>
-struct Fe {
+struct alignas(16) Fe {   // 16 B alignment: elements move as uint4 vectors, also through local memory
     static constexpr int N = P::N;
     uint32_t l[N];
 
@@ -343,27 +343,20 @@ typedef Fe<FpParams> Fp;
 typedef Fe<FrParams> Fr;
 
 #ifdef __CUDACC__
-// 16-byte vector load/store of field elements and points (all device arrays are 16 B aligned:
-// sizeof(Fr) = 32, sizeof(G1A) = 96, sizeof(G1J) = 144).
+// Whole-element loads / stores.  Fe (and everything built from it) is alignas(16), so a plain
+// struct copy lowers to 128-bit vector accesses (LDG.128 / STS.128 / ...).  Do NOT reinterpret
+// elements as uint4: that breaks the aliasing rules and nvcc then reorders / drops the copies
+// (observed: the first 16 bytes of a point silently not copied).
 template <class T>
 __device__ __forceinline__ T ld_vec(const T* p) {
-    static_assert(sizeof(T) % 16 == 0, "16 B multiple");
-    T r;
-    const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint4* d = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
-    return r;
+    static_assert(alignof(T) >= 16 && sizeof(T) % 16 == 0, "16 B aligned element");
+    return *p;
 }
 template <class T>
 __device__ __forceinline__ void st_vec(T* p, const T& v) {
-    static_assert(sizeof(T) % 16 == 0, "16 B multiple");
-    uint4* d = reinterpret_cast<uint4*>(p);
-    const uint4* s = reinterpret_cast<const uint4*>(&v);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+    static_assert(alignof(T) >= 16 && sizeof(T) % 16 == 0, "16 B aligned element");
+    *p = v;
 }
-
 #endif
 
 }  // namespace b200

@@ -11,13 +11,18 @@
 namespace b200 {
 
 // ---- out-of-line group law ---------------------------------------------------------------
-static __device__ __noinline__ void g1_dbl_ni(G1J* r, const G1J* p) { *r = g1_dbl(*p); }
-static __device__ __noinline__ void g1_add_ni(G1J* r, const G1J* p, const G1J* q) { *r = g1_add(*p, *q); }
-static __device__ __noinline__ void g1_add_mixed_ni(G1J* r, const G1J* p, const G1A* q) { *r = g1_add_mixed(*p, *q); }
-static __device__ __noinline__ void g1_add_sub_ni(G1J* sum, G1J* diff, const G1J* x, const G1J* t) {
-    G1J s, d;
-    g1_add_sub(*x, *t, s, d);
-    *sum = s; *diff = d;
+static __host__ __device__ __noinline__ void g1_dbl_ni(G1J* r, const G1J* p) { *r = g1_dbl(*p); }
+static __host__ __device__ __noinline__ void g1_add_ni(G1J* r, const G1J* p, const G1J* q) { *r = g1_add(*p, *q); }
+static __host__ __device__ __noinline__ void g1_add_mixed_ni(G1J* r, const G1J* p, const G1A* q) { *r = g1_add_mixed(*p, *q); }
+// (x + t, x - t): the radix-2 butterfly of fft_g1.go:52-54 as two out-of-line additions.
+// (A fused form sharing the common subexpressions saves 14 of ~1700 multiplications per butterfly
+// but needs more live registers than an ABI function gets; ptxas then spills inside a frameless
+// device function, which corrupted the caller's locals on sm_100a -- see DESIGN.md.)
+__host__ __device__ __forceinline__ void g1_add_sub_ni(G1J* sum, G1J* diff, const G1J* x, const G1J* t) {
+    G1J nt = g1_neg(*t), s;
+    g1_add_ni(&s, x, t);
+    g1_add_ni(diff, x, &nt);
+    *sum = s;
 }
 
 // ---- digit-programmed scalar multiplication ----------------------------------------------
@@ -29,8 +34,10 @@ static __device__ __noinline__ void g1_add_sub_ni(G1J* sum, G1J* diff, const G1J
 //   mode 1  width-5 NAF, odd digits in [-15, 15]: fewest additions, used when the whole warp
 //           shares one fixed scalar (batched G1 FFT: lanes = blobs).  table = {1,3,..,15} P
 // z^2 (x, y) = (beta x, -y).
-__device__ __forceinline__ void g1_mul_digits(G1J* out, const G1J* p, const int8_t* d1, const int8_t* d2, int top,
-                                              int mode) {
+// Out of line on purpose: with this body inlined next to the call that produced *p, nvcc 12.9
+// emitted the copy `tab[0] = *p` without its first 16 bytes (wrong twiddle products).
+static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* p, const int8_t* d1, const int8_t* d2, int top,
+                                                            int mode) {
     if (top < 0 || p->is_inf()) { *out = G1J::infinity(); return; }
     G1J tab[8];
     Fp bx[8];
@@ -75,7 +82,7 @@ __device__ __forceinline__ void g1_mul_digits(G1J* out, const G1J* p, const int8
     *out = acc;
 }
 
-__device__ __forceinline__ void g1_mul_program(G1J* out, const G1J* p, const ScalarProgram* prog) {
+__host__ __device__ __forceinline__ void g1_mul_program(G1J* out, const G1J* p, const ScalarProgram* prog) {
     int top = prog->top;
     if (prog->is_one) { *out = *p; return; }
     g1_mul_digits(out, p, prog->d1, prog->d2, top, prog->mode);
@@ -90,14 +97,14 @@ struct LaneDigits {
     int top;
 };
 
-__device__ __forceinline__ bool u128_ge(const uint32_t a[4], const uint32_t b[4]) {
+__host__ __device__ __forceinline__ bool u128_ge(const uint32_t a[4], const uint32_t b[4]) {
     for (int i = 3; i >= 0; i--) {
         if (a[i] > b[i]) return true;
         if (a[i] < b[i]) return false;
     }
     return true;
 }
-__device__ __forceinline__ void window4_recode(const uint32_t v_in[4], int8_t* out, int& top) {
+__host__ __device__ __forceinline__ void window4_recode(const uint32_t v_in[4], int8_t* out, int& top) {
     uint32_t v[5] = {v_in[0], v_in[1], v_in[2], v_in[3], 0};
     uint32_t carry = 0;
     for (int w = 0; w < 33; w++) {
@@ -108,7 +115,7 @@ __device__ __forceinline__ void window4_recode(const uint32_t v_in[4], int8_t* o
         if (dd != 0 && 4 * w > top) top = 4 * w;
     }
 }
-static __device__ __noinline__ void g1_recode_scalar(LaneDigits* ld, const uint32_t* k) {
+static __host__ __device__ __noinline__ void g1_recode_scalar(LaneDigits* ld, const uint32_t* k) {
     constexpr uint32_t z2[4] = B200_GLV_Z2;
     uint32_t rem[4] = {0, 0, 0, 0}, quo[4] = {0, 0, 0, 0};
     for (int bit = 255; bit >= 0; bit--) {
@@ -138,7 +145,7 @@ static __device__ __noinline__ void g1_recode_scalar(LaneDigits* ld, const uint3
 }
 
 // k * P for a per-lane scalar (canonical limbs)
-__device__ __forceinline__ void g1_mul_var(G1J* out, const G1J* p, const uint32_t* k_canon) {
+__host__ __device__ __forceinline__ void g1_mul_var(G1J* out, const G1J* p, const uint32_t* k_canon) {
     LaneDigits ld;
     g1_recode_scalar(&ld, k_canon);
     g1_mul_digits(out, p, ld.d1, ld.d2, ld.top, 0);

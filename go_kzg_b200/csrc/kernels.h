@@ -48,6 +48,16 @@ void launch_fr_ntt(const FrDomain& dom, const Fr* in, Fr* out, Fr* tmp, unsigned
                    const Fr* scale_or_null, cudaStream_t st);
 // das_extension.go:71-84 in place on Montgomery values [batch][2^logn]; inv_n = (2^logn)^-1 (Montgomery)
 void launch_das_fft_extension(const FrDomain& dom, Fr* vals, unsigned logn, size_t batch, const Fr& inv_n, cudaStream_t st);
+// zero_poly.go:116-217 (evaluation side): zero_eval[b][j] = prod_i (w^j - w^missing[b][i]) for j < n;
+// missing: [batch][miss_pitch] u32 indices, nmiss[b] of them valid; partial: [batch][segments][n] scratch
+size_t zero_eval_segments(size_t max_missing);
+void launch_zero_eval(const FrDomain& dom, size_t n, size_t batch, const uint32_t* d_missing, const uint32_t* d_nmiss,
+                      size_t miss_pitch, size_t max_missing, Fr* partial, Fr* zero_eval, cudaStream_t st);
+void launch_fr_mul_masked(Fr* dst, const Fr* a, const Fr* c, const uint8_t* present, size_t total, cudaStream_t st);
+void launch_fr_mul_table(Fr* v, const Fr* table, size_t n, size_t batch, cudaStream_t st);   // v[b][i] *= table[i]
+void launch_fr_div(Fr* a, const Fr* c, size_t total, cudaStream_t st);                        // a[i] /= c[i]  (x / 0 = 0)
+void launch_recover_check(const Fr* rec, const Fr* samples, const Fr* zero_eval, const uint8_t* present, size_t n, size_t batch,
+                          uint32_t* flags, cudaStream_t st);
 // fk20_single.go:106-119 toeplitzCoeffsStep over a batch: poly[b][n] canonical -> out[b][2n] Montgomery
 void launch_toeplitz_coeffs(const uint64_t* polys_canon, Fr* out, size_t n, size_t batch, cudaStream_t st);
 // fk20_single.go:89-103 toeplitzCoeffsStepStrided for every offset: out[b][off][2k] Montgomery
@@ -85,7 +95,8 @@ void launch_g1_copy(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J*
 // the rest of work (pre-filled) stays infinity
 void launch_fk20_gather_x(const G1J* secret_g1, G1J* work, size_t n, size_t l, cudaStream_t st);
 // self test: device field + group law against portable forms; returns mismatches
-void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, cudaStream_t st);
+void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, G1J* d_scratch /* 4 n points */, cudaStream_t st);
+void launch_selftest_programs(size_t n, const ScalarProgram* progs, const Fr* scalars_canon, unsigned long long* d_mismatch, cudaStream_t st);
 // throughput probe: `iters` dependent Fp multiplications per thread
 void launch_fp_mul_probe(uint32_t* d_buf, size_t threads, int iters, cudaStream_t st);
 

@@ -307,6 +307,132 @@ void launch_das_fft_extension(const FrDomain& dom, Fr* vals, unsigned logn, size
     for (size_t L = 2 * B; L <= n; L <<= 1) { k_das_level<true><<<lgrid, 256, 0, st>>>(vals, n, L, dom.expanded, L == n ? 1 : 0, inv_n); g_launch_count++; }
 }
 
+// ------------------------------------------------------------------------------ zero polynomial
+// zero_poly.go:116-217 computes Z(X) = prod_i (X - w^{m_i}) over the missing indices with a leaf /
+// FFT-convolution tree and then evaluates it.  The result is a uniquely determined polynomial,
+// so the device takes the shortest exact route instead: evaluate the product directly,
+//      zeroEval[j] = prod_i (w^j - w^{m_i}),
+// every (j, root-segment) pair in parallel with the segment's roots staged in shared memory, and
+// recover the coefficients with one inverse NTT (deg Z < length whenever the reference does not
+// panic).  Same field elements, hence the same bytes.
+#define ZP_SEG 512
+__global__ void __launch_bounds__(256) k_zero_eval_partial(const Fr* __restrict__ expanded, size_t stride, size_t n,
+                                                           const uint32_t* __restrict__ missing, const uint32_t* __restrict__ nmiss,
+                                                           size_t miss_pitch, Fr* __restrict__ partial, size_t nseg) {
+    __shared__ uint4 roots_raw[ZP_SEG * 2];
+    Fr* roots = reinterpret_cast<Fr*>(roots_raw);
+    const size_t b = blockIdx.z, seg = blockIdx.y;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cnt_all = nmiss[b];
+    const size_t lo = seg * ZP_SEG;
+    const uint32_t cnt = lo >= cnt_all ? 0u : (cnt_all - lo > ZP_SEG ? (uint32_t)ZP_SEG : (uint32_t)(cnt_all - lo));
+    for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x)
+        st_vec(roots + i, ld_vec(expanded + (size_t)missing[b * miss_pitch + lo + i] * stride));
+    __syncthreads();
+    if (j >= n) return;
+    const Fr x = ld_vec(expanded + j * stride);
+    Fr acc = Fr::one();
+    for (unsigned i = 0; i < cnt; i++) acc = fe_mul(acc, fe_sub(x, ld_vec(roots + i)));
+    st_vec(partial + (b * nseg + seg) * n + j, acc);
+}
+__global__ void k_zero_eval_combine(const Fr* __restrict__ partial, Fr* __restrict__ zero_eval, size_t n, size_t nseg,
+                                    const uint32_t* __restrict__ nmiss) {
+    const size_t b = blockIdx.y;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (nmiss[b] == 0) { st_vec(zero_eval + b * n + j, Fr::zero()); return; }   // zero_poly.go:117-119
+    Fr acc = ld_vec(partial + (b * nseg) * n + j);
+    for (size_t s = 1; s < nseg; s++) acc = fe_mul(acc, ld_vec(partial + (b * nseg + s) * n + j));
+    st_vec(zero_eval + b * n + j, acc);
+}
+void launch_zero_eval(const FrDomain& dom, size_t n, size_t batch, const uint32_t* d_missing, const uint32_t* d_nmiss,
+                      size_t miss_pitch, size_t max_missing, Fr* partial, Fr* zero_eval, cudaStream_t st) {
+    ProfScope prof_scope(PROF_FR_NTT, st);
+    if (!n || !batch) return;
+    size_t nseg = (max_missing + ZP_SEG - 1) / ZP_SEG;
+    if (nseg == 0) nseg = 1;
+    dim3 g1((unsigned)((n + 255) / 256), (unsigned)nseg, (unsigned)batch);
+    k_zero_eval_partial<<<g1, 256, 0, st>>>(dom.expanded, dom.max_width / n, n, d_missing, d_nmiss, miss_pitch, partial, nseg);
+    dim3 g2((unsigned)((n + 255) / 256), (unsigned)batch);
+    k_zero_eval_combine<<<g2, 256, 0, st>>>(partial, zero_eval, n, nseg, d_nmiss);
+    g_launch_count += 2;
+}
+size_t zero_eval_segments(size_t max_missing) { size_t s = (max_missing + ZP_SEG - 1) / ZP_SEG; return s ? s : 1; }
+
+// ------------------------------------------------------------------------------ recovery helpers
+// dst[b][i] = present[b][i] ? a[b][i] * c[b][i] : 0          recover_from_samples.go:60-67
+__global__ void k_fr_mul_masked(Fr* dst, const Fr* a, const Fr* c, const uint8_t* __restrict__ present, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    Fr v = Fr::zero();
+    if (present[i]) v = fe_mul(ld_vec(a + i), ld_vec(c + i));
+    st_vec(dst + i, v);
+}
+void launch_fr_mul_masked(Fr* dst, const Fr* a, const Fr* c, const uint8_t* present, size_t total, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!total) return;
+    k_fr_mul_masked<<<grid_for(total, 256), 256, 0, st>>>(dst, a, c, present, total); g_launch_count++;
+}
+// v[b][i] *= table[i]     (ShiftPoly / UnshiftPoly with precomputed powers, recover_from_samples.go:9-40)
+__global__ void k_fr_mul_table(Fr* v, const Fr* __restrict__ table, size_t n, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    st_vec(v + i, fe_mul(ld_vec(v + i), ld_vec(table + (i % n))));
+}
+void launch_fr_mul_table(Fr* v, const Fr* table, size_t n, size_t batch, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n || !batch) return;
+    k_fr_mul_table<<<grid_for(n * batch, 256), 256, 0, st>>>(v, table, n, n * batch); g_launch_count++;
+}
+// a[i] = a[i] / c[i] with Montgomery's trick over DIV_CHUNK consecutive elements per lane: one
+// Fermat inversion per chunk instead of one per element (the reference inverts every element,
+// recover_from_samples.go:89-91 / bls/bignum_kilic.go:103-107; x / 0 = 0 there as here).
+#define DIV_CHUNK 16
+__global__ void __launch_bounds__(128) k_fr_div(Fr* a, const Fr* __restrict__ c, size_t total) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * DIV_CHUNK;
+    if (lo >= total) return;
+    size_t cnt = total - lo < DIV_CHUNK ? total - lo : DIV_CHUNK;
+    Fr pre[DIV_CHUNK];
+    Fr acc = Fr::one();
+    for (size_t i = 0; i < cnt; i++) {
+        pre[i] = acc;
+        Fr d = ld_vec(c + lo + i);
+        if (!d.is_zero()) acc = fe_mul(acc, d);
+    }
+    acc = fe_inv(acc);
+    for (size_t i = cnt; i-- > 0;) {
+        Fr d = ld_vec(c + lo + i);
+        if (d.is_zero()) { st_vec(a + lo + i, Fr::zero()); continue; }
+        Fr inv = fe_mul(acc, pre[i]);
+        acc = fe_mul(acc, d);
+        st_vec(a + lo + i, fe_mul(ld_vec(a + lo + i), inv));
+    }
+}
+void launch_fr_div(Fr* a, const Fr* c, size_t total, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!total) return;
+    k_fr_div<<<grid_for((total + DIV_CHUNK - 1) / DIV_CHUNK, 128), 128, 0, st>>>(a, c, total); g_launch_count++;
+}
+// flags[b] |= 1 if a known sample changed (recover_from_samples.go:103-107);
+// flags[b] |= 2 if zeroEval[i] == 0 disagrees with "missing" (recover_from_samples.go:54-58)
+__global__ void k_recover_check(const Fr* __restrict__ rec, const Fr* __restrict__ samples, const Fr* __restrict__ zero_eval,
+                                const uint8_t* __restrict__ present, size_t n, size_t total, uint32_t* flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    unsigned f = 0;
+    bool pr = present[i] != 0;
+    if (pr && ld_vec(rec + i) != ld_vec(samples + i)) f |= 1;
+    if ((!pr) != ld_vec(zero_eval + i).is_zero()) f |= 2;
+    if (f) atomicOr(flags + i / n, f);
+}
+void launch_recover_check(const Fr* rec, const Fr* samples, const Fr* zero_eval, const uint8_t* present, size_t n, size_t batch,
+                          uint32_t* flags, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n || !batch) return;
+    k_recover_check<<<grid_for(n * batch, 256), 256, 0, st>>>(rec, samples, zero_eval, present, n, n * batch, flags); g_launch_count++;
+}
+
 // ------------------------------------------------------------------------------ Toeplitz gathers
 // fk20_single.go:106-119: [p[n-1], 0 x (n+1), p[1..n-2]]
 __global__ void k_toeplitz_coeffs(const uint64_t* __restrict__ polys, Fr* __restrict__ out, size_t n, size_t batch) {

@@ -212,47 +212,88 @@ __device__ uint32_t st_rand(uint64_t& s) {
     s = s * 6364136223846793005ULL + 1442695040888963407ULL;
     return (uint32_t)(s >> 32);
 }
-__global__ void k_selftest(size_t n, uint64_t seed, unsigned long long* mismatch) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// The self test is split into small kernels that hand points over through global memory: one
+// large kernel holding many 144-byte locals triggered wrong stack-slot sharing in nvcc 12.9
+// (a live point overwritten by a later temporary), see DESIGN.md "compiler notes".
+__device__ __forceinline__ void st_scalars(size_t i, uint64_t seed, Fp& a, Fp& b, Fr& c, Fr& d) {
     uint64_t s = seed + 0x9E3779B97F4A7C15ULL * (i + 1);
-    unsigned bad = 0;
-    Fp a, b;
     for (int k = 0; k < 12; k++) { a.l[k] = st_rand(s); b.l[k] = st_rand(s); }
     a.l[11] &= 0x0fffffffu; b.l[11] &= 0x0fffffffu;
     if (i % 5 == 0) for (int k = 0; k < 12; k++) a.l[k] = FpParams::mod(k) - (k == 0 ? 1u : 0u);
-    if (fe_mul(a, b) != fe_mul_portable(a, b)) bad++;
-    if (fe_sqr(a) != fe_mul_portable(a, a)) bad++;
-    Fr c, d;
     for (int k = 0; k < 8; k++) { c.l[k] = st_rand(s); d.l[k] = st_rand(s); }
     c.l[7] &= 0x3fffffffu; d.l[7] &= 0x3fffffffu;
-    if (fe_mul(c, d) != fe_mul_portable(c, d)) bad++;
-    if (fe_sub(fe_add(c, d), d) != c) bad++;
-    // group law: (k1 + k2) G == k1 G + k2 G through the three multiplication paths
-    G1J g = g1_generator();
-    Fr k1 = c, k2 = d, k3 = fe_add(c, d);
-    G1J p1, p2, p3, sum;
-    g1_mul_var(&p1, &g, k1.l);
-    g1_mul_var(&p2, &g, k2.l);
-    p3 = g1_mul_simple(g, k3.l);
-    g1_add_ni(&sum, &p1, &p2);
-    if (!g1_equal(sum, p3)) bad++;
-    G1J s2, d2;
-    g1_add_sub_ni(&s2, &d2, &p3, &p2);      // p3 + p2, p3 - p2 == p1
-    if (!g1_equal(d2, p1)) bad++;
-    g1_add_ni(&sum, &p3, &p2);
-    if (!g1_equal(sum, s2)) bad++;
-    g1_dbl_ni(&sum, &p1);
-    g1_add_ni(&d2, &p1, &p1);                // addition falling into the doubling branch
-    if (!g1_equal(sum, d2)) bad++;
-    G1J neg = g1_neg(p1);
-    g1_add_ni(&d2, &p1, &neg);
-    if (!d2.is_inf()) bad++;
-    if (bad) atomicAdd(mismatch, (unsigned long long)bad);
 }
-void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, cudaStream_t st) {
+#define ST_CHECK(idx, cond) do { if (!(cond)) { atomicAdd(mismatch, 1ULL); atomicAdd(mismatch + 1 + (idx), 1ULL); } } while (0)
+__global__ void k_selftest_field(size_t n, uint64_t seed, unsigned long long* mismatch) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp a, b; Fr c, d;
+    st_scalars(i, seed, a, b, c, d);
+    ST_CHECK(0, fe_mul(a, b) == fe_mul_portable(a, b));
+    ST_CHECK(1, fe_sqr(a) == fe_mul_portable(a, a));
+    ST_CHECK(2, fe_mul(c, d) == fe_mul_portable(c, d));
+    ST_CHECK(3, fe_sub(fe_add(c, d), d) == c);
+}
+// which: 0 -> k1 G windowed GLV, 1 -> k2 G windowed GLV, 2 -> (k1 + k2) G double-and-add, 3 -> k1 G double-and-add
+__global__ void k_selftest_mul(size_t n, uint64_t seed, int which, G1J* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp a, b; Fr c, d;
+    st_scalars(i, seed, a, b, c, d);
+    G1J g = g1_generator(), r;
+    if (which == 0) g1_mul_var(&r, &g, c.l);
+    else if (which == 1) g1_mul_var(&r, &g, d.l);
+    else if (which == 2) { Fr k3 = fe_add(c, d); r = g1_mul_simple(g, k3.l); }
+    else r = g1_mul_simple(g, c.l);
+    out[(size_t)which * n + i] = r;
+}
+__global__ void k_selftest_group(size_t n, const G1J* pts, unsigned long long* mismatch) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const G1J p1 = pts[i], p2 = pts[n + i], p3 = pts[2 * n + i], p1s = pts[3 * n + i];
+    G1J t, u;
+    ST_CHECK(4, g1_equal(p1, p1s));                       // windowed GLV path == double-and-add
+    g1_add_ni(&t, &p1, &p2);
+    ST_CHECK(5, g1_equal(t, p3));                         // k1 G + k2 G == (k1 + k2) G
+    g1_add_sub_ni(&t, &u, &p3, &p2);
+    ST_CHECK(6, g1_equal(u, p1));                         // butterfly difference
+    g1_add_ni(&u, &p3, &p2);
+    ST_CHECK(7, g1_equal(t, u));                          // butterfly sum
+    g1_dbl_ni(&t, &p1);
+    g1_add_ni(&u, &p1, &p1);                              // addition falling into the doubling branch
+    ST_CHECK(8, g1_equal(t, u));
+    t = g1_neg(p1);
+    g1_add_ni(&u, &p1, &t);
+    ST_CHECK(9, u.is_inf());                              // P + (-P)
+    if (i == 0) {
+        G1J g = g1_generator();
+        constexpr uint32_t z2[8] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u, 0, 0, 0, 0};
+        t = g1_endo(g);
+        u = g1_mul_simple(g, z2);
+        ST_CHECK(10, g1_equal(t, u));                     // z^2 (x, y) == (beta x, -y)
+    }
+}
+// host-built scalar programs executed on the device against double-and-add: checks 11 (mode 0), 12 (mode 1)
+__global__ void k_selftest_programs(size_t n, const ScalarProgram* progs, const Fr* scalars, unsigned long long* mismatch) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1J g = g1_generator(), got;
+    Fr k = scalars[i];
+    G1J base = g1_mul_simple(g, k.l);                 // some point other than the generator
+    G1J want = g1_mul_simple(base, k.l);
+    g1_mul_program(&got, &base, progs + i);
+    if (!g1_equal(got, want)) { atomicAdd(mismatch, 1ULL); atomicAdd(mismatch + 1 + 11 + progs[i].mode, 1ULL); }
+}
+void launch_selftest_programs(size_t n, const ScalarProgram* progs, const Fr* scalars, unsigned long long* d_mismatch, cudaStream_t st) {
     if (!n) return;
-    k_selftest<<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_mismatch); g_launch_count++;
+    k_selftest_programs<<<grid_for(n, 64), 64, 0, st>>>(n, progs, scalars, d_mismatch); g_launch_count++;
+}
+void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, G1J* d_scratch /* 4 n */, cudaStream_t st) {
+    if (!n) return;
+    k_selftest_field<<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_mismatch);
+    for (int which = 0; which < 4; which++) k_selftest_mul<<<grid_for(n, 64), 64, 0, st>>>(n, seed, which, d_scratch);
+    k_selftest_group<<<grid_for(n, 64), 64, 0, st>>>(n, d_scratch, d_mismatch);
+    g_launch_count += 6;
 }
 
 __global__ void k_fp_mul_probe(uint32_t* buf, int iters) {

@@ -284,7 +284,7 @@ class FFTSettings:
         pr = np.ascontiguousarray(present, dtype=np.uint8)
         out = np.zeros_like(s)
         _raise(lib().b200_recover_poly_from_samples(self.h, _p(s), _p(pr), s.shape[0], _p(out)),
-               errors=(TOO_LARGE, NOT_POW2, RECOVERY), what="RecoverPolyFromSamples")
+               errors=(RECOVERY,), what="RecoverPolyFromSamples")
         return out
 
     def recover_poly_from_samples_batch(self, samples, present) -> np.ndarray:
@@ -292,7 +292,7 @@ class FFTSettings:
         pr = np.ascontiguousarray(present, dtype=np.uint8)
         out = np.zeros_like(s)
         _raise(lib().b200_recover_poly_from_samples_batch(self.h, _p(s), _p(pr), s.shape[1], s.shape[0], _p(out)),
-               errors=(TOO_LARGE, NOT_POW2, RECOVERY), what="RecoverPolyFromSamples")
+               errors=(RECOVERY,), what="RecoverPolyFromSamples")
         return out
 
 

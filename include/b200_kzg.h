@@ -158,9 +158,9 @@ uint64_t b200_fk20_last_launch_count(const b200_fk* fk);
 int b200_profile_begin(void);
 int b200_profile_end(double ms_per_class[B200_PROFILE_CLASSES], uint64_t launches_per_class[B200_PROFILE_CLASSES]);
 
-/* Self-test hooks (tests/): run the device field/curve primitives against the portable
- * host forms on `n` pseudo-random operands; returns the mismatch count in *mismatches. */
-int b200_selftest_field(size_t n, uint64_t seed, uint64_t* mismatches);
+/* Self-test hook (tests/): run the device field/curve primitives against their portable forms
+ * on `n` pseudo-random operands; mismatches[0] = total, mismatches[1 + i] = count of check i. */
+int b200_selftest_field(size_t n, uint64_t seed, uint64_t mismatches[17]);
 /* Integer-pipe probe (bench.py's second roofline): `threads` lanes each run 2 * iters dependent
  * 381-bit Montgomery multiplications; *ms receives the device time of that launch. */
 int b200_probe_fp_mul(size_t threads, int iters, float* ms);

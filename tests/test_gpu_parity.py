@@ -23,9 +23,9 @@ def cmp_g1(got, want):
 # ------------------------------------------------------------------------------ primitives
 def test_device_field_and_group_selftest():
     import ctypes as C
-    bad = C.c_uint64(123)
-    assert kzg.lib().b200_selftest_field(4096, 7, C.byref(bad)) == 0
-    assert bad.value == 0
+    bad = (C.c_uint64 * 17)()
+    assert kzg.lib().b200_selftest_field(4096, 7, bad) == 0
+    assert list(bad) == [0] * 17, list(bad)
 
 
 # ------------------------------------------------------------------------------ Fr FFT
