@@ -852,7 +852,7 @@ extern "C" int b200_selftest_field(size_t n, uint64_t seed, uint64_t* mismatches
     CK(cudaMalloc(&d, 17 * 8));
     CK(cudaMemset(d, 0, 17 * 8));
     G1J* scratch = nullptr;
-    CK(cudaMalloc(&scratch, (n ? 4 * n : 1) * sizeof(G1J)));
+    CK(cudaMalloc(&scratch, (n ? 4 * n : 2) * sizeof(G1J)));
     launch_selftest(n, seed, d, scratch, nullptr);
     int rc = check_launches();
     cudaDeviceSynchronize();

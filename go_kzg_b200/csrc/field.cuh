@@ -342,6 +342,22 @@ HD Fe<P> fe_inv(const Fe<P>& a) {
 typedef Fe<FpParams> Fp;
 typedef Fe<FrParams> Fr;
 
+// ---------------------------------------------------------------------------------------
+// Fp products as used by the curve code.  On the device they are calls to ONE out-of-line copy
+// of the 381-bit Montgomery product (~350 SASS instructions) instead of an inline expansion per
+// call site: a point addition with 16 inlined products is ~90 KB of straight-line code, the G1
+// kernels then stall ~80 % of the time on instruction fetch (ncu: stall_no_inst) and ptxas,
+// short of aligned register pairs, breaks IMAD.WIDE into IMAD + IMAD.HI.  Operands travel
+// through local memory (L1-resident), 128-bit accesses.
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__ void fp_mul_out(Fp* r, const Fp* a, const Fp* b) { *r = fe_mul(*a, *b); }
+__device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) { Fp r; fp_mul_out(&r, &a, &b); return r; }
+__device__ __forceinline__ Fp fp_sqr(const Fp& a) { Fp r; fp_mul_out(&r, &a, &a); return r; }
+#else
+inline Fp fp_mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
+inline Fp fp_sqr(const Fp& a) { return fe_mul(a, a); }
+#endif
+
 #ifdef __CUDACC__
 // Whole-element loads / stores.  Fe (and everything built from it) is alignas(16), so a plain
 // struct copy lowers to 128-bit vector accesses (LDG.128 / STS.128 / ...).  Do NOT reinterpret

@@ -36,18 +36,18 @@ HD G1J g1_neg(const G1J& p) { G1J r = p; r.y = fe_neg(p.y); return r; }
 // 2P: 3M + 4S (a = 0)
 HD G1J g1_dbl(const G1J& p) {
     if (p.is_inf()) return p;
-    Fp a = fe_sqr(p.x);
-    Fp b = fe_sqr(p.y);
-    Fp c = fe_sqr(b);
-    Fp d = fe_mul(p.x, b);
+    Fp a = fp_sqr(p.x);
+    Fp b = fp_sqr(p.y);
+    Fp c = fp_sqr(b);
+    Fp d = fp_mul(p.x, b);
     d = fe_dbl(fe_dbl(d));            // 4 X Y^2
     Fp e = fe_add(fe_dbl(a), a);      // 3 X^2
-    Fp f = fe_sqr(e);
+    Fp f = fp_sqr(e);
     G1J r;
-    r.z = fe_dbl(fe_mul(p.y, p.z));
+    r.z = fe_dbl(fp_mul(p.y, p.z));
     r.x = fe_sub(f, fe_dbl(d));
     Fp c8 = fe_dbl(fe_dbl(fe_dbl(c)));
-    r.y = fe_sub(fe_mul(e, fe_sub(d, r.x)), c8);
+    r.y = fe_sub(fp_mul(e, fe_sub(d, r.x)), c8);
     return r;
 }
 
@@ -55,19 +55,19 @@ HD G1J g1_dbl(const G1J& p) {
 HD G1J g1_add(const G1J& p, const G1J& q) {
     if (p.is_inf()) return q;
     if (q.is_inf()) return p;
-    Fp z1z1 = fe_sqr(p.z), z2z2 = fe_sqr(q.z);
-    Fp u1 = fe_mul(p.x, z2z2), u2 = fe_mul(q.x, z1z1);
-    Fp s1 = fe_mul(fe_mul(p.y, q.z), z2z2), s2 = fe_mul(fe_mul(q.y, p.z), z1z1);
+    Fp z1z1 = fp_sqr(p.z), z2z2 = fp_sqr(q.z);
+    Fp u1 = fp_mul(p.x, z2z2), u2 = fp_mul(q.x, z1z1);
+    Fp s1 = fp_mul(fp_mul(p.y, q.z), z2z2), s2 = fp_mul(fp_mul(q.y, p.z), z1z1);
     if (u1 == u2) {
         if (s1 == s2) return g1_dbl(p);
         return G1J::infinity();
     }
     Fp h = fe_sub(u2, u1), rr = fe_sub(s2, s1);
-    Fp hh = fe_sqr(h), hhh = fe_mul(h, hh), v = fe_mul(u1, hh);
+    Fp hh = fp_sqr(h), hhh = fp_mul(h, hh), v = fp_mul(u1, hh);
     G1J r;
-    r.x = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
-    r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(s1, hhh));
-    r.z = fe_mul(fe_mul(p.z, q.z), h);
+    r.x = fe_sub(fe_sub(fp_sqr(rr), hhh), fe_dbl(v));
+    r.y = fe_sub(fp_mul(rr, fe_sub(v, r.x)), fp_mul(s1, hhh));
+    r.z = fp_mul(fp_mul(p.z, q.z), h);
     return r;
 }
 HD G1J g1_sub(const G1J& p, const G1J& q) { return g1_add(p, g1_neg(q)); }
@@ -76,18 +76,18 @@ HD G1J g1_sub(const G1J& p, const G1J& q) { return g1_add(p, g1_neg(q)); }
 HD G1J g1_add_mixed(const G1J& p, const G1A& q) {
     if (q.is_inf()) return p;
     if (p.is_inf()) { G1J r; r.x = q.x; r.y = q.y; r.z = Fp::one(); return r; }
-    Fp z1z1 = fe_sqr(p.z);
-    Fp u2 = fe_mul(q.x, z1z1), s2 = fe_mul(fe_mul(q.y, p.z), z1z1);
+    Fp z1z1 = fp_sqr(p.z);
+    Fp u2 = fp_mul(q.x, z1z1), s2 = fp_mul(fp_mul(q.y, p.z), z1z1);
     if (p.x == u2) {
         if (p.y == s2) return g1_dbl(p);
         return G1J::infinity();
     }
     Fp h = fe_sub(u2, p.x), rr = fe_sub(s2, p.y);
-    Fp hh = fe_sqr(h), hhh = fe_mul(h, hh), v = fe_mul(p.x, hh);
+    Fp hh = fp_sqr(h), hhh = fp_mul(h, hh), v = fp_mul(p.x, hh);
     G1J r;
-    r.x = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
-    r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(p.y, hhh));
-    r.z = fe_mul(p.z, h);
+    r.x = fe_sub(fe_sub(fp_sqr(rr), hhh), fe_dbl(v));
+    r.y = fe_sub(fp_mul(rr, fe_sub(v, r.x)), fp_mul(p.y, hhh));
+    r.z = fp_mul(p.z, h);
     return r;
 }
 
@@ -96,37 +96,37 @@ HD G1J g1_add_mixed(const G1J& p, const G1A& q) {
 HD void g1_add_sub(const G1J& x, const G1J& t, G1J& sum, G1J& diff) {
     if (t.is_inf()) { sum = x; diff = x; return; }
     if (x.is_inf()) { sum = t; diff = g1_neg(t); return; }
-    Fp z1z1 = fe_sqr(x.z), z2z2 = fe_sqr(t.z);
-    Fp u1 = fe_mul(x.x, z2z2), u2 = fe_mul(t.x, z1z1);
-    Fp s1 = fe_mul(fe_mul(x.y, t.z), z2z2), s2 = fe_mul(fe_mul(t.y, x.z), z1z1);
+    Fp z1z1 = fp_sqr(x.z), z2z2 = fp_sqr(t.z);
+    Fp u1 = fp_mul(x.x, z2z2), u2 = fp_mul(t.x, z1z1);
+    Fp s1 = fp_mul(fp_mul(x.y, t.z), z2z2), s2 = fp_mul(fp_mul(t.y, x.z), z1z1);
     if (u1 == u2) {   // t == +-x: rare, take the generic path
         sum = g1_add(x, t);
         diff = g1_add(x, g1_neg(t));
         return;
     }
     Fp h = fe_sub(u2, u1);
-    Fp hh = fe_sqr(h), hhh = fe_mul(h, hh), v = fe_mul(u1, hh);
-    Fp z3 = fe_mul(fe_mul(x.z, t.z), h);
-    Fp s1hhh = fe_mul(s1, hhh);
+    Fp hh = fp_sqr(h), hhh = fp_mul(h, hh), v = fp_mul(u1, hh);
+    Fp z3 = fp_mul(fp_mul(x.z, t.z), h);
+    Fp s1hhh = fp_mul(s1, hhh);
     Fp v2 = fe_dbl(v);
     Fp rp = fe_sub(s2, s1);                       // x + t
     Fp rm = fe_sub(fe_neg(s2), s1);               // x + (-t)
-    sum.x = fe_sub(fe_sub(fe_sqr(rp), hhh), v2);
-    sum.y = fe_sub(fe_mul(rp, fe_sub(v, sum.x)), s1hhh);
+    sum.x = fe_sub(fe_sub(fp_sqr(rp), hhh), v2);
+    sum.y = fe_sub(fp_mul(rp, fe_sub(v, sum.x)), s1hhh);
     sum.z = z3;
-    diff.x = fe_sub(fe_sub(fe_sqr(rm), hhh), v2);
-    diff.y = fe_sub(fe_mul(rm, fe_sub(v, diff.x)), s1hhh);
+    diff.x = fe_sub(fe_sub(fp_sqr(rm), hhh), v2);
+    diff.y = fe_sub(fp_mul(rm, fe_sub(v, diff.x)), s1hhh);
     diff.z = z3;
 }
 
 // endomorphism used by the GLV split k = k1 + k2 z^2:  z^2 (x, y) = (beta x, -y)
-HD G1J g1_endo(const G1J& p) { G1J r; r.x = fe_mul(p.x, fp_const_beta()); r.y = fe_neg(p.y); r.z = p.z; return r; }
+HD G1J g1_endo(const G1J& p) { G1J r; r.x = fp_mul(p.x, fp_const_beta()); r.y = fe_neg(p.y); r.z = p.z; return r; }
 
 HD bool g1_equal(const G1J& a, const G1J& b) {   // bls/bls_kilic.go:106 EqualG1
     if (a.is_inf() || b.is_inf()) return a.is_inf() && b.is_inf();
-    Fp za = fe_sqr(a.z), zb = fe_sqr(b.z);
-    if (fe_mul(a.x, zb) != fe_mul(b.x, za)) return false;
-    return fe_mul(a.y, fe_mul(zb, b.z)) == fe_mul(b.y, fe_mul(za, a.z));
+    Fp za = fp_sqr(a.z), zb = fp_sqr(b.z);
+    if (fp_mul(a.x, zb) != fp_mul(b.x, za)) return false;
+    return fp_mul(a.y, fp_mul(zb, b.z)) == fp_mul(b.y, fp_mul(za, a.z));
 }
 
 // ---------------------------------------------------------------------------------------

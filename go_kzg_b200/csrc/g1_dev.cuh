@@ -56,7 +56,7 @@ static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* 
         for (int i = 1; i < 8; i++) g1_add_ni(&tab[i], &tab[i - 1], &p2);
     }
     const Fp beta = fp_const_beta();
-    for (int i = 0; i < 8; i++) bx[i] = fe_mul(tab[i].x, beta);
+    for (int i = 0; i < 8; i++) bx[i] = fp_mul(tab[i].x, beta);
     G1J acc = G1J::infinity();
     G1J t;
     for (int i = top; i >= 0; i--) {

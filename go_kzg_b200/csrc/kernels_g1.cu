@@ -265,13 +265,15 @@ __global__ void k_selftest_group(size_t n, const G1J* pts, unsigned long long* m
     t = g1_neg(p1);
     g1_add_ni(&u, &p1, &t);
     ST_CHECK(9, u.is_inf());                              // P + (-P)
-    if (i == 0) {
-        G1J g = g1_generator();
-        constexpr uint32_t z2[8] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u, 0, 0, 0, 0};
-        t = g1_endo(g);
-        u = g1_mul_simple(g, z2);
-        ST_CHECK(10, g1_equal(t, u));                     // z^2 (x, y) == (beta x, -y)
-    }
+}
+// z^2 (x, y) == (beta x, -y) on the generator
+__global__ void k_selftest_endo(G1J* out) {
+    G1J g = g1_generator();
+    uint32_t z2[8] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u, 0, 0, 0, 0};
+    out[threadIdx.x] = threadIdx.x == 0 ? g1_endo(g) : g1_mul_simple(g, z2);
+}
+__global__ void k_selftest_endo_check(const G1J* pts, unsigned long long* mismatch) {
+    ST_CHECK(10, g1_equal(pts[0], pts[1]));
 }
 // host-built scalar programs executed on the device against double-and-add: checks 11 (mode 0), 12 (mode 1)
 __global__ void k_selftest_programs(size_t n, const ScalarProgram* progs, const Fr* scalars, unsigned long long* mismatch) {
@@ -293,7 +295,9 @@ void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, G1
     k_selftest_field<<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_mismatch);
     for (int which = 0; which < 4; which++) k_selftest_mul<<<grid_for(n, 64), 64, 0, st>>>(n, seed, which, d_scratch);
     k_selftest_group<<<grid_for(n, 64), 64, 0, st>>>(n, d_scratch, d_mismatch);
-    g_launch_count += 6;
+    k_selftest_endo<<<1, 2, 0, st>>>(d_scratch);
+    k_selftest_endo_check<<<1, 1, 0, st>>>(d_scratch, d_mismatch);
+    g_launch_count += 8;
 }
 
 __global__ void k_fp_mul_probe(uint32_t* buf, int iters) {

@@ -25,7 +25,7 @@ def test_device_field_and_group_selftest():
     import ctypes as C
     bad = (C.c_uint64 * 17)()
     assert kzg.lib().b200_selftest_field(4096, 7, bad) == 0
-    assert list(bad) == [0] * 17, list(bad)
+    assert sum(bad) == 0, "per-check mismatch counts: " + " ".join(str(int(v)) for v in bad)
 
 
 # ------------------------------------------------------------------------------ Fr FFT
@@ -312,3 +312,113 @@ def test_commit_fk20_batch_n4096(trusted_setup_bytes):
         s = np.zeros(18, dtype=np.uint64)
         L.b200_g1_add(s.ctypes.data, proofs[0][i].ctypes.data, proofs[1][i].ctypes.data)
         assert L.b200_g1_equal(s.ctypes.data, single[i].ctypes.data) == 1
+
+
+# ------------------------------------------------------------------------------ zero poly / recovery
+def test_zero_poly_golden(goldens):
+    """zero_poly_test.go:133-198 TestFFTSettings_ZeroPolyViaMultiplication_Python"""
+    g = goldens["zero_poly_scale4"]
+    missing = [i for i, e in enumerate(g["exists"]) if not e]
+    ze, zp = kzg.FFTSettings(4).zero_poly_via_multiplication(missing, 16)
+    assert kzg.fr_to_ints(ze) == [int(v) for v in g["expected_eval"]]
+    assert kzg.fr_to_ints(zp) == [int(v) for v in g["expected_poly"]]
+
+
+@pytest.mark.parametrize("scale,nmiss", [(3, 1), (5, 7), (7, 63), (7, 64), (8, 100), (10, 512), (11, 700), (12, 2048), (14, 8192)])
+def test_zero_poly_vs_oracle(scale, nmiss):
+    """zero_poly_test.go:251-261 shape; single-leaf, multi-leaf and multi-round cases"""
+    n = 1 << scale
+    rng = random.Random(scale * 1000 + nmiss)
+    missing = sorted(rng.sample(range(n), nmiss))
+    fs, fo = kzg.FFTSettings(scale), cref.FFTSettings(scale)
+    ze, zp = fs.zero_poly_via_multiplication(missing, n)
+    ze_o, zp_o = fo.zero_poly(missing, n)
+    assert np.array_equal(ze, ze_o) and np.array_equal(zp, zp_o)
+    zi = kzg.fr_to_ints(ze)
+    assert all((zi[i] == 0) == (i in set(missing)) for i in range(n))      # vanishes exactly on the missing set
+
+
+def test_zero_poly_edge_cases():
+    fs = kzg.FFTSettings(6)
+    ze, zp = fs.zero_poly_via_multiplication([], 64)                        # zero_poly.go:117-119
+    assert not ze.any() and not zp.any()
+    with pytest.raises(kzg.KZGPanic):                                       # zero_poly.go:120-122
+        fs.zero_poly_via_multiplication([1], 128)
+    with pytest.raises(kzg.KZGPanic):                                       # zero_poly.go:123-125
+        fs.zero_poly_via_multiplication([1], 48)
+    with pytest.raises(kzg.KZGPanic):                                       # degree does not fit (zero_poly.go:133 / 207-209)
+        fs.zero_poly_via_multiplication(list(range(64)), 64)
+    # sub-domain with stride (MaxWidth / length = 4)
+    fo = cref.FFTSettings(6)
+    ze, zp = fs.zero_poly_via_multiplication([0, 3, 5], 16)
+    ze_o, zp_o = fo.zero_poly([0, 3, 5], 16)
+    assert np.array_equal(ze, ze_o) and np.array_equal(zp, zp_o)
+
+
+def _recovery_case(scale, known_ratio, seed):
+    """recover_from_samples_test.go:61-137: poly = [0 .. n/2-1, 0 ...], random erasures"""
+    n = 1 << scale
+    fo = pyref.FFTSettings(scale) if scale <= 10 else None
+    poly = list(range(n // 2)) + [0] * (n // 2)
+    data = (kzg.fr_to_ints(cref.FFTSettings(scale).fft(cref.fr_to_limbs(poly))) if fo is None else fo.fft(poly))
+    rng = random.Random(seed)
+    nmiss = n - int(n * known_ratio)
+    miss = set(rng.sample(range(n), nmiss))
+    present = np.array([0 if i in miss else 1 for i in range(n)], dtype=np.uint8)
+    samples = kzg.fr_from_ints([0 if i in miss else d for i, d in enumerate(data)])
+    return data, samples, present
+
+
+def test_recover_simple():
+    """recover_from_samples_test.go:10-59: n = 4, keep indices 0 and 3"""
+    fs = kzg.FFTSettings(2)
+    data = pyref.FFTSettings(2).fft([1, 2, 0, 0])
+    rec = fs.recover_poly_from_samples(kzg.fr_from_ints([data[0], 0, 0, data[3]]), [1, 0, 0, 1])
+    assert kzg.fr_to_ints(rec) == data
+
+
+@pytest.mark.parametrize("scale,ratio,seed", [(4, 0.5, 0), (8, 0.7, 1), (10, 0.5, 2), (10, 0.95, 3), (14, 0.5, 14)])
+def test_recover_vs_oracle(scale, ratio, seed):
+    data, samples, present = _recovery_case(scale, ratio, seed)
+    fs = kzg.FFTSettings(scale)
+    rec = fs.recover_poly_from_samples(samples, present)
+    assert kzg.fr_to_ints(rec) == data
+    if scale <= 10:
+        assert np.array_equal(rec, cref.FFTSettings(scale).recover(samples, present))
+
+
+def test_recover_batch_and_errors():
+    scale = 9
+    fs = kzg.FFTSettings(scale)
+    cases = [_recovery_case(scale, 0.5 + 0.1 * b, 50 + b) for b in range(4)]
+    out = fs.recover_poly_from_samples_batch(np.stack([c[1] for c in cases]), np.stack([c[2] for c in cases]))
+    for b in range(4):
+        assert kzg.fr_to_ints(out[b]) == cases[b][0]
+    data, samples, present = cases[2]                                       # 70 % known: redundant samples
+    noisy = samples.copy()
+    noisy[np.flatnonzero(present)[0], 0] ^= 1                               # a corrupted known sample
+    with pytest.raises(kzg.KZGError):                                       # recover_from_samples.go:103-107
+        fs.recover_poly_from_samples(noisy, present)
+    assert cref.lib().orc_recover_poly_from_samples(cref.FFTSettings(scale).h, noisy.ctypes.data, present.ctypes.data, 1 << scale,
+                                                    np.zeros_like(noisy).ctypes.data) == 5   # the oracle errors too
+    with pytest.raises(kzg.KZGPanic):                                       # nothing missing: "bad zero eval" (:54-58)
+        fs.recover_poly_from_samples(samples, np.ones(1 << scale, dtype=np.uint8))
+
+
+def test_das_extension_then_recovery_round_trip():
+    """config 4 shape: extend 8192 -> 16384 samples, erase half, recover everything (size-independent property)"""
+    scale = 14
+    fs = kzg.FFTSettings(scale)
+    even = kzg.fr_from_ints(random_fr_ints(1 << (scale - 1), 4242))
+    odd = fs.das_fft_extension(even)
+    full = np.empty((1 << scale, 4), dtype=np.uint64)
+    full[0::2], full[1::2] = even, odd
+    rng = random.Random(14)
+    perm = list(range(1 << scale))
+    rng.shuffle(perm)
+    present = np.ones(1 << scale, dtype=np.uint8)
+    present[perm[: 1 << (scale - 1)]] = 0
+    samples = full.copy()
+    samples[present == 0] = 0
+    rec = fs.recover_poly_from_samples(samples, present)
+    assert np.array_equal(rec, full)
