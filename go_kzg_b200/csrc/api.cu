@@ -704,15 +704,39 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
     if (logk2 > 12) CKS(tmp.alloc(batch * l * k2 * sizeof(Fr), st));
     Fr scale = fr_inv_of_u64(k2);
     launch_fr_ntt(fs->dom, c.as<Fr>(), c.as<Fr>(), tmp.as<Fr>(), logk2, batch * l, false, &scale, st);
+    DevBuf eo;
+    if (mode == 0) {
+        // even entries carry 1/2 instead of 1/2k (see below): times k
+        Fr tab2[2] = {fr_from_u64(k), Fr::one()};
+        CKS(eo.alloc(sizeof tab2, st));
+        CK(cudaMemcpyAsync(eo.p, tab2, sizeof tab2, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // tab2 lives on this stack frame
+        launch_fr_mul_table(c.as<Fr>(), eo.as<Fr>(), 2, batch * l * k, st);
+    }
     launch_g1_mul_var(fk->d_x_ext_fft, 0, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
     for (size_t cnt = l; cnt > 1; cnt /= 2) launch_g1_fold(h.as<G1J>(), l * k2, (cnt / 2) * k2, cnt * k2, batch, st);
     CKS(check_launches());
     const size_t bstride = l * k2;
-    CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, true, true, st));
     if (mode == 0) {
-        CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2 - 1, batch, 2, bstride, false, false, st));
-        launch_g1_to_abi(h.as<G1J>(), d_proofs, k, batch, 2, bstride, 0, 0, st);
+        // FK20Single: only FFT_k(h[:k]) is wanted.  With H = hExt^ (2k evaluations of a polynomial
+        // h_lo + X^k h_hi) the even entries evaluate h_lo + h_hi on the order-k domain and the odd
+        // ones evaluate (h_lo - h_hi)(g X), g = w_2k.  Hence
+        //     FFT_k(h_lo) = 1/2 H_even + 1/2 FFT_k( g^-m . IFFT_k(H_odd)[m] ),
+        // two size-k transforms and k twists instead of a size-2k and a size-k transform
+        // (about 0.69x the twiddle multiplications).  1/2 and 1/(2k) were folded into c^ above.
+        // The odd slots (stride 2) are transformed in place: DIF inverse (bit-reversed result),
+        // twist by position, DIT forward; then the even slots are added.
+        const unsigned logk = logk2 - 1;
+        G1J* odd = h.as<G1J>() + 1;
+        CKS(dev_g1_fft_stages(fs, odd, logk, batch, 2, bstride, true, true, st));
+        const ScalarProgram* inv_progs;
+        CKS(fs_programs(fs, 1, program_mode_for_batch(batch), &inv_progs));
+        launch_g1_mul_programs(odd, k, batch, 2, bstride, inv_progs, (fs->max_width / 2) / k, 1, logk, st);
+        CKS(dev_g1_fft_stages(fs, odd, logk, batch, 2, bstride, false, false, st));
+        launch_g1_add_arrays(odd, 2, bstride, h.as<G1J>(), 2, bstride, k, batch, st);
+        launch_g1_to_abi(odd, d_proofs, k, batch, 2, bstride, 0, 0, st);
     } else {
+        CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, true, true, st));
         // clear the odd slots (the discarded upper half of the inverse transform): h ++ 0^k
         static G1J* d_inf = nullptr;   // one infinity element per process (never freed)
         if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }

@@ -235,17 +235,17 @@ __global__ void k_selftest_field(size_t n, uint64_t seed, unsigned long long* mi
     ST_CHECK(3, fe_sub(fe_add(c, d), d) == c);
 }
 // which: 0 -> k1 G windowed GLV, 1 -> k2 G windowed GLV, 2 -> (k1 + k2) G double-and-add, 3 -> k1 G double-and-add
-__global__ void k_selftest_mul(size_t n, uint64_t seed, int which, G1J* out) {
+template <int WHICH>
+__global__ void k_selftest_mul(size_t n, uint64_t seed, G1J* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fp a, b; Fr c, d;
     st_scalars(i, seed, a, b, c, d);
+    Fr k = WHICH == 1 ? d : (WHICH == 2 ? fe_add(c, d) : c);
     G1J g = g1_generator(), r;
-    if (which == 0) g1_mul_var(&r, &g, c.l);
-    else if (which == 1) g1_mul_var(&r, &g, d.l);
-    else if (which == 2) { Fr k3 = fe_add(c, d); r = g1_mul_simple(g, k3.l); }
-    else r = g1_mul_simple(g, c.l);
-    out[(size_t)which * n + i] = r;
+    if (WHICH <= 1) g1_mul_var(&r, &g, k.l);
+    else r = g1_mul_simple(g, k.l);
+    out[(size_t)WHICH * n + i] = r;
 }
 __global__ void k_selftest_group(size_t n, const G1J* pts, unsigned long long* mismatch) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,7 +293,10 @@ void launch_selftest_programs(size_t n, const ScalarProgram* progs, const Fr* sc
 void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, G1J* d_scratch /* 4 n */, cudaStream_t st) {
     if (!n) return;
     k_selftest_field<<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_mismatch);
-    for (int which = 0; which < 4; which++) k_selftest_mul<<<grid_for(n, 64), 64, 0, st>>>(n, seed, which, d_scratch);
+    k_selftest_mul<0><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
+    k_selftest_mul<1><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
+    k_selftest_mul<2><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
+    k_selftest_mul<3><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
     k_selftest_group<<<grid_for(n, 64), 64, 0, st>>>(n, d_scratch, d_mismatch);
     k_selftest_endo<<<1, 2, 0, st>>>(d_scratch);
     k_selftest_endo_check<<<1, 1, 0, st>>>(d_scratch, d_mismatch);
