@@ -106,16 +106,16 @@ def setup_points(kzg):
 
 
 def fp_mul_model_per_blob():
-    """Fp multiplications one blob needs on our path (DESIGN.md 'integer roofline'): counted from
-    the pipeline, M and S both as one multiplication."""
-    dbl, add, addsub = 7, 16, 18
+    """Fp multiplications one blob needs on our path (DESIGN.md 'integer roofline'), M = S = 1:
+    fixed-base products for ToeplitzPart2 (2n) and the commitment (n), two size-n G1 transforms
+    with width-5 NAF GLV twiddle programs, n twists, n final additions, the commitment fold."""
+    dbl, add, mixed = 7, 16, 11
     wnaf5 = 128 * dbl + (2 * 128 / 6) * add + (1 * dbl + 7 * add) + 8        # fixed-twiddle program, GLV
-    fixed4 = 128 * dbl + 66 * add + (4 * dbl + 3 * add) + 8                  # per-lane scalar, GLV
-    n, n2 = N_COEFFS, 2 * N_COEFFS
-    stages = lambda m: (m // 2) * (m.bit_length() - 1)
-    trivial = lambda m: m - 1
-    fft = lambda m: (stages(m) - trivial(m)) * wnaf5 + stages(m) * addsub
-    return fft(n2) + fft(n) + n2 * fixed4 + n * fixed4 + (n - 1) * add
+    fixed_base = 32 * mixed                                                  # 32 signed 8-bit windows
+    n = N_COEFFS
+    stages = (n // 2) * (n.bit_length() - 1)
+    fft = (stages - (n - 1)) * wnaf5 + stages * 2 * add                      # trivial twiddles skip the product
+    return 2 * fft + n * wnaf5 + n * add + 3 * n * fixed_base + (n - 1) * add
 
 
 def run_ours(args):

@@ -509,8 +509,9 @@ extern "C" int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inve
 // sum_i k[b][i] * pts[i] for each blob b: per-term scalar multiplication, then a fold tree.
 // d_k canonical ([batch][n]); result of blob b is left at work[b * n].
 static int dev_lincomb(const G1J* d_pts, size_t pts_bstride, const Fr* d_k, int k_is_mont, G1J* work, size_t n,
-                       size_t batch, cudaStream_t st) {
-    launch_g1_mul_var(d_pts, pts_bstride, d_k, k_is_mont, work, n, n, batch, st);
+                       size_t batch, cudaStream_t st, const G1A* fb_table = nullptr) {
+    if (fb_table) launch_g1_mul_fixed_base(fb_table, d_k, k_is_mont, work, n, n, batch, st);
+    else launch_g1_mul_var(d_pts, pts_bstride, d_k, k_is_mont, work, n, n, batch, st);
     for (size_t cnt = n; cnt > 1;) {
         size_t half = (cnt + 1) / 2;
         launch_g1_fold(work, n, half, cnt, batch, st);
@@ -562,7 +563,41 @@ struct b200_ks {
     b200_fs* fs = nullptr;
     size_t n_g1 = 0;
     G1J* d_secret_g1 = nullptr;   // Montgomery Jacobian
+    std::mutex mu;
+    G1A* d_fb_table = nullptr;    // fixed-base window table of SecretG1[:fb_n] (built on first commit)
+    size_t fb_n = 0;
 };
+
+// fixed-base tables are used while they stay below this many bytes per settings object
+static const size_t kFixedBaseBudget = (size_t)8 << 30;
+
+static int build_fixed_base(const G1J* d_pts, size_t n, G1A** out_table, cudaStream_t st) {
+    *out_table = nullptr;
+    if (n == 0 || fixed_base_table_bytes(n) > kFixedBaseBudget) return B200_OK;
+    G1A* table = nullptr;
+    CK(cudaMalloc(&table, fixed_base_table_bytes(n)));
+    DevBuf tmp;
+    int rc = tmp.alloc(fixed_base_tmp_bytes(n), st);
+    if (!rc) { launch_fixed_base_table(d_pts, n, tmp.as<G1J>(), table, st); rc = check_launches(); }
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "fixed-base table build"; rc = B200_ERR_CUDA; }
+    if (rc) { cudaFree(table); return rc; }
+    *out_table = table;
+    return B200_OK;
+}
+// table covering SecretG1[:n] (or null when over budget)
+static int ks_fixed_base(b200_ks* ks, size_t n, const G1A** table, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(ks->mu);
+    if (ks->fb_n < n) {
+        if (ks->d_fb_table) { cudaFree(ks->d_fb_table); ks->d_fb_table = nullptr; ks->fb_n = 0; }
+        G1A* t = nullptr;
+        CKS(build_fixed_base(ks->d_secret_g1, n, &t, st));
+        ks->d_fb_table = t;
+        ks->fb_n = t ? n : 0;
+        if (!t) { *table = nullptr; return B200_OK; }
+    }
+    *table = ks->d_fb_table;
+    return B200_OK;
+}
 
 extern "C" int b200_kzg_settings_new(b200_fs* fs, const uint64_t* secret_g1, size_t n_g1, size_t n_g2, b200_ks** out) {
     *out = nullptr;
@@ -591,6 +626,7 @@ extern "C" void b200_kzg_settings_free(b200_ks* ks) {
     if (!ks) return;
     cudaSetDevice(ks->device);
     cudaFree(ks->d_secret_g1);
+    cudaFree(ks->d_fb_table);
     delete ks;
 }
 
@@ -603,7 +639,9 @@ extern "C" int b200_commit_to_poly_batch(b200_ks* ks, const uint64_t* coeffs, si
     DevBuf k, work, res;
     CKS(k.alloc(batch * n * 32, st)); CKS(work.alloc(batch * n * sizeof(G1J), st)); CKS(res.alloc(batch * 144, st));
     CK(cudaMemcpyAsync(k.p, coeffs, batch * n * 32, cudaMemcpyHostToDevice, st));
-    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st));
+    const G1A* fb = nullptr;
+    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));     // worth a table only for real workloads
+    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb));
     launch_g1_to_abi(work.as<G1J>(), res.as<uint64_t>(), 1, batch, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(out, res.p, batch * 144, cudaMemcpyDeviceToHost, st));
@@ -620,6 +658,7 @@ struct b200_fk {
     b200_ks* ks = nullptr;
     size_t n2 = 0, chunk_len = 1;
     G1J* d_x_ext_fft = nullptr;   // [chunk_len][n2 / chunk_len], natural order (kzg.go:62,110-114)
+    G1A* d_fb_table = nullptr;    // fixed-base window table over d_x_ext_fft (null when over budget)
     unsigned long long last_launches = 0;
 };
 
@@ -652,6 +691,7 @@ static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk**
         launch_g1_copy(fk->d_x_ext_fft, 1, k2, work.as<G1J>(), 1, k2, k2, l, 1, logk2, st);
         if ((rc = check_launches())) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "sync in fk20 settings"; rc = B200_ERR_CUDA; break; }
+        if ((rc = build_fixed_base(fk->d_x_ext_fft, l * k2, &fk->d_fb_table, st))) break;
     } while (0);
     if (rc) { b200_fk20_settings_free(fk); return rc; }
     *out = fk;
@@ -666,6 +706,7 @@ extern "C" void b200_fk20_settings_free(b200_fk* fk) {
     if (!fk) return;
     cudaSetDevice(fk->device);
     cudaFree(fk->d_x_ext_fft);
+    cudaFree(fk->d_fb_table);
     delete fk;
 }
 extern "C" int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out) {
@@ -713,7 +754,8 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
         CK(cudaStreamSynchronize(st));   // tab2 lives on this stack frame
         launch_fr_mul_table(c.as<Fr>(), eo.as<Fr>(), 2, batch * l * k, st);
     }
-    launch_g1_mul_var(fk->d_x_ext_fft, 0, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
+    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
+    else launch_g1_mul_var(fk->d_x_ext_fft, 0, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
     for (size_t cnt = l; cnt > 1; cnt /= 2) launch_g1_fold(h.as<G1J>(), l * k2, (cnt / 2) * k2, cnt * k2, batch, st);
     CKS(check_launches());
     const size_t bstride = l * k2;
@@ -813,7 +855,9 @@ extern "C" int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size
     {
         DevBuf work;
         CKS(work.alloc(batch * n * sizeof(G1J), st));
-        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st));
+        const G1A* fb = nullptr;
+        CKS(ks_fixed_base(fk->ks, n, &fb, st));
+        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb));
         launch_g1_to_abi(work.as<G1J>(), (uint64_t*)d_commitments, 1, batch, 1, n, 0, 0, st);
     }
     CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 0, (uint64_t*)d_proofs, st));

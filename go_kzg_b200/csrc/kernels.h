@@ -80,6 +80,12 @@ void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_
 // out[b * out_bstride + i] = k[b * n + i] * pts[b * pts_bstride + i]   (pts_bstride = 0: shared bases)
 void launch_g1_mul_var(const G1J* pts, size_t pts_bstride, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride,
                        size_t n, size_t batch, cudaStream_t st);
+// fixed-base window tables (signed 8-bit windows, affine entries): build and use
+size_t fixed_base_table_bytes(size_t n);
+size_t fixed_base_tmp_bytes(size_t n);
+void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* table, cudaStream_t st);
+void launch_g1_mul_fixed_base(const G1A* table, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
+                              cudaStream_t st);
 // out[b * bstride + i * estride] = progs[idx(i) * prog_stride] * same element (in place)
 void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,
                             const ScalarProgram* progs, size_t prog_stride, int bitrev, unsigned logn, cudaStream_t st);

@@ -141,6 +141,85 @@ void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, s
     g_launch_count++;
 }
 
+// ------------------------------------------------------------------------------ fixed-base tables
+// The bases of ToeplitzPart2 (xExtFFT, fk20_single.go:72-74) and of CommitToPoly (SecretG1,
+// kzg_single_proofs.go:17-19) are fixed per settings object, so their scalar multiplications
+// become table look-ups: signed 8-bit windows, table[i][w][d-1] = d * 2^(8w) * P_i in affine
+// form (32 windows x 128 entries x 96 B = 384 KiB per base; 3 GiB for the 8192 bases of the
+// n = 4096 FK20 settings -- HBM is what a B200 has plenty of).  One product = 32 mixed additions
+// (~350 Fp multiplications) instead of ~2000.
+#define FB_WINDOWS 32
+#define FB_ENTRIES 128
+// bases[i][w] = 2^(8w) P_i (Jacobian)
+__global__ void __launch_bounds__(128) k_fb_bases(const G1J* __restrict__ pts, G1J* __restrict__ bases, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1J p = ld_vec(pts + i);
+    for (int w = 0; w < FB_WINDOWS; w++) {
+        st_vec(bases + i * FB_WINDOWS + w, p);
+        if (w + 1 < FB_WINDOWS) for (int k = 0; k < 8; k++) g1_dbl_ni(&p, &p);
+    }
+}
+// table[(i w) * 128 + d - 1] = affine(d * bases[i][w]), one entry per thread
+__global__ void __launch_bounds__(128) k_fb_entries(const G1J* __restrict__ bases, G1A* __restrict__ table, size_t n_rows) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * FB_ENTRIES) return;
+    const unsigned d = (unsigned)(t % FB_ENTRIES) + 1;
+    G1J b = ld_vec(bases + t / FB_ENTRIES), acc = G1J::infinity();
+    for (int bit = 7; bit >= 0; bit--) {
+        if (!acc.is_inf()) g1_dbl_ni(&acc, &acc);
+        if ((d >> bit) & 1u) g1_add_ni(&acc, &acc, &b);
+    }
+    G1A a;
+    if (acc.is_inf()) { a.x = Fp::zero(); a.y = Fp::zero(); }
+    else {
+        Fp zi = fe_inv(acc.z), zi2 = fp_sqr(zi);
+        a.x = fp_mul(acc.x, zi2);
+        a.y = fp_mul(acc.y, fp_mul(zi2, zi));
+    }
+    st_vec(table + t, a);
+}
+void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* table, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n) return;
+    k_fb_bases<<<grid_for(n, 128), 128, 0, st>>>(pts, bases_tmp, n);
+    k_fb_entries<<<grid_for(n * FB_WINDOWS * FB_ENTRIES, 128), 128, 0, st>>>(bases_tmp, table, n * FB_WINDOWS);
+    g_launch_count += 2;
+}
+// out[b * out_bstride + i] = k[b * n + i] * P_i through the table (thread <-> (i, blob), blob fastest:
+// a warp walks the same 12 KiB table row)
+__global__ void __launch_bounds__(128) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
+                                                           G1J* out, size_t out_bstride, size_t n, size_t batch) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    size_t b = t % batch, i = t / batch;
+    Fr s = ld_vec(k + b * n + i);
+    if (k_is_mont) s = fe_from_mont(s);
+    const G1A* row = table + i * (size_t)(FB_WINDOWS * FB_ENTRIES);
+    G1J acc = G1J::infinity();
+    unsigned carry = 0;
+    for (int w = 0; w < FB_WINDOWS; w++) {
+        unsigned d = ((s.l[w >> 2] >> ((w & 3) * 8)) & 255u) + carry;
+        bool neg = d > 128;
+        if (neg) { d = 256 - d; carry = 1; } else carry = 0;
+        if (d) {
+            G1A p = ld_vec(row + w * FB_ENTRIES + (d - 1));
+            if (neg) p.y = fe_neg(p.y);
+            g1_add_mixed_ni(&acc, &acc, &p);
+        }
+    }
+    st_vec(out + b * out_bstride + i, acc);
+}
+void launch_g1_mul_fixed_base(const G1A* table, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
+                              cudaStream_t st) {
+    ProfScope prof_scope(PROF_G1_MUL, st);
+    if (!n || !batch) return;
+    k_g1_mul_fixed_base<<<grid_for(n * batch, 128), 128, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+    g_launch_count++;
+}
+size_t fixed_base_table_bytes(size_t n) { return n * (size_t)FB_WINDOWS * FB_ENTRIES * sizeof(G1A); }
+size_t fixed_base_tmp_bytes(size_t n) { return n * (size_t)FB_WINDOWS * sizeof(G1J); }
+
 // ------------------------------------------------------------------------------ folds / adds
 __global__ void __launch_bounds__(128) k_g1_fold(G1J* data, size_t bstride, size_t half, size_t cnt, size_t batch) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,7 +313,7 @@ __global__ void k_selftest_field(size_t n, uint64_t seed, unsigned long long* mi
     ST_CHECK(2, fe_mul(c, d) == fe_mul_portable(c, d));
     ST_CHECK(3, fe_sub(fe_add(c, d), d) == c);
 }
-// which: 0 -> k1 G windowed GLV, 1 -> k2 G windowed GLV, 2 -> (k1 + k2) G double-and-add, 3 -> k1 G double-and-add
+// WHICH: 0 -> k1 G windowed GLV, 1 -> k2 G windowed GLV, 2 -> (k1 + k2) G double-and-add
 template <int WHICH>
 __global__ void k_selftest_mul(size_t n, uint64_t seed, G1J* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,11 +329,10 @@ __global__ void k_selftest_mul(size_t n, uint64_t seed, G1J* out) {
 __global__ void k_selftest_group(size_t n, const G1J* pts, unsigned long long* mismatch) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const G1J p1 = pts[i], p2 = pts[n + i], p3 = pts[2 * n + i], p1s = pts[3 * n + i];
+    const G1J p1 = pts[i], p2 = pts[n + i], p3 = pts[2 * n + i];
     G1J t, u;
-    ST_CHECK(4, g1_equal(p1, p1s));                       // windowed GLV path == double-and-add
     g1_add_ni(&t, &p1, &p2);
-    ST_CHECK(5, g1_equal(t, p3));                         // k1 G + k2 G == (k1 + k2) G
+    ST_CHECK(5, g1_equal(t, p3));                         // windowed GLV: k1 G + k2 G == (k1 + k2) G by double-and-add
     g1_add_sub_ni(&t, &u, &p3, &p2);
     ST_CHECK(6, g1_equal(u, p1));                         // butterfly difference
     g1_add_ni(&u, &p3, &p2);
@@ -296,7 +374,6 @@ void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, G1
     k_selftest_mul<0><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
     k_selftest_mul<1><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
     k_selftest_mul<2><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
-    k_selftest_mul<3><<<grid_for(n, 64), 64, 0, st>>>(n, seed, d_scratch);
     k_selftest_group<<<grid_for(n, 64), 64, 0, st>>>(n, d_scratch, d_mismatch);
     k_selftest_endo<<<1, 2, 0, st>>>(d_scratch);
     k_selftest_endo_check<<<1, 1, 0, st>>>(d_scratch, d_mismatch);
