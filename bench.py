@@ -122,6 +122,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import go_kzg_b200 as kzg
+    from go_kzg_b200 import shard
     from go_kzg_b200.synth import blob_polys
 
     rank = int(os.environ.get("RANK", "0"))
@@ -138,7 +139,7 @@ def run_ours(args):
 
     fs = kzg.FFTSettings(SCALE)
     fk = kzg.FK20SingleSettings(kzg.KZGSettings(fs, setup_points(kzg)), 2 * N_COEFFS)
-    polys = blob_polys(B, N_COEFFS, first_blob=rank * B)                      # (B, 4096, 4) u64
+    polys = blob_polys(B, N_COEFFS, first_blob=shard.blob_range(rank, world, B).start)   # (B, 4096, 4) u64
     h_polys = torch.from_numpy(polys.view(np.int64)).pin_memory()
     d_polys = h_polys.cuda(non_blocking=True)
     d_commit = torch.zeros((B, 18), dtype=torch.int64, device="cuda")
@@ -166,11 +167,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(x, dist if world > 1 else None, device="cuda")
 
     # ---- device-resident timing (value) + per-kernel-class events (roofline)
     for _ in range(W):
@@ -212,13 +209,20 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     hbm_peak, peak_kind = measured_peaks()
-    value = world * B * K / (ms_total / 1e3)
-    # dominant kernel: the G1 FFT butterfly stage.  One launch = one stage of B transforms; the
-    # transform's algorithmic bytes (288 n) are apportioned over its log2(n) stages.
+    value = shard.whole_job_rate(B, world, K, ms_total / 1e3)
+    # dominant kernel: the G1 FFT butterfly stage.  One launch = one stage of B size-n transforms;
+    # a transform's algorithmic bytes (288 n) are apportioned over its log2(n) stages
+    # and the step runs two size-n transforms per blob.
     stage_ms, stage_n = cls_ms[1], max(1, cls_n[1])
-    n2 = 2 * N_COEFFS
-    algo_stage_bytes = B * (G1_NTT_BYTES(n2) + G1_NTT_BYTES(N_COEFFS)) * K / stage_n     # average per launch
+    algo_stage_bytes = B * 2 * G1_NTT_BYTES(N_COEFFS) * K / stage_n                       # average per launch
     achieved = algo_stage_bytes / (stage_ms / stage_n / 1e3) / 1e9
+    traffic = None
+    try:   # per-launch DRAM bytes of this kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"] * (B / tj["blobs_per_launch"])
+    except Exception:
+        pass
     # integer roofline: Fp multiplication throughput of the whole step against the probe's peak
     pm = C.c_float()
     threads = 148 * 2048
@@ -237,7 +241,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_g1_fft_stage", "achieved": round(achieved, 4), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(achieved / hbm_peak, 6), "traffic": None, "peak_kind": peak_kind,
+                     "frac": round(achieved / hbm_peak, 6), "traffic": traffic, "peak_kind": peak_kind,
                      "share_of_step": round(stage_ms / ms_total, 4), "launches": int(stage_n),
                      "note": "integer-pipe bound kernel; see int_roofline"},
         "int_roofline": {"unit": "G Fp-mul/s", "achieved": round(fp_ach / 1e9, 3), "peak": round(fp_peak / 1e9, 3),
@@ -312,7 +316,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="blobs per GPU per step")
+    ap.add_argument("--batch", type=int, default=128, help="blobs per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

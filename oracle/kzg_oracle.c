@@ -53,16 +53,22 @@ int orc_max_threads(void)
     return n > 0 ? (int)n : 1;
 }
 void orc_set_threads(int n) { g_threads = n; }
+static __thread int t_in_parallel = 0; /* no nested thread teams: inner loops run serially */
+static void *pf_worker_outer(void *arg)
+{
+    t_in_parallel = 1;
+    return pf_worker(arg);
+}
 static void parallel_for(long long n, pf_body fn, void *ctx)
 {
     int nt = g_threads > 0 ? g_threads : orc_max_threads();
     if (nt > n) nt = (int)n;
-    if (nt <= 1) { for (long long i = 0; i < n; i++) fn(i, ctx); return; }
+    if (nt <= 1 || t_in_parallel) { for (long long i = 0; i < n; i++) fn(i, ctx); return; }
     long long next = 0;
     pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
     pf_job job = {fn, ctx, n, &next, &mu};
     pthread_t *th = malloc((size_t)nt * sizeof(pthread_t));
-    for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, pf_worker, &job);
+    for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, pf_worker_outer, &job);
     for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
     free(th);
 }
@@ -622,6 +628,48 @@ static void fft_g1_rec(const g1_t *vals, u64 off, u64 stride, const fr_t *roots,
         g1_sub(&out[i + half], &x, &t);
     }
 }
+/* The same recursion, unrolled at the top so that independent pieces can run on several host
+ * threads (the reference is single-threaded; the arithmetic performed is identical): the 2^d
+ * sub-transforms of depth d are independent, then each of the d merge levels is a loop of
+ * independent butterflies. */
+typedef struct { const g1_t *vals; const fr_t *roots; u64 rstride; g1_t *out; u64 n; unsigned d; unsigned lev; } fftp_ctx;
+static void fftp_leaf(long long j, void *c_)
+{
+    fftp_ctx *c = c_;
+    u64 sub = c->n >> c->d, pos = 0;
+    for (unsigned b = 0; b < c->d; b++) if ((u64)j & ((u64)1 << b)) pos |= (u64)1 << (c->d - 1 - b);
+    fft_g1_rec(c->vals, (u64)j, (u64)1 << c->d, c->roots, c->rstride << c->d, c->out + pos * sub, sub);
+}
+static void fftp_merge(long long q, void *c_)
+{
+    fftp_ctx *c = c_;
+    u64 len = c->n >> c->lev, half = len >> 1;
+    u64 blk = (u64)q / half, i = (u64)q % half;
+    g1_t *o = c->out + blk * len;
+    g1_t t, x = o[i], y = o[i + half];
+    g1_mul(&t, &y, &c->roots[i * (c->rstride << c->lev)]);
+    g1_add(&o[i], &x, &t);
+    g1_sub(&o[i + half], &x, &t);
+}
+static void fft_g1_top(const g1_t *vals, const fr_t *roots, u64 rstride, g1_t *out, u64 n)
+{
+    unsigned logn = 0, d = 0;
+    while (((u64)1 << logn) < n) logn++;
+    if (logn > 5) d = logn - 3 < 6 ? logn - 3 : 6;   /* sub-transforms stay >= 8 points (leaf rule l <= 4 untouched) */
+    if (d == 0) { fft_g1_rec(vals, 0, 1, roots, rstride, out, n); return; }
+    fftp_ctx c = {vals, roots, rstride, out, n, d, 0};
+    parallel_for((long long)1 << d, fftp_leaf, &c);
+    for (unsigned lev = d; lev-- > 0;) {
+        c.lev = lev;
+        parallel_for((long long)(n / 2), fftp_merge, &c);
+    }
+}
+typedef struct { g1_t *out; const g1_t *in; const fr_t *k; int per_elem; } mulv_ctx;
+static void mulv_body(long long i, void *c_)
+{
+    mulv_ctx *c = c_;
+    g1_mul(&c->out[i], &c->in[i], c->per_elem ? &c->k[i] : c->k);
+}
 /* fft_g1.go:58-94 FFTG1 on internal points. returns 0 ok, 1 too large, 2 not pow2 */
 static int fft_g1_int(const orc_fs *fs, const g1_t *vals, u64 n, int inv, g1_t *out)
 {
@@ -633,10 +681,11 @@ static int fft_g1_int(const orc_fs *fs, const g1_t *vals, u64 n, int inv, g1_t *
         fr_t inv_len;
         fr_from_u64(&inv_len, n);
         fr_inv(&inv_len, &inv_len);
-        fft_g1_rec(vals, 0, 1, fs->reverse, stride, out, n);
-        for (u64 i = 0; i < n; i++) g1_mul(&out[i], &out[i], &inv_len);
+        fft_g1_top(vals, fs->reverse, stride, out, n);
+        mulv_ctx mc = {out, out, &inv_len, 0};   /* fft_g1.go:81-84 */
+        parallel_for((long long)n, mulv_body, &mc);
     } else {
-        fft_g1_rec(vals, 0, 1, fs->expanded, stride, out, n);
+        fft_g1_top(vals, fs->expanded, stride, out, n);
     }
     return 0;
 }
@@ -874,7 +923,8 @@ static g1_t *toeplitz_part2(const orc_fs *fs, const fr_t *coeffs, const g1_t *x_
     fr_t *cf = malloc(n2 * sizeof(fr_t));
     inplace_fft(fs, coeffs, cf, n2, 0);
     g1_t *h = malloc(n2 * sizeof(g1_t));
-    for (u64 i = 0; i < n2; i++) g1_mul(&h[i], &x_ext_fft[i], &cf[i]);
+    mulv_ctx mc = {h, x_ext_fft, cf, 1};   /* fk20_single.go:72-74 */
+    parallel_for((long long)n2, mulv_body, &mc);
     free(cf);
     return h;
 }
@@ -1020,8 +1070,9 @@ int orc_fk20_multi_da(const orc_fk *fk, const u64 *poly, u64 n, u64 *out)
 }
 
 /* The headline unit of work: CommitToPoly + FK20Single for `nblobs` polynomials of n
- * coefficients, blobs spread over OpenMP threads (the reference itself is
- * single-threaded; one blob never uses more than one thread). */
+ * coefficients.  With several blobs the blobs are spread over host threads (one blob per
+ * thread); with fewer blobs than threads the independent butterflies inside each transform are
+ * spread instead.  The reference itself is single-threaded. */
 typedef struct { const orc_fk *fk; const u64 *polys; u64 n; u64 *commits, *proofs; int rc; } batch_ctx;
 static void batch_body(long long b, void *c_)
 {
@@ -1034,7 +1085,9 @@ int orc_commit_fk20_batch(const orc_fk *fk, const u64 *polys, u64 n, u64 nblobs,
     batch_ctx c = {fk, polys, n, commits, proofs, 0};
     int saved = g_threads;
     if (nthreads > 0) g_threads = nthreads;
-    parallel_for((long long)nblobs, batch_body, &c);
+    int nt = g_threads > 0 ? g_threads : orc_max_threads();
+    if ((long long)nblobs >= nt) parallel_for((long long)nblobs, batch_body, &c);
+    else for (u64 b = 0; b < nblobs; b++) batch_body((long long)b, &c);   /* threads go inside the transforms */
     g_threads = saved;
     return c.rc;
 }
