@@ -113,6 +113,7 @@ HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c, uint32_t& cf) {
 // ---------------------------------------------------------------------------------------
 struct FpParams {
     static constexpr int N = B200_FP_LIMBS;
+    static constexpr bool FAST_SQR = true;    // 3 p < 2^384: the doubled cross terms of fe_sqr fit the row accumulators
     static constexpr uint32_t INV = B200_FP_INV32;
     static HD constexpr uint32_t mod(int i) { constexpr uint32_t t[N] = B200_FP_MOD; return t[i]; }
     static HD constexpr uint32_t one(int i) { constexpr uint32_t t[N] = B200_FP_ONE; return t[i]; }
@@ -121,6 +122,7 @@ struct FpParams {
 };
 struct FrParams {
     static constexpr int N = B200_FR_LIMBS;
+    static constexpr bool FAST_SQR = false;   // 3 r > 2^256: squares go through fe_mul
     static constexpr uint32_t INV = B200_FR_INV32;
     static HD constexpr uint32_t mod(int i) { constexpr uint32_t t[N] = B200_FR_MOD; return t[i]; }
     static HD constexpr uint32_t one(int i) { constexpr uint32_t t[N] = B200_FR_ONE; return t[i]; }
@@ -307,8 +309,106 @@ HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
     return r;
 }
 
+// ---------------------------------------------------------------------------------------
+// Montgomery square: the same interleaved rows, but row J only multiplies the limbs j >= J of
+//     c^(J) = { a_J, 2 a_(J+1) mod W, d_(J+2), .., d_(N-1) },   d_i = (a_i << 1) | (a_(i-1) >> 31)
+// by a_J, i.e. a_J^2 plus the doubled cross terms a_J a_i (i > J) -- each cross product once
+// (N (N + 1) / 2 products instead of N^2; the reduction half of a row is unchanged).  Skipped
+// products degenerate into carry-propagating adds, which run on the otherwise idle ALU pipe.
+// Row accumulators hold up to (2a + p) W, so this needs 3p < W^N: true for Fp (381 of 384 bits),
+// not for Fr (255 of 256 bits), see FAST_SQR.
+// ---------------------------------------------------------------------------------------
+template <class P, int J>
+HD uint32_t sq_operand(const uint32_t* a, const uint32_t* d, int j) {
+    return j == J ? a[j] : (j == J + 1 ? (a[j] << 1) : d[j]);
+}
+template <class P, int J>
+HD void mont_row_sq(uint32_t* X, uint32_t* Y, const uint32_t* a, const uint32_t* d) {
+    constexpr int N = P::N;
+    constexpr int FIRST_EVEN = (J + 1) & ~1;          // first even limb index >= J
+    const uint32_t bi = a[J];
+    uint32_t cf = 0;
+    if (J == 0) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) { uint32_t c = sq_operand<P, J>(a, d, j); X[j] = mul_lo(c, bi); X[j + 1] = mul_hi(c, bi); }
+#pragma unroll
+        for (int j = 1; j < N; j += 2) { uint32_t c = sq_operand<P, J>(a, d, j); Y[j - 1] = mul_lo(c, bi); Y[j] = mul_hi(c, bi); }
+    } else {
+        X[0] = add_cc(X[0], Y[1], cf);
+#pragma unroll
+        for (int j = 1; j < N - 1; j += 2) {
+            if (j >= J) {
+                uint32_t c = sq_operand<P, J>(a, d, j);
+                Y[j - 1] = madc_lo_cc(c, bi, Y[j + 1], cf);
+                Y[j] = madc_hi_cc(c, bi, Y[j + 2], cf);
+            } else {
+                Y[j - 1] = addc_cc(Y[j + 1], 0u, cf);
+                Y[j] = addc_cc(Y[j + 2], 0u, cf);
+            }
+        }
+        {
+            uint32_t c = sq_operand<P, J>(a, d, N - 1);
+            Y[N - 2] = madc_lo_cc(c, bi, 0u, cf);
+            Y[N - 1] = madc_hi(c, bi, 0u, cf);
+        }
+        if (FIRST_EVEN < N) {
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                if (j < FIRST_EVEN) continue;
+                uint32_t c = sq_operand<P, J>(a, d, j);
+                if (j == FIRST_EVEN) { X[j] = mad_lo_cc(c, bi, X[j], cf); X[j + 1] = madc_hi_cc(c, bi, X[j + 1], cf); }
+                else { X[j] = madc_lo_cc(c, bi, X[j], cf); X[j + 1] = madc_hi_cc(c, bi, X[j + 1], cf); }
+            }
+            Y[N - 1] = addc(Y[N - 1], 0u, cf);
+        }
+    }
+    uint32_t m = X[0] * P::INV;
+    X[0] = mad_lo_cc(m, P::mod(0), X[0], cf);
+    X[1] = madc_hi_cc(m, P::mod(0), X[1], cf);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(m, P::mod(j), X[j], cf);
+        X[j + 1] = madc_hi_cc(m, P::mod(j), X[j + 1], cf);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0u, cf);
+    Y[0] = mad_lo_cc(m, P::mod(1), Y[0], cf);
+    Y[1] = madc_hi_cc(m, P::mod(1), Y[1], cf);
+#pragma unroll
+    for (int j = 3; j < N; j += 2) {
+        Y[j - 1] = madc_lo_cc(m, P::mod(j), Y[j - 1], cf);
+        Y[j] = madc_hi_cc(m, P::mod(j), Y[j], cf);
+    }
+}
+template <class P, int J>
+struct SqrRows {
+    static HD void run(uint32_t* X, uint32_t* Y, const uint32_t* a, const uint32_t* d) {
+        mont_row_sq<P, J>(X, Y, a, d);
+        SqrRows<P, J + 1>::run(Y, X, a, d);      // the two arrays swap roles every row
+    }
+};
 template <class P>
-HD Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul(a, a); }
+struct SqrRows<P, P::N> {
+    static HD void run(uint32_t*, uint32_t*, const uint32_t*, const uint32_t*) {}
+};
+
+template <class P>
+HD Fe<P> fe_sqr(const Fe<P>& a) {
+    constexpr int N = P::N;
+    if (!P::FAST_SQR) return fe_mul(a, a);
+    uint32_t ev[N], od[N], d[N];
+    d[0] = a.l[0] << 1;
+#pragma unroll
+    for (int i = 1; i < N; i++) d[i] = (a.l[i] << 1) | (a.l[i - 1] >> 31);
+    SqrRows<P, 0>::run(ev, od, a.l, d);
+    // N rows (even count): the last row had X = od, as in fe_mul
+    Fe<P> r; uint32_t cf = 0;
+    r.l[0] = add_cc(od[1], ev[0], cf);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r.l[k] = addc_cc(od[k + 1], ev[k], cf);
+    r.l[N - 1] = addc(ev[N - 1], 0u, cf);
+    fe_reduce_once(r);
+    return r;
+}
 
 // canonical <-> Montgomery
 template <class P>
@@ -352,10 +452,11 @@ typedef Fe<FrParams> Fr;
 #ifdef __CUDA_ARCH__
 static __device__ __noinline__ void fp_mul_out(Fp* r, const Fp* a, const Fp* b) { *r = fe_mul(*a, *b); }
 __device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) { Fp r; fp_mul_out(&r, &a, &b); return r; }
-__device__ __forceinline__ Fp fp_sqr(const Fp& a) { Fp r; fp_mul_out(&r, &a, &a); return r; }
+static __device__ __noinline__ void fp_sqr_out(Fp* r, const Fp* a) { *r = fe_sqr(*a); }
+__device__ __forceinline__ Fp fp_sqr(const Fp& a) { Fp r; fp_sqr_out(&r, &a); return r; }
 #else
 inline Fp fp_mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
-inline Fp fp_sqr(const Fp& a) { return fe_mul(a, a); }
+inline Fp fp_sqr(const Fp& a) { return fe_sqr(a); }
 #endif
 
 #ifdef __CUDACC__
