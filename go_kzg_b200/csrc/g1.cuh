@@ -33,14 +33,14 @@ HD G1J g1_generator() {
 
 HD G1J g1_neg(const G1J& p) { G1J r = p; r.y = fe_neg(p.y); return r; }
 
-// 2P: 3M + 4S (a = 0)
+// 2P: 2M + 5S (a = 0; dbl-2009-l: 4 X Y^2 is taken from (X + Y^2)^2, squares being cheaper than products)
 HD G1J g1_dbl(const G1J& p) {
     if (p.is_inf()) return p;
     Fp a = fp_sqr(p.x);
     Fp b = fp_sqr(p.y);
     Fp c = fp_sqr(b);
-    Fp d = fp_mul(p.x, b);
-    d = fe_dbl(fe_dbl(d));            // 4 X Y^2
+    Fp d = fe_sub(fe_sub(fp_sqr(fe_add(p.x, b)), a), c);
+    d = fe_dbl(d);                    // 4 X Y^2
     Fp e = fe_add(fe_dbl(a), a);      // 3 X^2
     Fp f = fp_sqr(e);
     G1J r;

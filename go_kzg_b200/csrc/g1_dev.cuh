@@ -14,15 +14,12 @@ namespace b200 {
 static __host__ __device__ __noinline__ void g1_dbl_ni(G1J* r, const G1J* p) { *r = g1_dbl(*p); }
 static __host__ __device__ __noinline__ void g1_add_ni(G1J* r, const G1J* p, const G1J* q) { *r = g1_add(*p, *q); }
 static __host__ __device__ __noinline__ void g1_add_mixed_ni(G1J* r, const G1J* p, const G1A* q) { *r = g1_add_mixed(*p, *q); }
-// (x + t, x - t): the radix-2 butterfly of fft_g1.go:52-54 as two out-of-line additions.
-// (A fused form sharing the common subexpressions saves 14 of ~1700 multiplications per butterfly
-// but needs more live registers than an ABI function gets; ptxas then spills inside a frameless
-// device function, which corrupted the caller's locals on sm_100a -- see DESIGN.md.)
-__host__ __device__ __forceinline__ void g1_add_sub_ni(G1J* sum, G1J* diff, const G1J* x, const G1J* t) {
-    G1J nt = g1_neg(*t), s;
-    g1_add_ni(&s, x, t);
-    g1_add_ni(diff, x, &nt);
-    *sum = s;
+// (x + t, x - t): the radix-2 butterfly of fft_g1.go:52-54, sharing the common subexpressions of
+// the two additions (18 products instead of 32).
+static __host__ __device__ __noinline__ void g1_add_sub_ni(G1J* sum, G1J* diff, const G1J* x, const G1J* t) {
+    G1J s, d;
+    g1_add_sub(*x, *t, s, d);
+    *sum = s; *diff = d;
 }
 
 // ---- digit-programmed scalar multiplication ----------------------------------------------
