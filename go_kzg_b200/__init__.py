@@ -22,5 +22,6 @@ from .kzg import (  # noqa: F401
     g1_from_compressed,
     lincomb_g1,
     g1_mul_many,
+    generate_testing_setup_g1,
     R_MOD,
 )

@@ -842,6 +842,110 @@ extern "C" int b200_da_using_fk20_multi(b200_fk* fk, const uint64_t* poly, size_
     return host_fk20(fk, poly, n, 2, proofs);
 }
 
+// ------------------------------------------------------------------------------ multi-GPU building blocks
+extern "C" int b200_fk20_multi_partial_dev(b200_fk* fk, const void* d_poly, size_t n, size_t off_begin, size_t off_end,
+                                           void* d_partial, void* cuda_stream) {
+    if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
+    const size_t l = fk->chunk_len, k = n / l, k2 = 2 * k;
+    if (off_begin > off_end || off_end > l) return B200_ERR_BAD_INPUT;
+    CK(cudaSetDevice(fk->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    b200_fs* fs = fk->ks->fs;
+    const size_t m = off_end - off_begin;
+    if (m == 0) { launch_g1_fill_infinity((G1J*)d_partial, k2, st); return check_launches(); }   // all-zero bytes == infinity in both encodings
+    const unsigned logk2 = log2u(k2);
+    DevBuf c, h, tmp;
+    CKS(c.alloc(l * k2 * sizeof(Fr), st));
+    CKS(h.alloc(m * k2 * sizeof(G1J), st));
+    launch_toeplitz_coeffs_strided((const uint64_t*)d_poly, c.as<Fr>(), n, l, 1, st);   // every offset; only [off_begin, off_end) is used
+    if (logk2 > 12) CKS(tmp.alloc(m * k2 * sizeof(Fr), st));
+    Fr scale = fr_inv_of_u64(k2);     // the inverse transform's 1/2k, as in dev_fk20
+    Fr* c_mine = c.as<Fr>() + off_begin * k2;
+    launch_fr_ntt(fs->dom, c_mine, c_mine, tmp.as<Fr>(), logk2, m, false, &scale, st);
+    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table + off_begin * k2 * (size_t)(32 * 128), c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
+    else launch_g1_mul_var(fk->d_x_ext_fft + off_begin * k2, 0, c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
+    // sum the m files: fold the tail onto the head until one file is left (m need not be a power of two)
+    for (size_t cnt = m; cnt > 1;) {
+        size_t half = (cnt + 1) / 2;
+        launch_g1_fold(h.as<G1J>(), m * k2, half * k2, cnt * k2, 1, st);
+        cnt = half;
+    }
+    launch_g1_to_abi(h.as<G1J>(), (uint64_t*)d_partial, k2, 1, 1, k2, 0, 0, st);
+    return check_launches();
+}
+
+extern "C" int b200_g1_sum_dev(const void* d_parts, size_t n_parts, size_t count, void* d_out, void* cuda_stream) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (n_parts == 0) { launch_g1_fill_infinity((G1J*)d_out, count, st); return check_launches(); }
+    DevBuf w;
+    CKS(w.alloc(n_parts * count * sizeof(G1J), st));
+    launch_g1_from_abi((const uint64_t*)d_parts, w.as<G1J>(), n_parts * count, st);
+    for (size_t cnt = n_parts; cnt > 1;) {
+        size_t half = (cnt + 1) / 2;
+        launch_g1_fold(w.as<G1J>(), n_parts * count, half * count, cnt * count, 1, st);
+        cnt = half;
+    }
+    launch_g1_to_abi(w.as<G1J>(), (uint64_t*)d_out, count, 1, 1, count, 0, 0, st);
+    return check_launches();
+}
+
+extern "C" int b200_fk20_multi_finish_dev(b200_fk* fk, const void* d_h_ext_fft, int reverse_bits, void* d_proofs, void* cuda_stream) {
+    CK(cudaSetDevice(fk->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    b200_fs* fs = fk->ks->fs;
+    const size_t k2 = fk->n2 / fk->chunk_len, k = k2 / 2;
+    const unsigned logk2 = log2u(k2);
+    DevBuf h;
+    CKS(h.alloc(k2 * sizeof(G1J), st));
+    launch_g1_from_abi((const uint64_t*)d_h_ext_fft, h.as<G1J>(), k2, st);
+    CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, 1, 1, k2, true, true, st));     // fk20_multi.go:93 (1/2k already folded in)
+    static G1J* d_inf = nullptr;
+    if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }
+    launch_g1_copy(h.as<G1J>() + 1, 2, k2, d_inf, 0, 0, k, 1, 0, 0, st);          // fk20_multi.go:100-103
+    CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, 1, 1, k2, false, false, st));   // fk20_multi.go:104
+    launch_g1_to_abi(h.as<G1J>(), (uint64_t*)d_proofs, k2, 1, 1, k2, reverse_bits ? 1 : 0, logk2, st);
+    return check_launches();
+}
+
+extern "C" int b200_commit_partial_dev(b200_ks* ks, const void* d_coeffs, size_t begin, size_t end, void* d_out, void* cuda_stream) {
+    if (begin > end || end > ks->n_g1) return B200_ERR_BAD_INPUT;
+    CK(cudaSetDevice(ks->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t m = end - begin;
+    if (m == 0) { launch_g1_fill_infinity((G1J*)d_out, 1, st); return check_launches(); }
+    DevBuf work;
+    CKS(work.alloc(m * sizeof(G1J), st));
+    CKS(dev_lincomb(ks->d_secret_g1 + begin, 0, (const Fr*)d_coeffs + begin, 0, work.as<G1J>(), m, 1, st));
+    launch_g1_to_abi(work.as<G1J>(), (uint64_t*)d_out, 1, 1, 1, m, 0, 0, st);
+    return check_launches();
+}
+
+extern "C" int b200_generate_testing_setup_g1(const uint64_t* secret, size_t n, uint64_t* out) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    if (n == 0) return B200_OK;
+    CK(cudaSetDevice(g_device));
+    cudaStream_t st = nullptr;
+    Fr sq[40];
+    sq[0] = fr_from_abi_mont(secret);
+    for (int j = 1; j < 40; j++) sq[j] = fe_mul(sq[j - 1], sq[j - 1]);
+    G1J gen = g1_generator();
+    DevBuf dsq, dk, dg, dpts, raw;
+    CKS(dsq.alloc(sizeof sq, st)); CKS(dk.alloc(n * sizeof(Fr), st)); CKS(dg.alloc(sizeof(G1J), st));
+    CKS(dpts.alloc(n * sizeof(G1J), st)); CKS(raw.alloc(n * 144, st));
+    CK(cudaMemcpyAsync(dsq.p, sq, sizeof sq, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dg.p, &gen, sizeof gen, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    launch_fr_powers(dsq.as<Fr>(), dk.as<Fr>(), n, st);
+    // one shared base, n scalars: (n = 1, batch = n) with a zero base stride
+    launch_g1_mul_var(dg.as<G1J>(), 0, dk.as<Fr>(), 0, dpts.as<G1J>(), 1, 1, n, st);
+    launch_g1_to_abi(dpts.as<G1J>(), raw.as<uint64_t>(), n, 1, 1, n, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------ headline unit
 extern "C" int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments,
                                           void* d_proofs, void* cuda_stream) {

@@ -63,6 +63,8 @@ void launch_toeplitz_coeffs(const uint64_t* polys_canon, Fr* out, size_t n, size
 // fk20_single.go:89-103 toeplitzCoeffsStepStrided for every offset: out[b][off][2k] Montgomery
 void launch_toeplitz_coeffs_strided(const uint64_t* polys_canon, Fr* out, size_t n, size_t chunk_len, size_t batch,
                                     cudaStream_t st);
+// out[i] = s^i (canonical limbs) for i < n; d_sq[j] = s^(2^j) (Montgomery), 40 entries
+void launch_fr_powers(const Fr* d_sq, Fr* out_canon, size_t n, cudaStream_t st);
 // pointwise helpers on Montgomery arrays
 void launch_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n, cudaStream_t st);   // dst = a * b
 

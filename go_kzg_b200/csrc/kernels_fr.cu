@@ -433,6 +433,21 @@ void launch_recover_check(const Fr* rec, const Fr* samples, const Fr* zero_eval,
     k_recover_check<<<grid_for(n * batch, 256), 256, 0, st>>>(rec, samples, zero_eval, present, n, n * batch, flags); g_launch_count++;
 }
 
+// ------------------------------------------------------------------------------ powers
+// out[i] = s^i (canonical), i < n, by square-and-multiply over the bits of i; sq[j] = s^(2^j) (Montgomery)
+__global__ void k_fr_powers(const Fr* __restrict__ sq, Fr* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr acc = Fr::one();
+    for (int j = 0; j < 40; j++) if ((i >> j) & 1) acc = fe_mul(acc, ld_vec(sq + j));
+    st_vec(out + i, fe_from_mont(acc));
+}
+void launch_fr_powers(const Fr* d_sq, Fr* out_canon, size_t n, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n) return;
+    k_fr_powers<<<grid_for(n, 256), 256, 0, st>>>(d_sq, out_canon, n); g_launch_count++;
+}
+
 // ------------------------------------------------------------------------------ Toeplitz gathers
 // fk20_single.go:106-119: [p[n-1], 0 x (n+1), p[1..n-2]]
 __global__ void k_toeplitz_coeffs(const uint64_t* __restrict__ polys, Fr* __restrict__ out, size_t n, size_t batch) {

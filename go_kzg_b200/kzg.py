@@ -118,6 +118,11 @@ def lib():
     L.b200_da_using_fk20_multi.argtypes = [vp, vp, sz, vp]
     L.b200_commit_fk20_batch.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200_commit_fk20_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+    L.b200_fk20_multi_partial_dev.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+    L.b200_g1_sum_dev.argtypes = [vp, sz, sz, vp, vp]
+    L.b200_fk20_multi_finish_dev.argtypes = [vp, vp, i32, vp, vp]
+    L.b200_commit_partial_dev.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.b200_generate_testing_setup_g1.argtypes = [vp, sz, vp]
     L.b200_fk20_last_launch_count.argtypes = [vp]
     L.b200_fk20_last_launch_count.restype = u64
     L.b200_selftest_field.argtypes = [sz, u64, C.POINTER(u64)]
@@ -197,6 +202,14 @@ def g1_mul_many(points, scalars) -> np.ndarray:
     assert pts.shape[0] == sc.shape[0]
     out = np.zeros_like(pts)
     _raise(lib().b200_g1_mul_many(_p(pts), _p(sc), pts.shape[0], _p(out)), what="MulG1 batch")
+    return out
+
+
+def generate_testing_setup_g1(secret: int, n: int) -> np.ndarray:
+    """setup.go:9-26 GenerateTestingSetup (G1 half): [secret^i * G] for i < n, computed on the device."""
+    out = np.zeros((n, 18), dtype=np.uint64)
+    s = fr_from_ints([secret % R_MOD])
+    _raise(lib().b200_generate_testing_setup_g1(_p(s), n, _p(out)), what="GenerateTestingSetup")
     return out
 
 

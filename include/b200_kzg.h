@@ -148,6 +148,24 @@ int b200_commit_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t n, size_t 
  * (a cudaStream_t, may be NULL for the default stream). */
 int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments,
                                void* d_proofs, void* cuda_stream);
+/* ------------------------------------------------------------------ multi-GPU building blocks --
+ * FK20 multi sharded by chunk offset: rank g computes the partial
+ * hExtFFT of its offsets [off_begin, off_end) (fk20_multi.go:80-91 restricted to those files),
+ * the partials (2k points each, ABI encoding, device memory) are exchanged as raw limbs over
+ * NCCL -- elliptic-curve addition is not an NCCL reduction, so the "allreduce" is an all-gather
+ * followed by b200_g1_sum_dev -- and b200_fk20_multi_finish_dev runs the two G1 transforms
+ * (fk20_multi.go:93-104, and the reverse-bit-order of :131 when reverse_bits != 0).
+ * All pointers are device pointers; calls are asynchronous on `cuda_stream`. */
+int b200_fk20_multi_partial_dev(b200_fk* fk, const void* d_poly, size_t n, size_t off_begin, size_t off_end,
+                                void* d_partial, void* cuda_stream);
+int b200_g1_sum_dev(const void* d_parts, size_t n_parts, size_t count, void* d_out, void* cuda_stream);
+int b200_fk20_multi_finish_dev(b200_fk* fk, const void* d_h_ext_fft, int reverse_bits, void* d_proofs, void* cuda_stream);
+/* Partial LinCombG1 over points/scalars [begin, end) of the settings' SecretG1 (MSM sharded by
+ * point range); partial sums are exchanged and added with b200_g1_sum_dev. */
+int b200_commit_partial_dev(b200_ks* ks, const void* d_coeffs, size_t begin, size_t end, void* d_out, void* cuda_stream);
+/* setup.go:9-26 GenerateTestingSetup, G1 half: out[i] = secret^i * G (host buffer, device compute). */
+int b200_generate_testing_setup_g1(const uint64_t secret[4], size_t n, uint64_t* out);
+
 /* Number of kernels the last batch call on this handle launched (bench.py gpu_launches). */
 uint64_t b200_fk20_last_launch_count(const b200_fk* fk);
 

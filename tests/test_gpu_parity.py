@@ -424,3 +424,102 @@ def test_das_extension_then_recovery_round_trip():
     samples[present == 0] = 0
     rec = fs.recover_poly_from_samples(samples, present)
     assert np.array_equal(rec, full)
+
+
+# ------------------------------------------------------------------------------ multi-GPU building blocks
+def test_generate_testing_setup_vs_oracle():
+    """setup.go:9-26"""
+    secret = 1927409816240961209460912649124
+    cmp_g1(kzg.generate_testing_setup_g1(secret, 70), cref.generate_setup_g1(secret, 70))
+
+
+def test_sharded_fk20_multi_blocks_on_one_gpu():
+    """offset-sharded FK20 multi (config 5 layout) with the ranks played one after another on a
+    single GPU: partials per offset range -> G1 sum -> finish == DAUsingFK20Multi"""
+    import ctypes as C
+    import torch
+    from go_kzg_b200 import multi_gpu
+    secret, l, cc = 1927409816240961209460912649124, 16, 32
+    n = l * cc
+    scale = (2 * n).bit_length() - 1
+    fs = kzg.FFTSettings(scale)
+    ks = kzg.KZGSettings(fs, kzg.generate_testing_setup_g1(secret, 2 * n))
+    fk = kzg.FK20MultiSettings(ks, 2 * n, l)
+    poly = kzg.fr_from_ints(random_fr_ints(n, 21))
+    want = fk.da_using_fk20_multi(poly)
+    L, k2, world = kzg.lib(), 2 * cc, 3                          # 3 ranks: uneven offset ranges (5, 5, 6)
+    d_poly = torch.from_numpy(poly.view(np.int64)).cuda()
+    parts = torch.zeros((world, k2, 18), dtype=torch.int64, device="cuda")
+    covered = []
+    for r in range(world):
+        rng_ = multi_gpu.offset_range(r, world, l)
+        covered += list(rng_)
+        assert L.b200_fk20_multi_partial_dev(fk.h, d_poly.data_ptr(), n, rng_.start, rng_.stop, parts[r].data_ptr(), None) == 0
+    assert covered == list(range(l))
+    d_sum = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+    assert L.b200_g1_sum_dev(parts.data_ptr(), world, k2, d_sum.data_ptr(), None) == 0
+    d_out = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+    assert L.b200_fk20_multi_finish_dev(fk.h, d_sum.data_ptr(), 1, d_out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    cmp_g1(d_out.cpu().numpy().view(np.uint64), want)
+    # the single-process entry of the sharded driver, and the point-range sharded commitment
+    cmp_g1(multi_gpu.da_using_fk20_multi_sharded(fk, poly), want)
+    c_parts = torch.zeros((world, 1, 18), dtype=torch.int64, device="cuda")
+    for r in range(world):
+        pr = multi_gpu.point_range(r, world, n)
+        assert L.b200_commit_partial_dev(ks.h, d_poly.data_ptr(), pr.start, pr.stop, c_parts[r].data_ptr(), None) == 0
+    c_sum = torch.zeros((1, 18), dtype=torch.int64, device="cuda")
+    assert L.b200_g1_sum_dev(c_parts.data_ptr(), world, 1, c_sum.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    cmp_g1(c_sum.cpu().numpy().view(np.uint64), ks.commit_to_poly(poly).reshape(1, 18))
+    del C
+
+
+def test_fk20_multi_config5_full_size():
+    """config 5 at full size on one GPU: n = 2^20 coefficients, chunk 16 -> 131072 coset proofs.
+    Expected values come from the pipeline restated in the exponent (secret known) with the
+    oracle's Fr FFT; a spread of positions is compared on compressed bytes, and one position
+    against the closed form q(s) G with p = q (X^l - x^l) + r."""
+    secret, l = 1927409816240961209460912649124, 16
+    n = 1 << 20
+    k = n // l
+    k2, scale = 2 * k, 21
+    fs = kzg.FFTSettings(scale)
+    setup = kzg.generate_testing_setup_g1(secret, 1 << scale)
+    ks = kzg.KZGSettings(fs, setup)
+    fk = kzg.FK20MultiSettings(ks, 1 << scale, l)
+    del setup
+    from go_kzg_b200.synth import random_fr_limbs
+    poly = random_fr_limbs(n, 5)
+    got = fk.da_using_fk20_multi(poly)
+    # --- exponent-domain restatement (pyref.fk20_multi_da_exponents) on the oracle's C Fr FFT
+    fo = cref.FFTSettings(scale)                      # transforms of size 2k use stride 2^21 / 2k
+    p_int = kzg.fr_to_ints(poly)
+    spow = [1] * n
+    for i in range(1, n):
+        spow[i] = spow[i - 1] * secret % R
+    h_ext = [0] * k2
+    for off in range(l):
+        start = n - l - 1 - off
+        x = [spow[start - i * l] for i in range(k - 1)] + [0] * (k + 1)
+        xf = kzg.fr_to_ints(fo.fft(cref.fr_to_limbs(x)))
+        c = pyref.toeplitz_coeffs_step_strided(p_int, off, l)
+        cf = kzg.fr_to_ints(fo.fft(cref.fr_to_limbs(c)))
+        for j in range(k2):
+            h_ext[j] = (h_ext[j] + cf[j] * xf[j]) % R
+    h = kzg.fr_to_ints(fo.fft(cref.fr_to_limbs(h_ext), True))[:k] + [0] * k
+    out = kzg.fr_to_ints(fo.fft(cref.fr_to_limbs(h)))
+    pyref.reverse_bit_order(out)
+    idx = list(range(0, k2, k2 // 61)) + [1, k2 - 1]
+    cmp_g1(got[idx], cref.g1_mul_gen([out[i] for i in idx]))
+    # closed form at one position
+    pos = 12345
+    w = pyref.scale2_root_of_unity(scale)
+    xq = pow(w, pyref.reverse_bits_limited(k2, pos) * ((1 << scale) // k2), R)
+    xl = pow(xq, l, R)
+    rem = list(p_int)
+    acc = 0
+    for i in range(n - 1, l - 1, -1):                 # synthetic division by X^l - x^l, quotient evaluated at s on the fly
+        acc = (acc + rem[i] * spow[i - l]) % R
+        rem[i - l] = (rem[i - l] + rem[i] * xl) % R
+    assert out[pos] == acc

@@ -61,3 +61,16 @@ def test_blob_range_edges():
         shard.blob_range(2, 2, 1)
     assert shard.max_over_ranks(3.5) == 3.5
     assert shard.blob_seed(5) == 0xB2000005
+
+
+def test_offset_and_point_ranges_partition():
+    """config 5 sharding: chunk offsets / MSM points are split into contiguous, disjoint, covering
+    ranges for every world size"""
+    from go_kzg_b200 import multi_gpu
+    for world in (1, 2, 3, 4, 8, 16, 24):
+        for total in (1, 16, 4096):
+            got = [i for r in range(world) for i in multi_gpu.offset_range(r, world, total)]
+            assert got == list(range(total))
+    assert list(multi_gpu.offset_range(1, 8, 16)) == [2, 3]
+    with pytest.raises(ValueError):
+        multi_gpu.point_range(4, 4, 10)
