@@ -515,7 +515,7 @@ def test_fk20_multi_config5_full_size():
     # closed form at one position
     pos = 12345
     w = pyref.scale2_root_of_unity(scale)
-    xq = pow(w, pyref.reverse_bits_limited(k2, pos) * ((1 << scale) // k2), R)
+    xq = pow(w, pyref.reverse_bits_limited(k2, pos), R)          # x = w_2n^brp(pos): coset x <w_l> (fk20_multi_test.go:60-64)
     xl = pow(xq, l, R)
     rem = list(p_int)
     acc = 0
