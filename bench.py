@@ -110,7 +110,10 @@ def fp_mul_model_per_blob():
     fixed-base products for ToeplitzPart2 (2n) and the commitment (n), two size-n G1 transforms
     with width-5 NAF GLV twiddle programs, n twists, n final additions, the commitment fold."""
     dbl, add, mixed = 7, 16, 11
-    wnaf5 = 128 * dbl + (2 * 128 / 6) * add + (1 * dbl + 7 * add) + 8        # fixed-twiddle program, GLV
+    # fixed-twiddle program (GLV, width-5 NAF): 128 doublings, ~43 mixed additions against an
+    # effective-affine table (1 doubling + 4 + 7 mixed additions + 34 rescaling products), 8 beta
+    # products, 1 product to leave the isomorphic curve
+    wnaf5 = 128 * dbl + (2 * 128 / 6) * mixed + (dbl + 4 + 7 * mixed + 34) + 8 + 1
     fixed_base = 32 * mixed                                                  # 32 signed 8-bit windows
     n = N_COEFFS
     stages = (n // 2) * (n.bit_length() - 1)

@@ -31,10 +31,13 @@ static __host__ __device__ __noinline__ void g1_add_sub_ni(G1J* sum, G1J* diff, 
 //   mode 1  width-5 NAF, odd digits in [-15, 15]: fewest additions, used when the whole warp
 //           shares one fixed scalar (batched G1 FFT: lanes = blobs).  table = {1,3,..,15} P
 // z^2 (x, y) = (beta x, -y).
+//
+// Reference path (Jacobian table, general additions).  Only taken when the table construction
+// below meets a degenerate addition, i.e. for points outside the prime-order subgroup.
 // Out of line on purpose: with this body inlined next to the call that produced *p, nvcc 12.9
 // emitted the copy `tab[0] = *p` without its first 16 bytes (wrong twiddle products).
-static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* p, const int8_t* d1, const int8_t* d2, int top,
-                                                            int mode) {
+static __host__ __device__ __noinline__ void g1_mul_digits_jac(G1J* out, const G1J* p, const int8_t* d1, const int8_t* d2, int top,
+                                                                int mode) {
     if (top < 0 || p->is_inf()) { *out = G1J::infinity(); return; }
     G1J tab[8];
     Fp bx[8];
@@ -76,6 +79,107 @@ static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* 
             g1_add_ni(&acc, &acc, &t);
         }
     }
+    *out = acc;
+}
+
+// r = p + q (q affine) for finite p, q with p != +-q, also handing back H (Z_r = Z_p * H).
+// Returns false (r untouched) in the degenerate cases.
+static __host__ __device__ __noinline__ bool g1_add_mixed_h(G1J* r, Fp* h_out, const G1J* p, const G1A* q) {
+    Fp z1z1 = fp_sqr(p->z);
+    Fp u2 = fp_mul(q->x, z1z1), s2 = fp_mul(fp_mul(q->y, p->z), z1z1);
+    Fp h = fe_sub(u2, p->x);
+    if (h.is_zero() || p->z.is_zero()) return false;
+    Fp rr = fe_sub(s2, p->y);
+    Fp hh = fp_sqr(h), hhh = fp_mul(h, hh), v = fp_mul(p->x, hh);
+    G1J o;
+    o.x = fe_sub(fe_sub(fp_sqr(rr), hhh), fe_dbl(v));
+    o.y = fe_sub(fp_mul(rr, fe_sub(v, o.x)), fp_mul(p->y, hhh));
+    o.z = fp_mul(p->z, h);
+    *r = o;
+    *h_out = h;
+    return true;
+}
+
+// The hot routine.  The look-up table is built and used on an isomorphic curve on which all of
+// its entries are AFFINE, so that every addition of the main loop is a mixed addition (8M + 3S
+// instead of 12M + 4S; ~43 of them per product):
+//   * y^2 = x^3 + b and y^2 = x^3 + b u^6 are isomorphic through (x, y) -> (u^2 x, u^3 y), and the
+//     Jacobian doubling / addition formulas of an a = 0 curve do not contain b.  A point with
+//     Jacobian coordinates (X, Y, Z) on the u-curve is (X, Y, Z u) on the original one.
+//   * the chain tab[i] = tab[i-1] + S is run with S affine on the curve scaled by Z_S (mixed
+//     additions), every step reporting the ratio H_i = Z_i / Z_(i-1); walking back, entry i is
+//     rescaled by (Z_7 / Z_i)^(2,3), which makes all entries affine on the curve scaled by
+//     Zg = Z_7 * Z_S.  The endomorphism (x, y) -> (beta x, -y) commutes with the scaling.
+//   * the accumulator lives on that curve; one product by Zg brings the result home.
+static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* p, const int8_t* d1, const int8_t* d2, int top,
+                                                            int mode) {
+    if (top < 0 || p->is_inf()) { *out = G1J::infinity(); return; }
+    G1J tab[8];       // x, y: table entry; z: the ratio H_i while the table is being built
+    Fp bx[8];
+    G1J cur, nxt;
+    G1A step;
+    Fp zs;            // Z_S: scaling of the curve the chain runs on
+    int first;
+    if (mode == 0) {  // {1..8} P: S = P, chain starts at 2P
+        zs = p->z;
+        step.x = p->x; step.y = p->y;
+        cur.x = p->x; cur.y = p->y; cur.z = Fp::one();
+        tab[0] = cur;
+        g1_dbl_ni(&nxt, &cur);
+        tab[1] = nxt;                      // z = Z_1 / Z_0 with Z_0 = 1
+        cur = nxt;
+        first = 2;
+    } else {          // {1,3,..,15} P: S = 2P, chain starts at P
+        g1_dbl_ni(&nxt, p);
+        zs = nxt.z;
+        step.x = nxt.x; step.y = nxt.y;
+        Fp c2 = fp_sqr(zs);
+        cur.x = fp_mul(p->x, c2); cur.y = fp_mul(p->y, fp_mul(c2, zs)); cur.z = p->z;
+        tab[0] = cur;
+        first = 1;
+    }
+    bool ok = !zs.is_zero();
+    for (int i = first; i < 8 && ok; i++) {
+        Fp h;
+        ok = g1_add_mixed_h(&nxt, &h, &cur, &step);
+        tab[i].x = nxt.x; tab[i].y = nxt.y; tab[i].z = h;
+        cur = nxt;
+    }
+    if (!ok) { g1_mul_digits_jac(out, p, d1, d2, top, mode); return; }
+    const Fp zg = fp_mul(cur.z, zs);
+    {
+        Fp s = tab[7].z;                   // Z_7 / Z_6
+        for (int i = 6; i >= 0; i--) {
+            Fp s2 = fp_sqr(s);
+            tab[i].x = fp_mul(tab[i].x, s2);
+            tab[i].y = fp_mul(tab[i].y, fp_mul(s2, s));
+            if (i) s = fp_mul(s, tab[i].z);
+        }
+    }
+    const Fp beta = fp_const_beta();
+    for (int i = 0; i < 8; i++) bx[i] = fp_mul(tab[i].x, beta);
+    G1J acc = G1J::infinity();
+    G1A t;
+    for (int i = top; i >= 0; i--) {
+        if (!acc.is_inf()) g1_dbl_ni(&acc, &acc);
+        int a = d1[i];
+        if (a) {
+            int m = a < 0 ? -a : a;
+            int idx = mode == 0 ? m - 1 : m >> 1;
+            t.x = tab[idx].x; t.y = tab[idx].y;
+            if (a < 0) t.y = fe_neg(t.y);
+            g1_add_mixed_ni(&acc, &acc, &t);
+        }
+        int b = d2[i];
+        if (b) {
+            int m = b < 0 ? -b : b;
+            int idx = mode == 0 ? m - 1 : m >> 1;
+            t.x = bx[idx]; t.y = tab[idx].y;
+            if (b > 0) t.y = fe_neg(t.y);
+            g1_add_mixed_ni(&acc, &acc, &t);
+        }
+    }
+    acc.z = fp_mul(acc.z, zg);
     *out = acc;
 }
 
