@@ -449,11 +449,16 @@ typedef Fe<FrParams> Fr;
 // kernels then stall ~80 % of the time on instruction fetch (ncu: stall_no_inst) and ptxas,
 // short of aligned register pairs, breaks IMAD.WIDE into IMAD + IMAD.HI.  Operands travel
 // through local memory (L1-resident), 128-bit accesses.
+// The out-of-line functions RETURN their result by value (PTX .param space, i.e. registers): an
+// earlier form `Fp r; fp_mul_out(&r, &a, &b); return r;` left one temporary alloca with inliner
+// lifetime markers per call site; nvcc 12.9 then forwarded a named variable onto such a
+// temporary (`Fp c2 = fp_sqr(z)` became the temporary itself) without extending its lifetime, and
+// stack colouring handed the slot to the next product's temporary while c2 was still live.
 #ifdef __CUDA_ARCH__
-static __device__ __noinline__ void fp_mul_out(Fp* r, const Fp* a, const Fp* b) { *r = fe_mul(*a, *b); }
-__device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) { Fp r; fp_mul_out(&r, &a, &b); return r; }
-static __device__ __noinline__ void fp_sqr_out(Fp* r, const Fp* a) { *r = fe_sqr(*a); }
-__device__ __forceinline__ Fp fp_sqr(const Fp& a) { Fp r; fp_sqr_out(&r, &a); return r; }
+static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) { return fe_mul(*a, *b); }
+__device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_out(&a, &b); }
+static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { return fe_sqr(*a); }
+__device__ __forceinline__ Fp fp_sqr(const Fp& a) { return fp_sqr_out(&a); }
 #else
 inline Fp fp_mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
 inline Fp fp_sqr(const Fp& a) { return fe_sqr(a); }

@@ -166,3 +166,20 @@ def test_synthetic_generator_is_pinned():
     assert kzg.fr_to_ints(random_fr_limbs(300, 0xB2000000)) == random_fr_ints(300, 0xB2000000)
     assert random_fr_ints(2, 0xB2000000) == [
         int(x) for x in kzg.fr_to_ints(random_fr_limbs(2, 0xB2000000))]
+
+
+def test_device_scalar_multiplication_code_on_the_host(tmp_path):
+    """g1_mul_digits (the effective-affine table routine the G1 FFT kernels run) is __host__
+    __device__: tools/host_check.cu runs it on the CPU against plain double-and-add for both digit
+    recodings, Jacobian inputs with Z != 1 and edge scalars (1, 2, 17, r - 1)."""
+    import shutil
+    import subprocess
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not (os.path.exists(nvcc) or shutil.which("nvcc")):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "host_check")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "go_kzg_b200", "csrc"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tools", "host_check.cu")],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
