@@ -455,9 +455,12 @@ typedef Fe<FrParams> Fr;
 // temporary (`Fp c2 = fp_sqr(z)` became the temporary itself) without extending its lifetime, and
 // stack colouring handed the slot to the next product's temporary while c2 was still live.
 #ifdef __CUDA_ARCH__
-static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) { return fe_mul(*a, *b); }
+// Operands are copied into locals first: multiplying straight out of *a / *b made ptxas split every
+// a_j * b_i product into IMAD + IMAD.HI + 2 IADD3.X instead of one IMAD.WIDE.X (ncu: half of the
+// multiplier issue slots of the G1 kernels), with the copies all 288 products fuse.
+static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul(x, y); }
 __device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_out(&a, &b); }
-static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { return fe_sqr(*a); }
+static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { Fp x = *a; return fe_sqr(x); }
 __device__ __forceinline__ Fp fp_sqr(const Fp& a) { return fp_sqr_out(&a); }
 #else
 inline Fp fp_mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
