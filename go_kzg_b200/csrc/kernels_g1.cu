@@ -14,6 +14,19 @@ namespace b200 {
 
 unsigned long long g_launch_count = 0;
 
+// Launch shape of the integer-pipe bound G1 kernels.  128 registers per thread hold the working
+// set of the out-of-line point operations without spills (ptxas -v), which lets 4 CTAs of 128
+// threads share an SM: the IMAD.WIDE carry chains of one warp are latency bound, so issue slots
+// are filled by warp count, not by ILP.
+#ifndef B200_G1_BLOCK
+#define B200_G1_BLOCK 128
+#endif
+#ifndef B200_G1_MINB
+#define B200_G1_MINB 4
+#endif
+constexpr unsigned G1_BLOCK = B200_G1_BLOCK;
+constexpr unsigned G1_MINB = B200_G1_MINB;
+
 static inline unsigned grid_for(size_t total, unsigned block) { return (unsigned)((total + block - 1) / block); }
 
 __device__ __forceinline__ uint32_t bitrev_u32(uint32_t v, unsigned logn) { return logn ? (__brev(v) >> (32 - logn)) : 0u; }
@@ -64,7 +77,7 @@ void launch_g1_fill_infinity(G1J* p, size_t n, cudaStream_t st) {
 // thread <-> (butterfly q, blob b) with b fastest: when batch is a multiple of 32 every lane of a
 // warp runs the same twiddle program on a different blob, so the digit branches are uniform.
 template <bool DIF>
-__global__ void __launch_bounds__(128) k_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
                                                       size_t bstride, const ScalarProgram* __restrict__ progs,
                                                       size_t prog_stride) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,13 +106,13 @@ void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_
     ProfScope prof_scope(PROF_G1_FFT_STAGE, st);
     size_t total = n_half * batch;
     if (!total) return;
-    if (dif) k_g1_fft_stage<true><<<grid_for(total, 128), 128, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
-    else k_g1_fft_stage<false><<<grid_for(total, 128), 128, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
+    if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
+    else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
     g_launch_count++;
 }
 
 // ------------------------------------------------------------------------------ scalar muls
-__global__ void __launch_bounds__(128) k_g1_mul_var(const G1J* pts, size_t pts_bstride,
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_var(const G1J* pts, size_t pts_bstride,
                                                     const Fr* __restrict__ k, int k_is_mont, G1J* out,
                                                     size_t out_bstride, size_t n, size_t batch) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,11 +130,11 @@ void launch_g1_mul_var(const G1J* pts, size_t pts_bstride, const Fr* k, int k_is
                        size_t n, size_t batch, cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_MUL, st);
     if (!n || !batch) return;
-    k_g1_mul_var<<<grid_for(n * batch, 128), 128, 0, st>>>(pts, pts_bstride, k, k_is_mont, out, out_bstride, n, batch);
+    k_g1_mul_var<<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(pts, pts_bstride, k, k_is_mont, out, out_bstride, n, batch);
     g_launch_count++;
 }
 
-__global__ void __launch_bounds__(128) k_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,
                                                          const ScalarProgram* __restrict__ progs, size_t prog_stride,
                                                          int bitrev, unsigned logn) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,7 +150,7 @@ void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, s
                             size_t prog_stride, int bitrev, unsigned logn, cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_MUL, st);
     if (!n || !batch) return;
-    k_g1_mul_programs<<<grid_for(n * batch, 128), 128, 0, st>>>(data, n, batch, estride, bstride, progs, prog_stride, bitrev, logn);
+    k_g1_mul_programs<<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n, batch, estride, bstride, progs, prog_stride, bitrev, logn);
     g_launch_count++;
 }
 
@@ -188,7 +201,7 @@ void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* tabl
 }
 // out[b * out_bstride + i] = k[b * n + i] * P_i through the table (thread <-> (i, blob), blob fastest:
 // a warp walks the same 12 KiB table row)
-__global__ void __launch_bounds__(128) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
                                                            G1J* out, size_t out_bstride, size_t n, size_t batch) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
@@ -214,7 +227,7 @@ void launch_g1_mul_fixed_base(const G1A* table, const Fr* k, int k_is_mont, G1J*
                               cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_MUL, st);
     if (!n || !batch) return;
-    k_g1_mul_fixed_base<<<grid_for(n * batch, 128), 128, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+    k_g1_mul_fixed_base<<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     g_launch_count++;
 }
 size_t fixed_base_table_bytes(size_t n) { return n * (size_t)FB_WINDOWS * FB_ENTRIES * sizeof(G1A); }

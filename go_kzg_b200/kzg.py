@@ -16,7 +16,7 @@ import numpy as np
 R_MOD = 52435875175126190479447740508185965837690552500527637822603658699938581184513
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libb200kzg.so")
+_LIB_PATH = os.environ.get("B200_KZG_LIB") or os.path.join(_HERE, "lib", "libb200kzg.so")   # override: tuning builds only
 
 OK, TOO_LARGE, NOT_POW2, LEN_MISMATCH, BAD_INPUT, ERR_CUDA, NO_DEVICE, TOO_SMALL, RECOVERY, ZERO_EVAL = range(10)
 
