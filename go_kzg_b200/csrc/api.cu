@@ -67,6 +67,25 @@ static int check_launches() {
     return B200_OK;
 }
 
+// Work buffers come from the device's stream-ordered pool.  Its default release threshold (0)
+// hands every freed block back to the driver at the next synchronisation, so a host-buffer call
+// (which ends in cudaStreamSynchronize) would re-map hundreds of MB on every call; keep them.
+static void keep_pool_memory() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done[dev] = true;
+}
+
 // RAII stream-ordered device buffer
 struct DevBuf {
     void* p = nullptr;
@@ -75,6 +94,7 @@ struct DevBuf {
     int alloc(size_t bytes, cudaStream_t s) {
         st = s;
         if (bytes == 0) bytes = 16;
+        keep_pool_memory();
         CK(cudaMallocAsync(&p, bytes, s));
         return B200_OK;
     }
