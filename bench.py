@@ -105,20 +105,30 @@ def setup_points(kzg):
     return np.concatenate([first, rest])
 
 
-def fp_mul_model_per_blob():
-    """Fp multiplications one blob needs on our path (DESIGN.md 'integer roofline'), M = S = 1:
+IMAD_PER_MUL, IMAD_PER_SQR = 300, 234   # 32x32->64 multiply-adds of fe_mul (2 N^2 + N) and fe_sqr (N (N + 1) / 2 + N^2 + N), N = 12
+
+
+def fp_ops_model_per_blob():
+    """(Fp products, Fp squares) one blob needs on our path (DESIGN.md 'integer roofline'):
     fixed-base products for ToeplitzPart2 (2n) and the commitment (n), two size-n G1 transforms
     with width-5 NAF GLV twiddle programs, n twists, n final additions, the commitment fold."""
-    dbl, add, mixed = 7, 16, 11
+    dbl, add, mixed = (2, 5), (12, 4), (8, 3)                               # (M, S) of the group operations
+    def cost(n_dbl=0, n_add=0, n_mixed=0, m=0, s=0):
+        return (n_dbl * dbl[0] + n_add * add[0] + n_mixed * mixed[0] + m, n_dbl * dbl[1] + n_add * add[1] + n_mixed * mixed[1] + s)
+    def plus(*cs):
+        return (sum(c[0] for c in cs), sum(c[1] for c in cs))
+    def times(k, c):
+        return (k * c[0], k * c[1])
     # fixed-twiddle program (GLV, width-5 NAF): 128 doublings, ~43 mixed additions against an
-    # effective-affine table (1 doubling + 4 + 7 mixed additions + 34 rescaling products), 8 beta
-    # products, 1 product to leave the isomorphic curve
-    wnaf5 = 128 * dbl + (2 * 128 / 6) * mixed + (dbl + 4 + 7 * mixed + 34) + 8 + 1
-    fixed_base = 32 * mixed                                                  # 32 signed 8-bit windows
+    # effective-affine table (1 doubling, 7 mixed additions, 4 + 34 rescaling products of which 7 are
+    # squares), 8 beta products, 1 product to leave the isomorphic curve
+    wnaf5 = cost(n_dbl=129, n_mixed=2 * 128 / 6 + 7, m=3 + 27 + 8 + 1, s=1 + 7)
+    fixed_base = cost(n_mixed=32)                                           # 32 signed 8-bit windows
+    butterfly = (14, 4)                                                     # shared-subexpression add/sub pair
     n = N_COEFFS
     stages = (n // 2) * (n.bit_length() - 1)
-    fft = (stages - (n - 1)) * wnaf5 + stages * 2 * add                      # trivial twiddles skip the product
-    return 2 * fft + n * wnaf5 + n * add + 3 * n * fixed_base + (n - 1) * add
+    fft = plus(times(stages - (n - 1), wnaf5), times(stages, butterfly))    # trivial twiddles skip the product
+    return plus(times(2, fft), times(n, wnaf5), times(n, cost(n_add=1)), times(3 * n, fixed_base), times(n - 1, cost(n_add=1)))
 
 
 def run_ours(args):
@@ -226,12 +236,15 @@ def run_ours(args):
         traffic = tj["dram_bytes_per_launch"] * (B / tj["blobs_per_launch"])
     except Exception:
         pass
-    # integer roofline: Fp multiplication throughput of the whole step against the probe's peak
+    # integer roofline: 32x32->64 multiply-adds (IMAD.WIDE) the step needs against what the multiplier
+    # probe sustains (dependent 381-bit Montgomery products on all SMs, 300 multiply-adds each)
     pm = C.c_float()
     threads = 148 * 2048
     L.b200_probe_fp_mul(threads, 2000, C.byref(pm))
     fp_peak = threads * 2000 * 2 / (pm.value / 1e3)
-    fp_ach = fp_mul_model_per_blob() * value / world
+    n_mul, n_sqr = fp_ops_model_per_blob()
+    imad_ach = (n_mul * IMAD_PER_MUL + n_sqr * IMAD_PER_SQR) * value / world
+    imad_peak = fp_peak * IMAD_PER_MUL
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": "blobs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -247,9 +260,11 @@ def run_ours(args):
                      "frac": round(achieved / hbm_peak, 6), "traffic": traffic, "peak_kind": peak_kind,
                      "share_of_step": round(stage_ms / ms_total, 4), "launches": int(stage_n),
                      "note": "integer-pipe bound kernel; see int_roofline"},
-        "int_roofline": {"unit": "G Fp-mul/s", "achieved": round(fp_ach / 1e9, 3), "peak": round(fp_peak / 1e9, 3),
-                         "frac": round(fp_ach / fp_peak, 4),
-                         "how": "model Fp-mul count per blob x blobs/s per GPU vs b200_probe_fp_mul (dependent 381-bit Montgomery products, all SMs)"},
+        "int_roofline": {"unit": "T multiply-add/s (32x32->64)", "achieved": round(imad_ach / 1e12, 3), "peak": round(imad_peak / 1e12, 3),
+                         "frac": round(imad_ach / imad_peak, 4), "fp_mul_probe_G_per_s": round(fp_peak / 1e9, 3),
+                         "model_per_blob": {"fp_mul": round(n_mul), "fp_sqr": round(n_sqr)},
+                         "how": "model count of Fp products/squares per blob x (300 | 234) multiply-adds x blobs/s per GPU vs "
+                                "b200_probe_fp_mul (dependent Montgomery products, all SMs) x 300"},
         "kernel_class_ms_per_step": {k: round(cls_ms[i] / K, 3) for i, k in enumerate(["fr_ntt", "g1_fft_stage", "g1_mul", "g1_fold", "misc"])},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -442,6 +442,10 @@ HD Fe<P> fe_inv(const Fe<P>& a) {
 typedef Fe<FpParams> Fp;
 typedef Fe<FrParams> Fr;
 
+}  // namespace b200
+#include "field_fp64_impl.cuh"
+namespace b200 {
+
 // ---------------------------------------------------------------------------------------
 // Fp products as used by the curve code.  On the device they are calls to ONE out-of-line copy
 // of the 381-bit Montgomery product (~350 SASS instructions) instead of an inline expansion per
@@ -454,13 +458,39 @@ typedef Fe<FrParams> Fr;
 // lifetime markers per call site; nvcc 12.9 then forwarded a named variable onto such a
 // temporary (`Fp c2 = fp_sqr(z)` became the temporary itself) without extending its lifetime, and
 // stack colouring handed the slot to the next product's temporary while c2 was still live.
-#ifdef __CUDA_ARCH__
+//
 // Operands are copied into locals first: multiplying straight out of *a / *b made ptxas split every
 // a_j * b_i product into IMAD + IMAD.HI + 2 IADD3.X instead of one IMAD.WIDE.X (ncu: half of the
 // multiplier issue slots of the G1 kernels), with the copies all 288 products fuse.
+//
+// Two pipes (B200_FP64_SLOTS, default 0 = off): the integer product is bound by the IMAD.WIDE
+// issue rate (1 per 4 cycles per SM sub-partition) while the FP64 pipe idles, so the warps of
+// every other resident CTA (hardware warp slot / 4 = index of the CTA on its SM, CTAs being 4
+// warps) run the bit-identical FP64-pipe product of field_fp64.cuh instead.
+#ifdef __CUDA_ARCH__
+#ifndef B200_FP64_SLOTS
+#define B200_FP64_SLOTS 0
+#endif
+#if B200_FP64_SLOTS
+__device__ __forceinline__ bool fp_on_fp64_pipe() {
+    unsigned w; asm("mov.u32 %0, %%warpid;" : "=r"(w));
+    return ((w >> 2) & 3u) < (unsigned)B200_FP64_SLOTS;
+}
+static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) {
+    Fp x = *a, y = *b;
+    if (fp_on_fp64_pipe()) return fe_mul_fp64(x, y);
+    return fe_mul(x, y);
+}
+static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) {
+    Fp x = *a;
+    if (fp_on_fp64_pipe()) return fe_sqr_fp64(x);
+    return fe_sqr(x);
+}
+#else
 static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul(x, y); }
-__device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_out(&a, &b); }
 static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { Fp x = *a; return fe_sqr(x); }
+#endif
+__device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_out(&a, &b); }
 __device__ __forceinline__ Fp fp_sqr(const Fp& a) { return fp_sqr_out(&a); }
 #else
 inline Fp fp_mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
