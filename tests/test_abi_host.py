@@ -183,3 +183,19 @@ def test_device_scalar_multiplication_code_on_the_host(tmp_path):
                           stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
+
+
+def test_fp64_pipe_product_matches_integer_product_on_the_host(tmp_path):
+    """field_fp64_impl.cuh (Montgomery product in 24-bit limbs on doubles) against fe_mul / fe_sqr:
+    random operands and the edge values 0, 1, p - 1, p - 2, 2^380 - 1 (tools/fp64_check.cu)."""
+    import shutil
+    import subprocess
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not (os.path.exists(nvcc) or shutil.which("nvcc")):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "fp64_check")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "go_kzg_b200", "csrc"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tools", "fp64_check.cu")],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
