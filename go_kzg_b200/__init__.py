@@ -19,6 +19,7 @@ from .kzg import (  # noqa: F401
     fr_from_ints,
     fr_to_ints,
     g1_to_compressed,
+    g1_to_compressed_device,
     g1_from_compressed,
     lincomb_g1,
     g1_mul_many,

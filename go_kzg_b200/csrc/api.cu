@@ -753,7 +753,9 @@ extern "C" uint64_t b200_fk20_last_launch_count(const b200_fk* fk) { return fk->
 //   proofs = FFT_G1(h)              (mode 0: k points, the even slots *are* the bit-reversed input of a DIT)
 //          | FFT_G1(h ++ 0^k)       (mode 1/2: 2k points; odd slots are cleared first)
 // mode 0: FK20Single (natural order); 1: *DAOptimized (natural order, 2k proofs); 2: DAUsing* (reverse bit order)
-static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch, int mode, uint64_t* d_proofs, cudaStream_t st) {
+// d_comp != nullptr: the proofs leave as 48-byte compressed points (d_proofs unused)
+static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch, int mode, uint64_t* d_proofs, cudaStream_t st,
+                    uint8_t* d_comp = nullptr) {
     b200_fs* fs = fk->ks->fs;
     const size_t l = fk->chunk_len, k = n / l, k2 = 2 * k;
     const unsigned logk2 = log2u(k2);
@@ -796,7 +798,8 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
         launch_g1_mul_programs(odd, k, batch, 2, bstride, inv_progs, (fs->max_width / 2) / k, 1, logk, st);
         CKS(dev_g1_fft_stages(fs, odd, logk, batch, 2, bstride, false, false, st));
         launch_g1_add_arrays(odd, 2, bstride, h.as<G1J>(), 2, bstride, k, batch, st);
-        launch_g1_to_abi(odd, d_proofs, k, batch, 2, bstride, 0, 0, st);
+        if (d_comp) launch_g1_compress(odd, d_comp, k, batch, 2, bstride, 0, 0, st);
+        else launch_g1_to_abi(odd, d_proofs, k, batch, 2, bstride, 0, 0, st);
     } else {
         CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, true, true, st));
         // clear the odd slots (the discarded upper half of the inverse transform): h ++ 0^k
@@ -804,7 +807,8 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
         if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }
         launch_g1_copy(h.as<G1J>() + 1, 2, bstride, d_inf, 0, 0, k, batch, 0, 0, st);
         CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, false, false, st));
-        launch_g1_to_abi(h.as<G1J>(), d_proofs, k2, batch, 1, bstride, mode == 2 ? 1 : 0, logk2, st);
+        if (d_comp) launch_g1_compress(h.as<G1J>(), d_comp, k2, batch, 1, bstride, mode == 2 ? 1 : 0, logk2, st);
+        else launch_g1_to_abi(h.as<G1J>(), d_proofs, k2, batch, 1, bstride, mode == 2 ? 1 : 0, logk2, st);
     }
     return check_launches();
 }
@@ -1000,6 +1004,101 @@ extern "C" int b200_commit_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t
     CK(cudaMemcpyAsync(commitments, dc.p, batch * 144, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(proofs, dout.p, batch * n * 144, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// ---- compressed outputs and the eth blob path (rank 1) -----------------------
+static int commit_fk20_compressed_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, uint8_t* d_commit48,
+                                      uint8_t* d_proofs48, cudaStream_t st) {
+    if (fk->chunk_len != 1) return B200_ERR_BAD_INPUT;
+    if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
+    if (n > fk->ks->n_g1) return B200_ERR_LEN_MISMATCH;
+    if (batch == 0) return B200_OK;
+    unsigned long long before = g_launch_count;
+    {
+        DevBuf work;
+        CKS(work.alloc(batch * n * sizeof(G1J), st));
+        const G1A* fb = nullptr;
+        CKS(ks_fixed_base(fk->ks, n, &fb, st));
+        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb));
+        launch_g1_compress(work.as<G1J>(), d_commit48, 1, batch, 1, n, 0, 0, st);
+    }
+    CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 0, nullptr, st, d_proofs48));
+    fk->last_launches = g_launch_count - before;
+    return B200_OK;
+}
+extern "C" int b200_commit_fk20_batch_compressed_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments48,
+                                                     void* d_proofs48, void* cuda_stream) {
+    CK(cudaSetDevice(fk->ks->fs->device));
+    return commit_fk20_compressed_dev(fk, d_polys, n, batch, (uint8_t*)d_commitments48, (uint8_t*)d_proofs48, (cudaStream_t)cuda_stream);
+}
+extern "C" int b200_commit_fk20_batch_compressed(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint8_t* commitments48,
+                                                 uint8_t* proofs48) {
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fk->ks->fs->device));
+    cudaStream_t st = nullptr;
+    DevBuf dp, dc, dout;
+    CKS(dp.alloc(batch * n * 32, st)); CKS(dc.alloc(batch * 48, st)); CKS(dout.alloc(batch * n * 48, st));
+    CK(cudaMemcpyAsync(dp.p, polys, batch * n * 32, cudaMemcpyHostToDevice, st));
+    CKS(commit_fk20_compressed_dev(fk, dp.p, n, batch, dc.as<uint8_t>(), dout.as<uint8_t>(), st));
+    CK(cudaMemcpyAsync(commitments48, dc.p, batch * 48, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(proofs48, dout.p, batch * n * 48, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+// ToCompressedG1 over an array of ABI points resident in HBM
+extern "C" int b200_g1_compress_dev(const void* d_points, size_t n, void* d_out48, void* cuda_stream) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    if (n == 0) return B200_OK;
+    CK(cudaSetDevice(g_device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DevBuf m;
+    CKS(m.alloc(n * sizeof(G1J), st));
+    launch_g1_from_abi((const uint64_t*)d_points, m.as<G1J>(), n, st);
+    launch_g1_compress(m.as<G1J>(), (uint8_t*)d_out48, n, 1, 1, n, 0, 0, st);
+    return check_launches();
+}
+extern "C" int b200_g1_to_compressed_batch(const uint64_t* points, size_t n, uint8_t* out48) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    if (n == 0) return B200_OK;
+    CK(cudaSetDevice(g_device));
+    cudaStream_t st = nullptr;
+    DevBuf in, out;
+    CKS(in.alloc(n * 144, st)); CKS(out.alloc(n * 48, st));
+    CK(cudaMemcpyAsync(in.p, points, n * 144, cudaMemcpyHostToDevice, st));
+    CKS(b200_g1_compress_dev(in.p, n, out.p, st));
+    CK(cudaMemcpyAsync(out48, out.p, n * 48, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+// eth.BlobToKZGCommitment over a batch (eth/helpers.go:98-103 PolynomialToKZGCommitment after
+// :264-273 BlobToPolynomial): `ks` holds the bit-reversed Lagrange setup (eth/globals.go:48), a blob is
+// n x 32 little-endian bytes.  ok[b] = 0 and an all-zero commitment when blob b holds an element >= r.
+extern "C" int b200_blob_to_kzg_commitment_batch(b200_ks* ks, const uint8_t* blobs, size_t n, size_t batch, uint8_t* out48, uint8_t* ok) {
+    if (n > ks->n_g1) return B200_ERR_LEN_MISMATCH;
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(ks->fs->device));
+    cudaStream_t st = nullptr;
+    if (n == 0) { for (size_t b = 0; b < batch; b++) { memset(out48 + 48 * b, 0, 48); out48[48 * b] = 0xC0; ok[b] = 1; } return B200_OK; }
+    DevBuf k, work, res, flags;
+    CKS(k.alloc(batch * n * 32, st)); CKS(work.alloc(batch * n * sizeof(G1J), st)); CKS(res.alloc(batch * 48, st));
+    CKS(flags.alloc(batch * 4, st));
+    std::vector<uint32_t> h_ok(batch, 1u);
+    CK(cudaMemcpyAsync(flags.p, h_ok.data(), batch * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k.p, blobs, batch * n * 32, cudaMemcpyHostToDevice, st));
+    launch_fr_check_canonical(k.as<uint64_t>(), n, batch, flags.as<uint32_t>(), st);
+    const G1A* fb = nullptr;
+    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb));
+    launch_g1_compress(work.as<G1J>(), res.as<uint8_t>(), 1, batch, 1, n, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out48, res.p, batch * 48, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_ok.data(), flags.p, batch * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t b = 0; b < batch; b++) {
+        ok[b] = h_ok[b] ? 1 : 0;
+        if (!h_ok[b]) memset(out48 + 48 * b, 0, 48);
+    }
     return B200_OK;
 }
 

@@ -65,6 +65,9 @@ void launch_toeplitz_coeffs_strided(const uint64_t* polys_canon, Fr* out, size_t
                                     cudaStream_t st);
 // out[i] = s^i (canonical limbs) for i < n; d_sq[j] = s^(2^j) (Montgomery), 40 entries
 void launch_fr_powers(const Fr* d_sq, Fr* out_canon, size_t n, cudaStream_t st);
+// bls/bignum_all.go:12-35 ValidFr over batch x n canonical elements: ok[b] (pre-set to 1) is cleared when
+// an element of blob b is >= r  (eth/helpers.go:264-273 BlobToPolynomial)
+void launch_fr_check_canonical(const uint64_t* vals, size_t n, size_t batch, uint32_t* ok, cudaStream_t st);
 // pointwise helpers on Montgomery arrays
 void launch_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n, cudaStream_t st);   // dst = a * b
 
@@ -74,6 +77,9 @@ void launch_g1_from_abi(const uint64_t* in, G1J* out, size_t n, cudaStream_t st)
 void launch_g1_to_abi(const G1J* in, uint64_t* out, size_t n, size_t batch, size_t estride, size_t bstride, int bitrev,
                       unsigned logn, cudaStream_t st);
 void launch_g1_fill_infinity(G1J* p, size_t n, cudaStream_t st);
+// same addressing as launch_g1_to_abi, output = 48-byte compressed points (bls/bls_kilic.go:114 ToCompressedG1)
+void launch_g1_compress(const G1J* in, uint8_t* out48, size_t n, size_t batch, size_t estride, size_t bstride, int bitrev,
+                        unsigned logn, cudaStream_t st);
 // one radix-2 stage over batch transforms of 2 * n_half points each; element i of blob b lives at
 // data[b * bstride + i * estride]; m = half block length of this stage.  DIT: (x0 + w x1, x0 - w x1),
 // DIF: (x0 + x1, w (x0 - x1)), w = progs[j * prog_stride] for position j inside the block.

@@ -487,4 +487,24 @@ void launch_toeplitz_coeffs_strided(const uint64_t* polys, Fr* out, size_t n, si
     k_toeplitz_coeffs_strided<<<grid_for(total, 256), 256, 0, st>>>(polys, out, n, chunk_len, batch); g_launch_count++;
 }
 
+// ------------------------------------------------------------------------------ blob validation
+__global__ void k_fr_check_canonical(const Fr* __restrict__ vals, size_t n, size_t batch, uint32_t* ok) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    Fr a = ld_vec(vals + t);
+    uint32_t cf = 0, d;
+    d = sub_cc(a.l[0], FrParams::mod(0), cf);
+#pragma unroll
+    for (int i = 1; i < 8; i++) d = subc_cc(a.l[i], FrParams::mod(i), cf);
+    (void)d;
+    if (subc(0u, 0u, cf) == 0) atomicAnd(ok + t / n, 0u);   // no borrow: a >= r
+}
+void launch_fr_check_canonical(const uint64_t* vals, size_t n, size_t batch, uint32_t* ok, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    size_t total = n * batch;
+    if (!total) return;
+    k_fr_check_canonical<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(vals), n, batch, ok);
+    g_launch_count++;
+}
+
 }  // namespace b200

@@ -73,6 +73,81 @@ void launch_g1_fill_infinity(G1J* p, size_t n, cudaStream_t st) {
     k_g1_fill_infinity<<<grid_for(n, 256), 256, 0, st>>>(p, n); g_launch_count++;
 }
 
+// ------------------------------------------------------------------------------ compression
+// ToCompressedG1 (bls/bls_kilic.go:114-116; ZCash 48-byte form: big-endian affine x, bit 7
+// "compressed", bit 6 infinity, bit 5 y > (p-1)/2) for whole arrays on the device: the step right
+// after the hot path (proofs and commitments leave the system compressed) and a third of the
+// device->host bytes.  One thread normalises COMP_GROUP points with a single Fermat inversion
+// (Montgomery's trick on the Z coordinates): ~45 Fp products per point instead of ~580.
+#define COMP_GROUP 16
+struct alignas(16) Comp48 { uint32_t w[12]; };
+__device__ __forceinline__ bool fp_canon_gt_half_dev(const Fp& y) {   // y > (p-1)/2, canonical limbs
+    constexpr uint32_t half[12] = B200_FP_HALF;
+    uint32_t cf = 0, t;
+    t = sub_cc(half[0], y.l[0], cf);
+#pragma unroll
+    for (int i = 1; i < 12; i++) t = subc_cc(half[i], y.l[i], cf);
+    (void)t;
+    return subc(0u, 0u, cf) != 0;   // borrow <=> half < y
+}
+static __device__ __noinline__ Fp fp_inv_fermat(const Fp* a) {         // a^(p-2); a != 0
+    constexpr uint32_t e[12] = B200_FP_MODM2;
+    Fp acc = *a;
+    for (int i = 379; i >= 0; i--) {                                  // bit 380 is the top bit of p - 2
+        acc = fp_sqr(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1u) acc = fp_mul(acc, *a);
+    }
+    return acc;
+}
+__device__ __forceinline__ size_t comp_src_index(size_t t, size_t n, size_t estride, size_t bstride, int bitrev, unsigned logn) {
+    size_t b = t / n, i = t % n;
+    size_t src = bitrev ? bitrev_u32((uint32_t)i, logn) : i;
+    return b * bstride + src * estride;
+}
+__global__ void __launch_bounds__(128) k_g1_compress(const G1J* __restrict__ in, Comp48* __restrict__ out, size_t n, size_t batch,
+                                                     size_t estride, size_t bstride, int bitrev, unsigned logn) {
+    const size_t total = n * batch;
+    const size_t t0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * COMP_GROUP;
+    if (t0 >= total) return;
+    const int cnt = (int)(total - t0 < COMP_GROUP ? total - t0 : COMP_GROUP);
+    Fp pre[COMP_GROUP];
+    Fp acc = Fp::one();
+    for (int k = 0; k < cnt; k++) {
+        Fp z = ld_vec(&in[comp_src_index(t0 + k, n, estride, bstride, bitrev, logn)].z);
+        pre[k] = acc;
+        if (!z.is_zero()) acc = fp_mul(acc, z);
+    }
+    Fp inv = fp_inv_fermat(&acc);
+    Fp raw_one = Fp::zero(); raw_one.l[0] = 1;                        // x * 1 / R: leaves Montgomery form
+    for (int k = cnt - 1; k >= 0; k--) {
+        G1J p = ld_vec(&in[comp_src_index(t0 + k, n, estride, bstride, bitrev, logn)]);
+        Comp48 c;
+        if (p.is_inf()) {
+#pragma unroll
+            for (int j = 0; j < 12; j++) c.w[j] = 0;
+            c.w[0] = 0xC0u;
+        } else {
+            Fp zi = fp_mul(inv, pre[k]);
+            inv = fp_mul(inv, p.z);
+            Fp zi2 = fp_sqr(zi);
+            Fp x = fp_mul(fp_mul(p.x, zi2), raw_one);
+            Fp y = fp_mul(fp_mul(p.y, fp_mul(zi2, zi)), raw_one);
+#pragma unroll
+            for (int j = 0; j < 12; j++) c.w[j] = __byte_perm(x.l[11 - j], 0u, 0x0123);   // big-endian bytes
+            c.w[0] |= 0x80u | (fp_canon_gt_half_dev(y) ? 0x20u : 0u);
+        }
+        out[t0 + k] = c;
+    }
+}
+void launch_g1_compress(const G1J* in, uint8_t* out48, size_t n, size_t batch, size_t estride, size_t bstride, int bitrev,
+                        unsigned logn, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n || !batch) return;
+    size_t groups = (n * batch + COMP_GROUP - 1) / COMP_GROUP;
+    k_g1_compress<<<grid_for(groups, 128), 128, 0, st>>>(in, reinterpret_cast<Comp48*>(out48), n, batch, estride, bstride, bitrev, logn);
+    g_launch_count++;
+}
+
 // ------------------------------------------------------------------------------ FFT stage
 // thread <-> (butterfly q, blob b) with b fastest: when batch is a multiple of 32 every lane of a
 // warp runs the same twiddle program on a different blob, so the digit branches are uniform.

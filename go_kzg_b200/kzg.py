@@ -118,6 +118,11 @@ def lib():
     L.b200_da_using_fk20_multi.argtypes = [vp, vp, sz, vp]
     L.b200_commit_fk20_batch.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200_commit_fk20_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+    L.b200_commit_fk20_batch_compressed.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.b200_commit_fk20_batch_compressed_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp]
+    L.b200_g1_compress_dev.argtypes = [vp, sz, vp, vp]
+    L.b200_g1_to_compressed_batch.argtypes = [vp, sz, vp]
+    L.b200_blob_to_kzg_commitment_batch.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200_fk20_multi_partial_dev.argtypes = [vp, vp, sz, sz, sz, vp, vp]
     L.b200_g1_sum_dev.argtypes = [vp, sz, sz, vp, vp]
     L.b200_fk20_multi_finish_dev.argtypes = [vp, vp, i32, vp, vp]
@@ -176,6 +181,14 @@ def g1_to_compressed(pts) -> np.ndarray:
     pts = _g1(pts)
     out = np.zeros((pts.shape[0], 48), dtype=np.uint8)
     lib().b200_g1_to_compressed_many(_p(out), _p(pts), pts.shape[0])
+    return out
+
+
+def g1_to_compressed_device(pts) -> np.ndarray:
+    """ToCompressedG1 over an array, normalised and compressed on the GPU (b200_g1_to_compressed_batch)."""
+    pts = _g1(pts)
+    out = np.zeros((pts.shape[0], 48), dtype=np.uint8)
+    _raise(lib().b200_g1_to_compressed_batch(_p(pts), pts.shape[0], _p(out)), what="ToCompressedG1 (device)")
     return out
 
 
@@ -337,6 +350,17 @@ class KZGSettings:
         _raise(lib().b200_commit_to_poly(self.h, _p(c), c.shape[0], _p(out)), what="CommitToPoly")
         return out
 
+    def blob_to_kzg_commitment_batch(self, blobs):
+        """eth.BlobToKZGCommitment (eth/helpers.go:264-273 + :98-103) for blobs of n x 32 little-endian bytes;
+        these settings must hold the bit-reversed Lagrange setup (eth/globals.go:48).
+        Returns (commitments (batch, 48) uint8, ok (batch,) bool); ok is False where an element is >= r."""
+        b = np.ascontiguousarray(blobs, dtype=np.uint8)
+        batch, n = b.shape[0], b.shape[1]
+        out = np.zeros((batch, 48), dtype=np.uint8)
+        ok = np.zeros(batch, dtype=np.uint8)
+        _raise(lib().b200_blob_to_kzg_commitment_batch(self.h, _p(b), n, batch, _p(out), _p(ok)), what="BlobToKZGCommitment")
+        return out, ok.astype(bool)
+
     def commit_to_poly_batch(self, coeffs) -> np.ndarray:
         c = np.ascontiguousarray(coeffs, dtype=np.uint64)
         out = np.zeros((c.shape[0], 18), dtype=np.uint64)
@@ -401,6 +425,16 @@ class FK20SingleSettings(_FK20Base):
         commits = np.zeros((batch, 18), dtype=np.uint64)
         proofs = np.zeros((batch, n, 18), dtype=np.uint64)
         _raise(lib().b200_commit_fk20_batch(self.h, _p(p), n, batch, _p(commits), _p(proofs)), what="commit+FK20Single")
+        return commits, proofs
+
+
+    def commit_fk20_batch_compressed(self, polys):
+        """commit_fk20_batch with 48-byte compressed outputs produced on the device."""
+        p = np.ascontiguousarray(polys, dtype=np.uint64)
+        batch, n = p.shape[0], p.shape[1]
+        commits = np.zeros((batch, 48), dtype=np.uint8)
+        proofs = np.zeros((batch, n, 48), dtype=np.uint8)
+        _raise(lib().b200_commit_fk20_batch_compressed(self.h, _p(p), n, batch, _p(commits), _p(proofs)), what="commit+FK20Single (compressed)")
         return commits, proofs
 
 

@@ -148,6 +148,23 @@ int b200_commit_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t n, size_t 
  * (a cudaStream_t, may be NULL for the default stream). */
 int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments,
                                void* d_proofs, void* cuda_stream);
+/* ------------------------------------------------------------------ compressed outputs, eth blobs --
+ * The callers of the path consume 48-byte compressed points (bls/bls_kilic.go:114-116 ToCompressedG1;
+ * eth/helpers.go:98-103, :199-202).  These entry points normalise and compress on the device (one
+ * inversion per 16 points), so a third of the bytes travels back to the host. */
+int b200_commit_fk20_batch_compressed(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint8_t* commitments48,
+                                      uint8_t* proofs48);
+int b200_commit_fk20_batch_compressed_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments48,
+                                          void* d_proofs48, void* cuda_stream);
+/* ToCompressedG1 over n points: device-resident ABI points -> device 48-byte strings; host-buffer form. */
+int b200_g1_compress_dev(const void* d_points, size_t n, void* d_out48, void* cuda_stream);
+int b200_g1_to_compressed_batch(const uint64_t* points, size_t n, uint8_t* out48);
+/* eth.BlobToKZGCommitment for `batch` blobs of n x 32 little-endian bytes (eth/helpers.go:264-273
+ * BlobToPolynomial + :98-103 PolynomialToKZGCommitment).  `ks` must hold the bit-reversed Lagrange
+ * setup (eth/globals.go:48).  ok[b] = 0 (and a zeroed output) where a field element is >= r
+ * (bls/bignum_all.go:12-35 ValidFr), matching BlobToPolynomial's `false`. */
+int b200_blob_to_kzg_commitment_batch(b200_ks* ks, const uint8_t* blobs, size_t n, size_t batch, uint8_t* out48, uint8_t* ok);
+
 /* ------------------------------------------------------------------ multi-GPU building blocks --
  * FK20 multi sharded by chunk offset: rank g computes the partial
  * hExtFFT of its offsets [off_begin, off_end) (fk20_multi.go:80-91 restricted to those files),

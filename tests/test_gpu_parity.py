@@ -314,6 +314,78 @@ def test_commit_fk20_batch_n4096(trusted_setup_bytes):
         assert L.b200_g1_equal(s.ctypes.data, single[i].ctypes.data) == 1
 
 
+# ------------------------------------------------------------------------------ compressed outputs, eth blobs
+def _brp(i, bits):
+    return int(format(i, "0%db" % bits)[::-1], 2)
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 250])
+def test_g1_compress_on_device(n, goldens):
+    """ToCompressedG1 (bls/bls_kilic.go:114) normalised and compressed on the GPU == the oracle's and the
+    host level-1 bytes: Jacobian inputs with Z != 1, infinities, group sizes around the 16-point
+    inversion batches; the reference's golden vector (bls/bls_test.go:13,18)."""
+    rnd = random.Random(n)
+    gen = cref.g1_generator()
+    pts = kzg.g1_mul_many(np.repeat(gen[None, :], n, axis=0), kzg.fr_from_ints([rnd.randrange(1, R) for _ in range(n)]))
+    gold = goldens["point_compression"]                     # bls/bls_test.go:13,18 TestPointCompression
+    if n > 2:
+        pts[n // 2] = 0                                     # infinity (Z == 0)
+        pts[n - 1] = gen                                    # Z == 1
+        pts[0] = kzg.g1_mul_many(gen[None, :], kzg.fr_from_ints([int(gold["scalar"])]))[0]
+    got = kzg.g1_to_compressed_device(pts)
+    assert np.array_equal(got, cref.g1_compress(pts))
+    assert np.array_equal(got, kzg.g1_to_compressed(pts))
+    if n > 2:
+        assert got[n // 2, 0] == 0xC0 and not got[n // 2, 1:].any()
+        assert list(got[0]) == gold["expected"]
+
+
+def test_commit_fk20_batch_compressed_matches_uncompressed(trusted_setup_bytes):
+    """The compressed-output form of the headline unit returns exactly ToCompressedG1 of the Jacobian results."""
+    fs = kzg.FFTSettings(13)
+    fk = kzg.FK20SingleSettings(kzg.KZGSettings(fs, _setup_8192(trusted_setup_bytes)), 8192)
+    polys = blob_polys(32, 4096, first_blob=500)
+    commits, proofs = fk.commit_fk20_batch(polys)
+    c48, p48 = fk.commit_fk20_batch_compressed(polys)
+    assert np.array_equal(c48, cref.g1_compress(commits))
+    for b in (0, 13, 31):
+        assert np.array_equal(p48[b], cref.g1_compress(proofs[b]))
+    assert np.array_equal(p48.reshape(-1, 48)[::97], kzg.g1_to_compressed(proofs.reshape(-1, 18)[::97]))
+
+
+def test_blob_to_kzg_commitment(trusted_setup_bytes):
+    """eth.BlobToKZGCommitment (eth/helpers.go:98-103, :264-273) over the bit-reversed Lagrange setup
+    (eth/globals.go:48): for evaluations v of a polynomial c on the natural domain, the blob is brp(v) and the
+    commitment is c(1337) G (known-secret closed form) == the oracle's LinCombG1 on the same inputs.
+    A field element >= r makes BlobToPolynomial fail: ok = False."""
+    s1, lag = trusted_setup_bytes
+    n, bits = 4096, 12
+    lagrange = kzg.g1_from_compressed(lag)
+    perm = np.array([_brp(i, bits) for i in range(n)])
+    fs = kzg.FFTSettings(bits)
+    ks = kzg.KZGSettings(fs, lagrange[perm])
+    batch = 5
+    blobs = np.zeros((batch, n, 32), dtype=np.uint8)
+    want = []
+    ofs = cref.FFTSettings(bits)
+    for b in range(batch):
+        v = random_fr_ints(n, 0xE7000000 + b)
+        coeffs = cref.limbs_to_fr(ofs.fft(cref.fr_to_limbs(v), True))
+        want.append(pyref.eval_poly(coeffs, 1337))
+        blob_vals = [v[perm[i]] for i in range(n)]
+        blobs[b] = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in blob_vals), dtype=np.uint8).reshape(n, 32)
+    got, ok = ks.blob_to_kzg_commitment_batch(blobs)
+    assert ok.all()
+    assert np.array_equal(got, cref.g1_compress(cref.g1_mul_gen(want)))
+    lin = cref.lincomb_g1(lagrange[perm], np.ascontiguousarray(blobs[0]).view(np.uint64).reshape(n, 4))
+    assert np.array_equal(got[0], cref.g1_compress(lin[None, :])[0])
+    bad = blobs.copy()
+    bad[3, 77] = np.frombuffer(R.to_bytes(32, "little"), dtype=np.uint8)          # == r: not a field element
+    got2, ok2 = ks.blob_to_kzg_commitment_batch(bad)
+    assert list(ok2) == [True, True, True, False, True]
+    assert np.array_equal(got2[[0, 1, 2, 4]], got[[0, 1, 2, 4]]) and not got2[3].any()
+
+
 # ------------------------------------------------------------------------------ zero poly / recovery
 def test_zero_poly_golden(goldens):
     """zero_poly_test.go:133-198 TestFFTSettings_ZeroPolyViaMultiplication_Python"""
