@@ -159,6 +159,8 @@ def run_ours(args):
     d_proofs = torch.zeros((B, N_COEFFS, 18), dtype=torch.int64, device="cuda")
     h_commit = torch.zeros((B, 18), dtype=torch.int64).pin_memory()
     h_proofs = torch.zeros((B, N_COEFFS, 18), dtype=torch.int64).pin_memory()
+    h_commit48 = torch.zeros((B, 48), dtype=torch.uint8).pin_memory()
+    h_proofs48 = torch.zeros((B, N_COEFFS, 48), dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")   # > 126 MB L2
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
@@ -173,6 +175,11 @@ def run_ours(args):
         rc = L.b200_commit_fk20_batch(fk.h, h_polys.data_ptr(), N_COEFFS, B, h_commit.data_ptr(), h_proofs.data_ptr())
         if rc:
             raise RuntimeError("b200_commit_fk20_batch: %s / %s" % (L.b200_strerror(rc), L.b200_last_cuda_error()))
+
+    def step_e2e_compressed():
+        rc = L.b200_commit_fk20_batch_compressed(fk.h, h_polys.data_ptr(), N_COEFFS, B, h_commit48.data_ptr(), h_proofs48.data_ptr())
+        if rc:
+            raise RuntimeError("b200_commit_fk20_batch_compressed: %s / %s" % (L.b200_strerror(rc), L.b200_last_cuda_error()))
 
     def barrier():
         if world > 1:
@@ -212,6 +219,15 @@ def run_ours(args):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    # same call with 48-byte compressed outputs produced on the device (what the callers of the path consume)
+    step_e2e_compressed()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e_compressed()
+    torch.cuda.synchronize()
+    e2e_c_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
 
     # results of the device path and the host path agree (same blobs)
@@ -254,6 +270,9 @@ def run_ours(args):
                    "parallelism": "blob-parallel replicas x%d" % world, "results_match_host_path": same},
         "e2e": {"value": round(world * B * K / e2e_s, 3), "unit": "blobs/s",
                 "h2d_bytes_per_step": int(B * N_COEFFS * 32), "d2h_bytes_per_step": int(B * (N_COEFFS + 1) * 144)},
+        "e2e_compressed": {"value": round(world * B * K / e2e_c_s, 3), "unit": "blobs/s", "h2d_bytes_per_step": int(B * N_COEFFS * 32),
+                           "d2h_bytes_per_step": int(B * (N_COEFFS + 1) * 48),
+                           "note": "b200_commit_fk20_batch_compressed: ToCompressedG1 on the device, 48 B per point back to the host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_g1_fft_stage", "achieved": round(achieved, 4), "peak": hbm_peak, "unit": "GB/s",

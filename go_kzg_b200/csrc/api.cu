@@ -1102,6 +1102,48 @@ extern "C" int b200_blob_to_kzg_commitment_batch(b200_ks* ks, const uint8_t* blo
     return B200_OK;
 }
 
+// eth.ComputeKZGProof for a batch (eth/helpers.go:179-203): polys are evaluations on the bit-reversed domain
+// (blob order), z one challenge per polynomial; proofs48 = ToCompressedG1(LinCombG1(lagrange, quotient)),
+// y = f(z) (canonical, may be NULL).  ok[b] = 0 for "invalid z challenge" (z in the domain) or an input >= r.
+extern "C" int b200_compute_kzg_proof_batch(b200_ks* ks, const uint64_t* polys, const uint64_t* z, size_t n, size_t batch,
+                                            uint8_t* proofs48, uint64_t* y_out, uint8_t* ok) {
+    b200_fs* fs = ks->fs;
+    if (n > fs->max_width) return B200_ERR_TOO_LARGE;
+    if (!is_pow2(n) || n < 16) return B200_ERR_NOT_POW2;
+    if (n > ks->n_g1) return B200_ERR_LEN_MISMATCH;          // "polynomial has invalid length"
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fs->device));
+    cudaStream_t st = nullptr;
+    const unsigned logn = log2u(n);
+    DevBuf f, dz, inv, part, ym, yc, q, work, res, flags;
+    CKS(f.alloc(batch * n * 32, st)); CKS(dz.alloc(batch * 32, st)); CKS(inv.alloc(batch * n * 32, st));
+    CKS(part.alloc(batch * (n / 16) * 32, st)); CKS(ym.alloc(batch * 32, st)); CKS(yc.alloc(batch * 32, st));
+    CKS(q.alloc(batch * n * 32, st)); CKS(work.alloc(batch * n * sizeof(G1J), st)); CKS(res.alloc(batch * 48, st));
+    CKS(flags.alloc(batch * 4, st));
+    std::vector<uint32_t> h_ok(batch, 1u);
+    CK(cudaMemcpyAsync(flags.p, h_ok.data(), batch * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(f.p, polys, batch * n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dz.p, z, batch * 32, cudaMemcpyHostToDevice, st));
+    launch_fr_check_canonical(f.as<uint64_t>(), n, batch, flags.as<uint32_t>(), st);
+    launch_fr_check_canonical(dz.as<uint64_t>(), 1, batch, flags.as<uint32_t>(), st);
+    launch_eval_form_quotient(fs->dom, f.as<uint64_t>(), dz.as<uint64_t>(), logn, batch, fr_inv_of_u64(n), inv.as<Fr>(), part.as<Fr>(),
+                              ym.as<Fr>(), yc.as<uint64_t>(), q.as<uint64_t>(), flags.as<uint32_t>(), st);
+    const G1A* fb = nullptr;
+    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, q.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb));
+    launch_g1_compress(work.as<G1J>(), res.as<uint8_t>(), 1, batch, 1, n, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(proofs48, res.p, batch * 48, cudaMemcpyDeviceToHost, st));
+    if (y_out) CK(cudaMemcpyAsync(y_out, yc.p, batch * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_ok.data(), flags.p, batch * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t b = 0; b < batch; b++) {
+        ok[b] = h_ok[b] ? 1 : 0;
+        if (!h_ok[b]) { memset(proofs48 + 48 * b, 0, 48); if (y_out) memset(y_out + 4 * b, 0, 32); }
+    }
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------ profiling
 namespace b200 {
 bool g_prof_on = false;

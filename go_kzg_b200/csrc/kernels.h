@@ -68,6 +68,11 @@ void launch_fr_powers(const Fr* d_sq, Fr* out_canon, size_t n, cudaStream_t st);
 // bls/bignum_all.go:12-35 ValidFr over batch x n canonical elements: ok[b] (pre-set to 1) is cleared when
 // an element of blob b is >= r  (eth/helpers.go:264-273 BlobToPolynomial)
 void launch_fr_check_canonical(const uint64_t* vals, size_t n, size_t batch, uint32_t* ok, cudaStream_t st);
+// eth/helpers.go:179-203 ComputeKZGProof, field side: y[b] = f_b(z_b) (bls/globals.go:106-153) and the quotient
+// q[b][i] = (f[b][i] - y[b]) / (D[i] - z[b]) on the bit-reversed domain of size 2^logn >= 16; ok[b] cleared if z[b] is in the domain
+void launch_eval_form_quotient(const FrDomain& dom, const uint64_t* f_canon, const uint64_t* z_canon, unsigned logn, size_t batch,
+                               const Fr& inv_n, Fr* inv_den, Fr* partial, Fr* y_mont, uint64_t* y_canon_or_null, uint64_t* q_canon,
+                               uint32_t* ok, cudaStream_t st);
 // pointwise helpers on Montgomery arrays
 void launch_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n, cudaStream_t st);   // dst = a * b
 

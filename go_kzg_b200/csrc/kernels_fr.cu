@@ -507,4 +507,87 @@ void launch_fr_check_canonical(const uint64_t* vals, size_t n, size_t batch, uin
     g_launch_count++;
 }
 
+// ------------------------------------------------------------------------------ evaluation-form proofs
+// eth.ComputeKZGProof (eth/helpers.go:179-203) with bls.EvaluatePolyInEvaluationForm (bls/globals.go:106-153)
+// for a batch of polynomials given by their evaluations on the bit-reversed domain D[i] = w^brp(i)
+// (eth/globals.go:60-67), one challenge z per polynomial:
+//     y    = (z^n - 1) / n * sum_i f_i D_i / (z - D_i)
+//     q_i  = (f_i - y) / (D_i - z)
+// Pass 1 inverts the n denominators (Montgomery's trick, EVAL_CHUNK per lane) and leaves a partial sum
+// per lane; pass 2 folds the partial sums into y; pass 3 forms the quotient (canonical, ready for the MSM).
+#define EVAL_CHUNK 16
+__device__ __forceinline__ size_t eval_domain_index(size_t i, unsigned logn, size_t stride) { return (size_t)(__brev((uint32_t)i) >> (32 - logn)) * stride; }
+__global__ void __launch_bounds__(128) k_eval_form_pass1(const Fr* __restrict__ f_canon, const Fr* __restrict__ z_canon,
+                                                         const Fr* __restrict__ expanded, size_t stride, size_t n, unsigned logn,
+                                                         size_t batch, Fr* inv_den, Fr* partial, uint32_t* ok) {
+    const size_t chunks = n / EVAL_CHUNK;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks * batch) return;
+    size_t b = t / chunks, lo = (t % chunks) * EVAL_CHUNK;
+    Fr z = fe_to_mont(ld_vec(z_canon + b));
+    Fr pre[EVAL_CHUNK];
+    Fr acc = Fr::one();
+    bool hit = false;
+    for (int k = 0; k < EVAL_CHUNK; k++) {
+        Fr d = fe_sub(ld_vec(expanded + eval_domain_index(lo + k, logn, stride)), z);    // D_i - z
+        pre[k] = acc;
+        if (d.is_zero()) hit = true; else acc = fe_mul(acc, d);
+    }
+    if (hit) atomicAnd(ok + b, 0u);                                                       // "invalid z challenge"
+    acc = fe_inv(acc);
+    Fr sum = Fr::zero();
+    for (int k = EVAL_CHUNK - 1; k >= 0; k--) {
+        Fr dom = ld_vec(expanded + eval_domain_index(lo + k, logn, stride));
+        Fr d = fe_sub(dom, z);
+        Fr inv = Fr::zero();
+        if (!d.is_zero()) { inv = fe_mul(acc, pre[k]); acc = fe_mul(acc, d); }
+        st_vec(inv_den + b * n + lo + k, inv);                                            // 1 / (D_i - z), Montgomery
+        Fr fi = fe_to_mont(ld_vec(f_canon + b * n + lo + k));
+        sum = fe_sub(sum, fe_mul(fe_mul(fi, dom), inv));                                  // + f_i D_i / (z - D_i)
+    }
+    st_vec(partial + t, sum);
+}
+// y[b] = (z^n - 1) / n * sum of the partial sums; one block per polynomial
+__global__ void __launch_bounds__(256) k_eval_form_pass2(const Fr* __restrict__ partial, size_t chunks, const Fr* __restrict__ z_canon,
+                                                         unsigned logn, Fr inv_n, Fr* y_mont, Fr* y_canon) {
+    __shared__ Fr sh[256];
+    size_t b = blockIdx.x;
+    Fr s = Fr::zero();
+    for (size_t i = threadIdx.x; i < chunks; i += blockDim.x) s = fe_add(s, ld_vec(partial + b * chunks + i));
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (unsigned w = blockDim.x / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] = fe_add(sh[threadIdx.x], sh[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Fr zn = fe_to_mont(ld_vec(z_canon + b));
+        for (unsigned k = 0; k < logn; k++) zn = fe_mul(zn, zn);                          // z^n, n = 2^logn
+        Fr y = fe_mul(fe_mul(fe_sub(zn, Fr::one()), inv_n), sh[0]);
+        st_vec(y_mont + b, y);
+        if (y_canon) st_vec(y_canon + b, fe_from_mont(y));
+    }
+}
+__global__ void k_eval_form_pass3(const Fr* __restrict__ f_canon, const Fr* __restrict__ inv_den, const Fr* __restrict__ y_mont,
+                                  size_t n, size_t batch, Fr* q_canon) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    Fr fi = fe_to_mont(ld_vec(f_canon + t));
+    Fr q = fe_mul(fe_sub(fi, ld_vec(y_mont + t / n)), ld_vec(inv_den + t));
+    st_vec(q_canon + t, fe_from_mont(q));
+}
+void launch_eval_form_quotient(const FrDomain& dom, const uint64_t* f_canon, const uint64_t* z_canon, unsigned logn, size_t batch,
+                               const Fr& inv_n, Fr* inv_den /* batch n */, Fr* partial /* batch n / 16 */, Fr* y_mont /* batch */,
+                               uint64_t* y_canon_or_null, uint64_t* q_canon /* batch n */, uint32_t* ok, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    const size_t n = (size_t)1 << logn, chunks = n / EVAL_CHUNK;
+    if (!batch) return;
+    const Fr* f = reinterpret_cast<const Fr*>(f_canon);
+    const Fr* z = reinterpret_cast<const Fr*>(z_canon);
+    k_eval_form_pass1<<<grid_for(chunks * batch, 128), 128, 0, st>>>(f, z, dom.expanded, dom.max_width >> logn, n, logn, batch, inv_den, partial, ok);
+    k_eval_form_pass2<<<(unsigned)batch, 256, 0, st>>>(partial, chunks, z, logn, inv_n, y_mont, reinterpret_cast<Fr*>(y_canon_or_null));
+    k_eval_form_pass3<<<grid_for(n * batch, 256), 256, 0, st>>>(f, inv_den, y_mont, n, batch, reinterpret_cast<Fr*>(q_canon));
+    g_launch_count += 3;
+}
+
 }  // namespace b200

@@ -123,6 +123,7 @@ def lib():
     L.b200_g1_compress_dev.argtypes = [vp, sz, vp, vp]
     L.b200_g1_to_compressed_batch.argtypes = [vp, sz, vp]
     L.b200_blob_to_kzg_commitment_batch.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.b200_compute_kzg_proof_batch.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
     L.b200_fk20_multi_partial_dev.argtypes = [vp, vp, sz, sz, sz, vp, vp]
     L.b200_g1_sum_dev.argtypes = [vp, sz, sz, vp, vp]
     L.b200_fk20_multi_finish_dev.argtypes = [vp, vp, i32, vp, vp]
@@ -360,6 +361,20 @@ class KZGSettings:
         ok = np.zeros(batch, dtype=np.uint8)
         _raise(lib().b200_blob_to_kzg_commitment_batch(self.h, _p(b), n, batch, _p(out), _p(ok)), what="BlobToKZGCommitment")
         return out, ok.astype(bool)
+
+    def compute_kzg_proof_batch(self, polys, zs):
+        """eth.ComputeKZGProof (eth/helpers.go:179-203) per polynomial (evaluations in blob order) and challenge.
+        Returns (proofs (batch, 48) uint8, y (batch, 4) uint64 canonical, ok (batch,) bool)."""
+        p = np.ascontiguousarray(polys, dtype=np.uint64)
+        z = np.ascontiguousarray(zs, dtype=np.uint64).reshape(-1, 4)
+        batch, n = p.shape[0], p.shape[1]
+        assert z.shape[0] == batch
+        proofs = np.zeros((batch, 48), dtype=np.uint8)
+        y = np.zeros((batch, 4), dtype=np.uint64)
+        ok = np.zeros(batch, dtype=np.uint8)
+        _raise(lib().b200_compute_kzg_proof_batch(self.h, _p(p), _p(z), n, batch, _p(proofs), _p(y), _p(ok)),
+               errors=(TOO_LARGE, NOT_POW2, LEN_MISMATCH), what="ComputeKZGProof")
+        return proofs, y, ok.astype(bool)
 
     def commit_to_poly_batch(self, coeffs) -> np.ndarray:
         c = np.ascontiguousarray(coeffs, dtype=np.uint64)

@@ -164,6 +164,13 @@ int b200_g1_to_compressed_batch(const uint64_t* points, size_t n, uint8_t* out48
  * setup (eth/globals.go:48).  ok[b] = 0 (and a zeroed output) where a field element is >= r
  * (bls/bignum_all.go:12-35 ValidFr), matching BlobToPolynomial's `false`. */
 int b200_blob_to_kzg_commitment_batch(b200_ks* ks, const uint8_t* blobs, size_t n, size_t batch, uint8_t* out48, uint8_t* ok);
+/* eth.ComputeKZGProof for a batch (eth/helpers.go:179-203, with bls.EvaluatePolyInEvaluationForm
+ * bls/globals.go:106-153): polys[b] = n evaluations on the bit-reversed domain (eth/globals.go:60-67),
+ * z[b] the challenge.  proofs48[b] = compressed LinCombG1(lagrange setup, (f - y) / (D - z)), y[b] = f_b(z_b)
+ * (canonical, may be NULL).  ok[b] = 0 where the reference returns an error ("invalid z challenge": z in
+ * the domain) or an input is not a field element.  n: power of two >= 16, <= both settings' widths. */
+int b200_compute_kzg_proof_batch(b200_ks* ks, const uint64_t* polys, const uint64_t* z, size_t n, size_t batch,
+                                 uint8_t* proofs48, uint64_t* y, uint8_t* ok);
 
 /* ------------------------------------------------------------------ multi-GPU building blocks --
  * FK20 multi sharded by chunk offset: rank g computes the partial

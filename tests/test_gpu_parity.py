@@ -386,6 +386,40 @@ def test_blob_to_kzg_commitment(trusted_setup_bytes):
     assert np.array_equal(got2[[0, 1, 2, 4]], got[[0, 1, 2, 4]]) and not got2[3].any()
 
 
+def test_compute_kzg_proof_evaluation_form(trusted_setup_bytes):
+    """eth.ComputeKZGProof (eth/helpers.go:179-203) + EvaluatePolyInEvaluationForm (bls/globals.go:106-153):
+    y == p(z) for the interpolating polynomial p (oracle inverse NTT + Horner, independent of the barycentric
+    formula) and proof == ((p(s) - y) / (s - z)) G for the known secret s = 1337; z inside the domain is the
+    reference's "invalid z challenge" error."""
+    s1, lag = trusted_setup_bytes
+    n, bits = 4096, 12
+    perm = np.array([_brp(i, bits) for i in range(n)])
+    fs = kzg.FFTSettings(bits)
+    ks = kzg.KZGSettings(fs, kzg.g1_from_compressed(lag)[perm])
+    ofs = cref.FFTSettings(bits)
+    batch = 4
+    polys = np.zeros((batch, n, 4), dtype=np.uint64)
+    zs, want_y, want_q = [], [], []
+    w = pow(7, (R - 1) // n, R)
+    for b in range(batch):
+        v = random_fr_ints(n, 0xE8000000 + b)
+        coeffs = cref.limbs_to_fr(ofs.fft(cref.fr_to_limbs(v), True))
+        z = random_fr_ints(1, 0xE9000000 + b)[0] if b != 2 else pow(w, int(perm[5]), R)      # blob 2: z == D[5]
+        zs.append(z)
+        y = pyref.eval_poly(coeffs, z)
+        want_y.append(y)
+        want_q.append((pyref.eval_poly(coeffs, 1337) - y) * pow((1337 - z) % R, -1, R) % R if b != 2 else 0)
+        polys[b] = kzg.fr_from_ints([v[perm[i]] for i in range(n)])
+    proofs, y, ok = ks.compute_kzg_proof_batch(polys, kzg.fr_from_ints(zs))
+    assert list(ok) == [True, True, False, True]
+    good = [0, 1, 3]
+    assert [kzg.fr_to_ints(y[b:b + 1])[0] for b in good] == [want_y[b] for b in good]
+    assert np.array_equal(proofs[good], cref.g1_compress(cref.g1_mul_gen([want_q[b] for b in good])))
+    assert not proofs[2].any()
+    with pytest.raises(kzg.KZGError):
+        ks.compute_kzg_proof_batch(polys[:, :100], kzg.fr_from_ints(zs))               # not a power of two
+
+
 # ------------------------------------------------------------------------------ zero poly / recovery
 def test_zero_poly_golden(goldens):
     """zero_poly_test.go:133-198 TestFFTSettings_ZeroPolyViaMultiplication_Python"""
