@@ -355,12 +355,24 @@ static int dev_zero_poly(b200_fs* fs, const std::vector<uint32_t>& h_missing, co
     for (size_t b = 0; b < batch; b++) if (h_nmiss[b] > max_missing) max_missing = h_nmiss[b];
     DevBuf miss, cnt, partial;
     CKS(miss.alloc(h_missing.size() * 4, st)); CKS(cnt.alloc(batch * 4, st));
-    CKS(partial.alloc(batch * zero_eval_segments(max_missing) * n * sizeof(Fr), st));
     CK(cudaMemcpyAsync(miss.p, h_missing.data(), h_missing.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(cnt.p, h_nmiss.data(), batch * 4, cudaMemcpyHostToDevice, st));
-    launch_zero_eval(fs->dom, n, batch, miss.as<uint32_t>(), cnt.as<uint32_t>(), pitch, max_missing, partial.as<Fr>(), d_zero_eval, st);
-    CKS(check_launches());
-    CKS(dev_fr_fft(fs, d_zero_eval, d_zero_poly, log2u(n), batch, true, st));
+    const size_t mp = zero_poly_tree_size(max_missing);
+    if (max_missing >= 256 && mp <= n && max_missing < n) {
+        // large sets: coefficients through the product tree, evaluations with one forward NTT
+        DevBuf ca, cb, padded, tmp;
+        CKS(ca.alloc(batch * mp * sizeof(Fr), st)); CKS(cb.alloc(batch * mp * sizeof(Fr), st));
+        CKS(padded.alloc(batch * 2 * mp * sizeof(Fr), st)); CKS(tmp.alloc(batch * 2 * mp * sizeof(Fr), st));
+        launch_zero_poly_tree(fs->dom, n, batch, miss.as<uint32_t>(), cnt.as<uint32_t>(), pitch, mp, ca.as<Fr>(), cb.as<Fr>(),
+                              padded.as<Fr>(), tmp.as<Fr>(), d_zero_poly, st);
+        CKS(check_launches());
+        CKS(dev_fr_fft(fs, d_zero_poly, d_zero_eval, log2u(n), batch, false, st));
+    } else {
+        CKS(partial.alloc(batch * zero_eval_segments(max_missing) * n * sizeof(Fr), st));
+        launch_zero_eval(fs->dom, n, batch, miss.as<uint32_t>(), cnt.as<uint32_t>(), pitch, max_missing, partial.as<Fr>(), d_zero_eval, st);
+        CKS(check_launches());
+        CKS(dev_fr_fft(fs, d_zero_eval, d_zero_poly, log2u(n), batch, true, st));
+    }
     CK(cudaStreamSynchronize(st));   // h_missing / h_nmiss are the caller's stack vectors
     return B200_OK;
 }

@@ -51,6 +51,12 @@ void launch_das_fft_extension(const FrDomain& dom, Fr* vals, unsigned logn, size
 // zero_poly.go:116-217 (evaluation side): zero_eval[b][j] = prod_i (w^j - w^missing[b][i]) for j < n;
 // missing: [batch][miss_pitch] u32 indices, nmiss[b] of them valid; partial: [batch][segments][n] scratch
 size_t zero_eval_segments(size_t max_missing);
+// product-tree route for large missing sets: zero_poly[b][0..n) (Montgomery coefficients); mp = zero_poly_tree_size(max
+// missing) <= n padded roots per list; coef_a, coef_b: batch * mp scratch each, padded, ntt_tmp: batch * 2 mp each
+size_t zero_poly_tree_size(size_t max_missing);
+void launch_zero_poly_tree(const FrDomain& dom, size_t n, size_t batch, const uint32_t* d_missing, const uint32_t* d_nmiss,
+                           size_t miss_pitch, size_t mp, Fr* coef_a, Fr* coef_b, Fr* padded, Fr* ntt_tmp, Fr* zero_poly,
+                           cudaStream_t st);
 void launch_zero_eval(const FrDomain& dom, size_t n, size_t batch, const uint32_t* d_missing, const uint32_t* d_nmiss,
                       size_t miss_pitch, size_t max_missing, Fr* partial, Fr* zero_eval, cudaStream_t st);
 void launch_fr_mul_masked(Fr* dst, const Fr* a, const Fr* c, const uint8_t* present, size_t total, cudaStream_t st);

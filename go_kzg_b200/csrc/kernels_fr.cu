@@ -359,6 +359,111 @@ void launch_zero_eval(const FrDomain& dom, size_t n, size_t batch, const uint32_
 }
 size_t zero_eval_segments(size_t max_missing) { size_t s = (max_missing + ZP_SEG - 1) / ZP_SEG; return s ? s : 1; }
 
+// ---- product tree for large missing sets --------------------------------------------------------------
+// The direct evaluation above costs n * |missing| products (1.3 * 10^8 at n = 2^14, half missing).  For large
+// sets the coefficients of Z are built like zero_poly.go:17-113 does -- leaves of ZP_LEAF roots multiplied out
+// directly, then pairwise products through NTTs -- and evaluated with one forward NTT.  Differences that do not
+// change the polynomial: binary instead of 4-way reduction, monic factors stored without their leading 1
+// ((X^d + p)(X^d + q) = X^2d + X^d (p + q) + p q, so a size-2d cyclic convolution is exact), and every
+// list padded to ZP_LEAF * 2^L roots with the root 0 (a factor X^k that is shifted out at the end).
+#define ZP_LEAF 32
+// coef[b][leaf][0..32): low coefficients of prod_i (X - r_i), r_i = w^missing or 0 (padding)
+__global__ void __launch_bounds__(128) k_zp_leaves(const Fr* __restrict__ expanded, size_t stride, const uint32_t* __restrict__ missing,
+                                                   const uint32_t* __restrict__ nmiss, size_t miss_pitch, size_t leaves, size_t batch,
+                                                   Fr* __restrict__ coef) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= leaves * batch) return;
+    size_t b = t / leaves, leaf = t % leaves;
+    const uint32_t cnt = nmiss[b];
+    Fr c[ZP_LEAF];
+    for (int deg = 0; deg < ZP_LEAF; deg++) {
+        size_t ri = leaf * ZP_LEAF + deg;
+        Fr r = ri < cnt ? ld_vec(expanded + (size_t)missing[b * miss_pitch + ri] * stride) : Fr::zero();
+        // (X^deg + c) (X - r): new c_deg = c_(deg-1) - r, c_k = c_(k-1) - r c_k, c_0 = -r c_0
+        if (deg == 0) { c[0] = fe_neg(r); continue; }
+        c[deg] = fe_sub(c[deg - 1], r);
+        for (int k = deg - 1; k >= 1; k--) c[k] = fe_sub(c[k - 1], fe_mul(r, c[k]));
+        c[0] = fe_neg(fe_mul(r, c[0]));
+    }
+    for (int k = 0; k < ZP_LEAF; k++) st_vec(coef + t * ZP_LEAF + k, c[k]);
+}
+// padded[node][0..d) = coef[node][0..d), padded[node][d..2d) = 0
+__global__ void k_zp_pad(const Fr* __restrict__ coef, Fr* __restrict__ padded, size_t d, size_t total /* nodes * 2d */) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    size_t node = t / (2 * d), k = t % (2 * d);
+    st_vec(padded + t, k < d ? ld_vec(coef + node * d + k) : Fr::zero());
+}
+// prod[pair][k] = padded[2 pair][k] * padded[2 pair + 1][k]   (transform domain, 2d values per node)
+__global__ void k_zp_pointwise(const Fr* __restrict__ padded, Fr* __restrict__ prod, size_t d2, size_t total /* pairs * 2d */) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    size_t pair = t / d2, k = t % d2;
+    st_vec(prod + t, fe_mul(ld_vec(padded + (2 * pair) * d2 + k), ld_vec(padded + (2 * pair + 1) * d2 + k)));
+}
+// next[pair][k] = (p q)[k] + (k >= d ? p[k - d] + q[k - d] : 0)
+__global__ void k_zp_combine(const Fr* __restrict__ prod, const Fr* __restrict__ coef, Fr* __restrict__ next, size_t d,
+                             size_t total /* pairs * 2d */) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    size_t pair = t / (2 * d), k = t % (2 * d);
+    Fr v = ld_vec(prod + t);
+    if (k >= d) v = fe_add(v, fe_add(ld_vec(coef + (2 * pair) * d + (k - d)), ld_vec(coef + (2 * pair + 1) * d + (k - d))));
+    st_vec(next + t, v);
+}
+// zero_poly[b][i] = coefficient i + (mp - nmiss[b]) of X^mp + coef[b]   (i < n); all zero if nothing is missing
+__global__ void k_zp_finish(const Fr* __restrict__ coef, const uint32_t* __restrict__ nmiss, size_t mp, size_t n, size_t batch,
+                            Fr* __restrict__ zero_poly) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    size_t b = t / n, i = t % n;
+    const uint32_t cnt = nmiss[b];
+    size_t src = i + (mp - cnt);
+    Fr v = Fr::zero();
+    if (cnt) { if (src < mp) v = ld_vec(coef + b * mp + src); else if (src == mp) v = Fr::one(); }
+    st_vec(zero_poly + t, v);
+}
+size_t zero_poly_tree_size(size_t max_missing) {       // padded root count ZP_LEAF * 2^L
+    size_t mp = ZP_LEAF;
+    while (mp < max_missing) mp <<= 1;
+    return mp;
+}
+void launch_zero_poly_tree(const FrDomain& dom, size_t n, size_t batch, const uint32_t* d_missing, const uint32_t* d_nmiss,
+                           size_t miss_pitch, size_t mp, Fr* coef_a /* batch mp */, Fr* coef_b /* batch mp */,
+                           Fr* padded /* batch 2 mp */, Fr* ntt_tmp /* batch 2 mp */, Fr* zero_poly /* batch n */, cudaStream_t st) {
+    {
+        ProfScope prof_scope(PROF_MISC, st);
+        size_t leaves = mp / ZP_LEAF;
+        k_zp_leaves<<<grid_for(leaves * batch, 128), 128, 0, st>>>(dom.expanded, dom.max_width / n, d_missing, d_nmiss, miss_pitch, leaves, batch, coef_a);
+        g_launch_count++;
+    }
+    Fr* cur = coef_a; Fr* nxt = coef_b;
+    for (size_t d = ZP_LEAF; d < mp; d <<= 1) {
+        const size_t nodes = batch * (mp / d), pairs = nodes / 2, d2 = 2 * d;
+        unsigned logd2 = 0; while (((size_t)1 << logd2) < d2) logd2++;
+        {
+            ProfScope prof_scope(PROF_MISC, st);
+            k_zp_pad<<<grid_for(nodes * d2, 256), 256, 0, st>>>(cur, padded, d, nodes * d2); g_launch_count++;
+        }
+        launch_fr_ntt(dom, padded, padded, ntt_tmp, logd2, nodes, false, nullptr, st);
+        {
+            ProfScope prof_scope(PROF_MISC, st);
+            k_zp_pointwise<<<grid_for(pairs * d2, 256), 256, 0, st>>>(padded, nxt, d2, pairs * d2); g_launch_count++;
+        }
+        Fr inv = fe_inv(fe_to_mont([&] { Fr v = Fr::zero(); v.l[0] = (uint32_t)d2; v.l[1] = (uint32_t)((uint64_t)d2 >> 32); return v; }()));
+        launch_fr_ntt(dom, nxt, nxt, ntt_tmp, logd2, pairs, true, &inv, st);
+        {
+            ProfScope prof_scope(PROF_MISC, st);
+            k_zp_combine<<<grid_for(pairs * d2, 256), 256, 0, st>>>(nxt, cur, padded, d, pairs * d2); g_launch_count++;
+        }
+        // the combined level sits in `padded` (first batch * mp elements): make it the current compact buffer
+        cudaMemcpyAsync(cur, padded, pairs * d2 * sizeof(Fr), cudaMemcpyDeviceToDevice, st);
+    }
+    ProfScope prof_scope(PROF_MISC, st);
+    k_zp_finish<<<grid_for(n * batch, 256), 256, 0, st>>>(cur, d_nmiss, mp, n, batch, zero_poly); g_launch_count++;
+    (void)nxt;
+}
+
 // ------------------------------------------------------------------------------ recovery helpers
 // dst[b][i] = present[b][i] ? a[b][i] * c[b][i] : 0          recover_from_samples.go:60-67
 __global__ void k_fr_mul_masked(Fr* dst, const Fr* a, const Fr* c, const uint8_t* __restrict__ present, size_t total) {
