@@ -444,6 +444,7 @@ typedef Fe<FrParams> Fr;
 
 }  // namespace b200
 #include "field_fp64_impl.cuh"
+#include "field_karatsuba.cuh"
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------
@@ -486,6 +487,11 @@ static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) {
     if (fp_on_fp64_pipe()) return fe_sqr_fp64(x);
     return fe_sqr(x);
 }
+#elif defined(B200_KARATSUBA)
+// Karatsuba product half + m * p-only reduction rows (field_karatsuba.cuh); the square keeps fe_sqr
+// (the Karatsuba square needs more FMA-pipe cycles than it saves once its carry adds are counted).
+static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul_k(x, y); }
+static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { Fp x = *a; return fe_sqr(x); }
 #else
 static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul(x, y); }
 static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { Fp x = *a; return fe_sqr(x); }
