@@ -944,6 +944,70 @@ extern "C" int b200_fk20_multi_finish_dev(b200_fk* fk, const void* d_h_ext_fft, 
     return check_launches();
 }
 
+// Sharded form of b200_fk20_multi_finish_dev for `world` = 2^s ranks that all hold the summed hExtFFT
+// (fk20_multi.go:93-106 on several GPUs).  A DIF transform splits after s stages into 2^s independent
+// transforms on contiguous blocks, a DIT transform (bit-reversed input) is block-local until its last s stages:
+//   local:  rank r takes the input down to its block with s half stages (only the outputs it needs), runs the
+//           remaining inverse stages, clears the odd slots (= the upper half of h in natural order,
+//           fk20_multi.go:100-103) and runs the block-local forward stages;  d_block: k2 / world internal points
+//   merge:  after an all-gather of the blocks in rank order, the last s forward stages and the output conversion.
+// Per rank ~ (1 + 2 (log2 k2 - s) / 2^s + 3 s) k2 / 2 twiddle products instead of 2 log2 k2 * k2 / 2.
+extern "C" int b200_fk20_multi_finish_local_dev(b200_fk* fk, const void* d_h_ext_fft, size_t rank, size_t world, void* d_block,
+                                                void* cuda_stream) {
+    CK(cudaSetDevice(fk->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    b200_fs* fs = fk->ks->fs;
+    const size_t k2 = fk->n2 / fk->chunk_len;
+    const unsigned logk2 = log2u(k2);
+    if (!is_pow2(world) || rank >= world || world * 2 > k2) return B200_ERR_BAD_INPUT;
+    const unsigned s = log2u(world);
+    const size_t blk = k2 >> s;
+    const unsigned logblk = logk2 - s;
+    const ScalarProgram *inv_progs, *fwd_progs;
+    CKS(fs_programs(fs, 1, 0, &inv_progs));
+    CKS(fs_programs(fs, 0, 0, &fwd_progs));
+    const size_t halfw = fs->max_width / 2;
+    DevBuf h, t0, t1;
+    CKS(h.alloc(k2 * sizeof(G1J), st));
+    launch_g1_from_abi((const uint64_t*)d_h_ext_fft, h.as<G1J>(), k2, st);
+    G1J* cur = h.as<G1J>();
+    if (s > 0) { CKS(t0.alloc((k2 / 2) * sizeof(G1J), st)); CKS(t1.alloc((k2 / 4 ? k2 / 4 : 1) * sizeof(G1J), st)); }
+    size_t m = k2 / 2;
+    for (unsigned lvl = 0; lvl < s; lvl++, m >>= 1) {
+        const int lower = (int)((rank >> (s - 1 - lvl)) & 1);             // block index, most significant bit first
+        G1J* out = (lvl + 1 == s) ? (G1J*)d_block : ((lvl & 1) ? t1.as<G1J>() : t0.as<G1J>());
+        launch_g1_dif_half_stage(cur, out, m, lower, inv_progs, halfw / m, st);
+        cur = out;
+    }
+    G1J* block = (G1J*)d_block;
+    if (s == 0) CK(cudaMemcpyAsync(block, cur, k2 * sizeof(G1J), cudaMemcpyDeviceToDevice, st));
+    for (size_t mm = blk / 2; mm >= 1; mm >>= 1) launch_g1_fft_stage(block, blk / 2, 1, mm, 1, blk, true, inv_progs, halfw / mm, st);
+    static G1J* d_inf = nullptr;
+    if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }
+    launch_g1_copy(block + 1, 2, blk, d_inf, 0, 0, blk / 2, 1, 0, 0, st);
+    for (size_t mm = 1; mm <= blk / 2; mm <<= 1) launch_g1_fft_stage(block, blk / 2, 1, mm, 1, blk, false, fwd_progs, halfw / mm, st);
+    (void)logblk;
+    return check_launches();
+}
+extern "C" int b200_fk20_multi_finish_merge_dev(b200_fk* fk, const void* d_blocks, size_t world, int reverse_bits, void* d_proofs,
+                                                void* cuda_stream) {
+    CK(cudaSetDevice(fk->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    b200_fs* fs = fk->ks->fs;
+    const size_t k2 = fk->n2 / fk->chunk_len;
+    const unsigned logk2 = log2u(k2);
+    if (!is_pow2(world) || world * 2 > k2) return B200_ERR_BAD_INPUT;
+    const ScalarProgram* fwd_progs;
+    CKS(fs_programs(fs, 0, 0, &fwd_progs));
+    const size_t halfw = fs->max_width / 2;
+    DevBuf h;
+    CKS(h.alloc(k2 * sizeof(G1J), st));
+    CK(cudaMemcpyAsync(h.p, d_blocks, k2 * sizeof(G1J), cudaMemcpyDeviceToDevice, st));
+    for (size_t mm = k2 / world; mm <= k2 / 2; mm <<= 1) launch_g1_fft_stage(h.as<G1J>(), k2 / 2, 1, mm, 1, k2, false, fwd_progs, halfw / mm, st);
+    launch_g1_to_abi(h.as<G1J>(), (uint64_t*)d_proofs, k2, 1, 1, k2, reverse_bits ? 1 : 0, logk2, st);
+    return check_launches();
+}
+
 extern "C" int b200_commit_partial_dev(b200_ks* ks, const void* d_coeffs, size_t begin, size_t end, void* d_out, void* cuda_stream) {
     if (begin > end || end > ks->n_g1) return B200_ERR_BAD_INPUT;
     CK(cudaSetDevice(ks->device));

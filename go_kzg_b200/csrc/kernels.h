@@ -96,6 +96,9 @@ void launch_g1_compress(const G1J* in, uint8_t* out48, size_t n, size_t batch, s
 // DIF: (x0 + x1, w (x0 - x1)), w = progs[j * prog_stride] for position j inside the block.
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
                          const ScalarProgram* progs, size_t prog_stride, cudaStream_t st);
+// DIF stage of one transform keeping one half of the outputs: out[i] = in[i] + in[i + m] (lower = 0) or
+// progs[i * prog_stride] * (in[i] - in[i + m]) (lower = 1), i < m
+void launch_g1_dif_half_stage(const G1J* in, G1J* out, size_t m, int lower, const ScalarProgram* progs, size_t prog_stride, cudaStream_t st);
 // out[b * out_bstride + i] = k[b * n + i] * pts[b * pts_bstride + i]   (pts_bstride = 0: shared bases)
 void launch_g1_mul_var(const G1J* pts, size_t pts_bstride, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride,
                        size_t n, size_t batch, cudaStream_t st);

@@ -186,6 +186,26 @@ void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_
     g_launch_count++;
 }
 
+// One decimation-in-frequency stage of a single transform, keeping only the half of the outputs that a
+// rank owning one of the 2^s output blocks needs: out[i] = in[i] + in[i + m] (upper block) or
+// w^i (in[i] - in[i + m]) (lower block), i < m.  s such stages take the all-gathered input of size n down
+// to the rank's block of size n / 2^s with 1/2 + 1/4 + .. of the butterflies instead of s n / 2.
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_dif_half_stage(const G1J* __restrict__ in, G1J* __restrict__ out, size_t m, int lower,
+                                                                         const ScalarProgram* __restrict__ progs, size_t prog_stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    G1J x0 = ld_vec(in + i), x1 = ld_vec(in + i + m), s, d;
+    g1_add_sub_ni(&s, &d, &x0, &x1);
+    if (lower) { g1_mul_program(&x1, &d, progs + i * prog_stride); st_vec(out + i, x1); }
+    else st_vec(out + i, s);
+}
+void launch_g1_dif_half_stage(const G1J* in, G1J* out, size_t m, int lower, const ScalarProgram* progs, size_t prog_stride, cudaStream_t st) {
+    ProfScope prof_scope(PROF_G1_FFT_STAGE, st);
+    if (!m) return;
+    k_g1_dif_half_stage<<<grid_for(m, G1_BLOCK), G1_BLOCK, 0, st>>>(in, out, m, lower, progs, prog_stride);
+    g_launch_count++;
+}
+
 // ------------------------------------------------------------------------------ scalar muls
 __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_var(const G1J* pts, size_t pts_bstride,
                                                     const Fr* __restrict__ k, int k_is_mont, G1J* out,

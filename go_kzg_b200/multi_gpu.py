@@ -2,7 +2,8 @@
 
 * FK20 multi sharded by chunk offset (config 5): every rank computes the partial hExtFFT of its
   offsets, the partials are all-gathered as raw limbs (NCCL has no elliptic-curve reduction, so the
-  "G1 allreduce" is all-gather + a local add kernel) and every rank finishes the two G1 transforms;
+  "G1 allreduce" is all-gather + a local add kernel); the two G1 transforms are then block-sharded as
+  well (power-of-two worlds): block-local stages, one all-gather of the blocks, the last log2(world) stages;
 * LinCombG1 / CommitToPoly sharded by point range: partial sums (144 B each) are all-gathered and
   added locally.
 
@@ -62,7 +63,15 @@ def da_using_fk20_multi_sharded(fk: "kzg.FK20MultiSettings", poly: np.ndarray, d
     else:
         d_sum = d_part
     d_out = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
-    _check(L.b200_fk20_multi_finish_dev(fk.h, d_sum.data_ptr(), 1, d_out.data_ptr(), sp), "FK20 multi finish")
+    if world > 1 and world & (world - 1) == 0 and 2 * world <= k2:
+        # the two G1 transforms, block-sharded: local stages, one all-gather of the blocks, the last log2(world) stages
+        d_block = torch.zeros((k2 // world, 18), dtype=torch.int64, device="cuda")
+        _check(L.b200_fk20_multi_finish_local_dev(fk.h, d_sum.data_ptr(), rank, world, d_block.data_ptr(), sp), "FK20 multi finish (local)")
+        blocks = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(blocks, d_block)
+        _check(L.b200_fk20_multi_finish_merge_dev(fk.h, blocks.data_ptr(), world, 1, d_out.data_ptr(), sp), "FK20 multi finish (merge)")
+    else:
+        _check(L.b200_fk20_multi_finish_dev(fk.h, d_sum.data_ptr(), 1, d_out.data_ptr(), sp), "FK20 multi finish")
     torch.cuda.synchronize()
     return d_out.cpu().numpy().view(np.uint64)
 

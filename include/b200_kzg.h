@@ -184,6 +184,11 @@ int b200_fk20_multi_partial_dev(b200_fk* fk, const void* d_poly, size_t n, size_
                                 void* d_partial, void* cuda_stream);
 int b200_g1_sum_dev(const void* d_parts, size_t n_parts, size_t count, void* d_out, void* cuda_stream);
 int b200_fk20_multi_finish_dev(b200_fk* fk, const void* d_h_ext_fft, int reverse_bits, void* d_proofs, void* cuda_stream);
+/* The same two G1 transforms spread over world = 2^s ranks that all hold the summed hExtFFT: _local leaves rank r's
+ * block of k2 / world points (internal 144-byte form) after the inverse transform, the zero padding and the block-local
+ * forward stages; the blocks are all-gathered in rank order; _merge runs the last s forward stages and converts. */
+int b200_fk20_multi_finish_local_dev(b200_fk* fk, const void* d_h_ext_fft, size_t rank, size_t world, void* d_block, void* cuda_stream);
+int b200_fk20_multi_finish_merge_dev(b200_fk* fk, const void* d_blocks, size_t world, int reverse_bits, void* d_proofs, void* cuda_stream);
 /* Partial LinCombG1 over points/scalars [begin, end) of the settings' SecretG1 (MSM sharded by
  * point range); partial sums are exchanged and added with b200_g1_sum_dev. */
 int b200_commit_partial_dev(b200_ks* ks, const void* d_coeffs, size_t begin, size_t end, void* d_out, void* cuda_stream);

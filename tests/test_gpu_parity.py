@@ -568,6 +568,17 @@ def test_sharded_fk20_multi_blocks_on_one_gpu():
     assert L.b200_fk20_multi_finish_dev(fk.h, d_sum.data_ptr(), 1, d_out.data_ptr(), None) == 0
     torch.cuda.synchronize()
     cmp_g1(d_out.cpu().numpy().view(np.uint64), want)
+    # block-sharded finish (the two G1 transforms spread over 2^s ranks), ranks played one after another
+    for w2 in (1, 2, 4, 8):
+        blocks = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+        for r in range(w2):
+            blk = blocks[r * (k2 // w2):(r + 1) * (k2 // w2)]
+            assert L.b200_fk20_multi_finish_local_dev(fk.h, d_sum.data_ptr(), r, w2, blk.data_ptr(), None) == 0
+        d_out2 = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+        assert L.b200_fk20_multi_finish_merge_dev(fk.h, blocks.data_ptr(), w2, 1, d_out2.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        cmp_g1(d_out2.cpu().numpy().view(np.uint64), want)
+    assert L.b200_fk20_multi_finish_local_dev(fk.h, d_sum.data_ptr(), 0, 3, blocks.data_ptr(), None) != 0      # not a power of two
     # the single-process entry of the sharded driver, and the point-range sharded commitment
     cmp_g1(multi_gpu.da_using_fk20_multi_sharded(fk, poly), want)
     c_parts = torch.zeros((world, 1, 18), dtype=torch.int64, device="cuda")
