@@ -264,8 +264,8 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": "blobs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 limbs (381-bit Fp / 255-bit Fr Montgomery integers)", "data": "synthetic",
-        "config": {"workload": "CommitToPoly + FK20Single, n=4096 (configs[1]+configs[2]), eth trusted setup secret 1337 "
+        "dtype": "u32", "data": "synthetic",
+        "config": {"arithmetic": "381-bit Fp / 255-bit Fr Montgomery integers on 32-bit limbs (IMAD.WIDE)", "workload": "CommitToPoly + FK20Single, n=4096 (configs[1]+configs[2]), eth trusted setup secret 1337 "
                                "extended to 8192 points", "blobs_per_gpu_per_step": B, "l2": "256 MiB flush write between steps",
                    "parallelism": "blob-parallel replicas x%d" % world, "results_match_host_path": same},
         "e2e": {"value": round(world * B * K / e2e_s, 3), "unit": "blobs/s",
@@ -340,7 +340,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(v, 5), "unit": "blobs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Montgomery integers)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "CommitToPoly + FK20Single, n=4096, one blob per step (bounded sample), all host threads"},
         "cpu_baseline": {"value": round(v, 5), "unit": "blobs/s", "cores": cores, "kind": "port",
                          "sample": "1 blob per step, reference algorithm restated in C (oracle/), %d threads" % cores},

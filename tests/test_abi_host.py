@@ -199,3 +199,20 @@ def test_fp64_pipe_product_matches_integer_product_on_the_host(tmp_path):
                           stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
+
+
+def test_karatsuba_product_matches_integer_product_on_the_host(tmp_path):
+    """field_karatsuba.cuh (Karatsuba product half + m * p-only reduction rows, opt-in) against fe_mul / the
+    portable product: random operands and edge values incl. equal halves (tools/kara_check.cu)."""
+    import shutil
+    import subprocess
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not (os.path.exists(nvcc) or shutil.which("nvcc")):
+        pytest.skip("nvcc not available")
+    for levels in ("1", "2"):
+        exe = str(tmp_path / ("kara_check" + levels))
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-DB200_KARA_LEVELS=" + levels, "-I", os.path.join(ROOT, "go_kzg_b200", "csrc"),
+                               "-I", os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tools", "kara_check.cu")],
+                              stderr=subprocess.DEVNULL)
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
