@@ -259,7 +259,8 @@ static int fs_programs(b200_fs* fs, int inverse, int mode, const ScalarProgram**
     return B200_OK;
 }
 // lanes of a warp share the twiddle when the batch fills whole warps -> sparse (wNAF) recoding
-static inline int program_mode_for_batch(size_t batch) { return batch % 32 == 0 ? 1 : 0; }
+// matches g1_lanes_for_batch (kernels_g1.cu): whole warps per butterfly from 16 blobs on
+static inline int program_mode_for_batch(size_t batch) { return batch >= 16 ? 1 : 0; }
 
 // ------------------------------------------------------------------------------ Fr FFT
 static int dev_fr_fft(b200_fs* fs, const Fr* d_in, Fr* d_out, unsigned logn, size_t batch, bool inverse, cudaStream_t st) {

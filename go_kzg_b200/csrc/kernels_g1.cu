@@ -24,6 +24,10 @@ unsigned long long g_launch_count = 0;
 #ifndef B200_G1_MINB
 #define B200_G1_MINB 4
 #endif
+// Batched transforms map (butterfly, blob) to threads with the blob index fastest.  From 16 blobs on the
+// lane count per butterfly is rounded up to whole warps (the padding lanes idle), so that every warp works on
+// ONE butterfly and the sparse (width-5 NAF) twiddle programs stay convergent for any batch size.
+__host__ __device__ inline size_t g1_lanes_for_batch(size_t batch) { return batch >= 16 ? (batch + 31) / 32 * 32 : batch; }
 constexpr unsigned G1_BLOCK = B200_G1_BLOCK;
 constexpr unsigned G1_MINB = B200_G1_MINB;
 
@@ -155,9 +159,12 @@ template <bool DIF>
 __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
                                                       size_t bstride, const ScalarProgram* __restrict__ progs,
                                                       size_t prog_stride) {
+    // lanes of a butterfly: the batch, padded to whole warps (idle lanes) so that a warp never mixes twiddles
+    const size_t lanes = g1_lanes_for_batch(batch);
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_half * batch) return;
-    size_t b = t % batch, q = t / batch;
+    if (t >= n_half * lanes) return;
+    size_t b = t % lanes, q = t / lanes;
+    if (b >= batch) return;
     size_t j = q & (m - 1);
     size_t i0 = 2 * q - j, i1 = i0 + m;
     G1J* p0 = data + b * bstride + i0 * estride;
@@ -179,8 +186,8 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage(G1J* data, s
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
                          const ScalarProgram* progs, size_t prog_stride, cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_FFT_STAGE, st);
-    size_t total = n_half * batch;
-    if (!total) return;
+    size_t total = n_half * g1_lanes_for_batch(batch);
+    if (!total || !batch) return;
     if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
     else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
     g_launch_count++;
@@ -232,9 +239,11 @@ void launch_g1_mul_var(const G1J* pts, size_t pts_bstride, const Fr* k, int k_is
 __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,
                                                          const ScalarProgram* __restrict__ progs, size_t prog_stride,
                                                          int bitrev, unsigned logn) {
+    const size_t lanes = g1_lanes_for_batch(batch);
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * batch) return;
-    size_t b = t % batch, i = t / batch;
+    if (t >= n * lanes) return;
+    size_t b = t % lanes, i = t / lanes;
+    if (b >= batch) return;
     size_t pi = bitrev ? bitrev_u32((uint32_t)i, logn) : i;
     G1J* p = data + b * bstride + i * estride;
     G1J x = ld_vec(p), r;
@@ -245,7 +254,7 @@ void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, s
                             size_t prog_stride, int bitrev, unsigned logn, cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_MUL, st);
     if (!n || !batch) return;
-    k_g1_mul_programs<<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n, batch, estride, bstride, progs, prog_stride, bitrev, logn);
+    k_g1_mul_programs<<<grid_for(n * g1_lanes_for_batch(batch), G1_BLOCK), G1_BLOCK, 0, st>>>(data, n, batch, estride, bstride, progs, prog_stride, bitrev, logn);
     g_launch_count++;
 }
 

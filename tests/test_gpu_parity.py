@@ -161,6 +161,20 @@ def test_fft_g1_batch_uses_shared_twiddle_programs():
         cmp_g1(out[b], cref.g1_mul_gen(fo.fft(ks[b], True)))
 
 
+@pytest.mark.parametrize("batch", [15, 16, 20, 33])
+def test_fft_g1_batch_sizes_around_the_warp_padding(batch):
+    """from 16 transforms on, the lanes of a butterfly are padded to whole warps and the sparse twiddle programs
+    are used; below, per-lane fixed windows: both sides of the switch and ragged last warps"""
+    rng = random.Random(batch)
+    fs, fo = kzg.FFTSettings(3), pyref.FFTSettings(3)
+    ks = [[rng.randrange(R) for _ in range(8)] for _ in range(batch)]
+    pts = np.stack([cref.g1_mul_gen(k) for k in ks])
+    for inv in (False, True):
+        out = fs.fft_g1_batch(pts, inv)
+        for b in (0, batch // 2, batch - 1):
+            cmp_g1(out[b], cref.g1_mul_gen(fo.fft(ks[b], inv)))
+
+
 # ------------------------------------------------------------------------------ LinCombG1 / commit
 def test_empty_lincomb_is_infinity():
     """bls/bls_test.go:69-77 TestEmptyG1Lincomb"""
