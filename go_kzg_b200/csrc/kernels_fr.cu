@@ -127,20 +127,47 @@ __global__ void __launch_bounds__(1024) k_fr_ntt_pass(NttPass P) {
     __syncthreads();
     if (tw_bytes) mbar_wait(&bar, 0);   // every thread observes the completed phase (acquire)
 
-    const unsigned nbf = (M / 2) * C;
-    for (unsigned m = 1; m < M; m <<= 1) {
-        const unsigned tstride = (M / 2) / m;
-        for (unsigned bf = tid; bf < nbf; bf += T) {
+    // Stages in pairs (radix 4): a thread takes the four elements g, g + m, g + 2m, g + 3m through the stages
+    // m and 2m in registers -- the same four twiddle products as two radix-2 stages, half the shared-memory
+    // traffic and half the barriers.  An odd stage count starts with one radix-2 stage.
+    unsigned m = 1;
+    if (P.logm & 1) {
+        const unsigned nbf = (M / 2) * C;
+        for (unsigned bf = tid; bf < nbf; bf += T) {          // m = 1: j = 0, no twiddle
             unsigned c = bf % C, q = bf / C;
-            unsigned j = q & (m - 1);
-            unsigned i0 = 2 * q - j, i1 = i0 + m;
-            Fr* a0 = s + (size_t)i0 * C + c;
-            Fr* a1 = s + (size_t)i1 * C + c;
-            Fr x1 = ld_vec(a1);
-            if (j) x1 = fe_mul(x1, ld_vec(tws + (size_t)j * tstride));
-            Fr x0 = ld_vec(a0);
+            Fr* a0 = s + (size_t)(2 * q) * C + c;
+            Fr* a1 = a0 + C;
+            Fr x0 = ld_vec(a0), x1 = ld_vec(a1);
             st_vec(a0, fe_add(x0, x1));
             st_vec(a1, fe_sub(x0, x1));
+        }
+        __syncthreads();
+        m = 2;
+    }
+    const unsigned nunits = (M / 4) * C;
+    for (; m < M; m <<= 2) {
+        const unsigned ts1 = (M / 2) / m, ts2 = ts1 / 2;
+        for (unsigned u = tid; u < nunits; u += T) {
+            unsigned c = u % C, q = u / C;
+            unsigned j = q & (m - 1);
+            unsigned g = ((q - j) << 2) + j;
+            Fr* a0 = s + (size_t)g * C + c;
+            Fr* a1 = a0 + (size_t)m * C;
+            Fr* a2 = a1 + (size_t)m * C;
+            Fr* a3 = a2 + (size_t)m * C;
+            Fr x0 = ld_vec(a0), x1 = ld_vec(a1), x2 = ld_vec(a2), x3 = ld_vec(a3);
+            if (j) {
+                Fr w = ld_vec(tws + (size_t)j * ts1);
+                x1 = fe_mul(x1, w);
+                x3 = fe_mul(x3, w);
+            }
+            Fr y0 = fe_add(x0, x1), y1 = fe_sub(x0, x1), y2 = fe_add(x2, x3), y3 = fe_sub(x2, x3);
+            if (j) y2 = fe_mul(y2, ld_vec(tws + (size_t)j * ts2));
+            y3 = fe_mul(y3, ld_vec(tws + (size_t)(j + m) * ts2));
+            st_vec(a0, fe_add(y0, y2));
+            st_vec(a2, fe_sub(y0, y2));
+            st_vec(a1, fe_add(y1, y3));
+            st_vec(a3, fe_sub(y1, y3));
         }
         __syncthreads();
     }
@@ -159,8 +186,8 @@ __global__ void __launch_bounds__(1024) k_fr_ntt_pass(NttPass P) {
 static void run_pass(NttPass& P, size_t ngroups, size_t batch, cudaStream_t st) {
     const size_t M = (size_t)1 << P.logm;
     size_t smem = M * P.cols * sizeof(Fr) + (M / 2) * sizeof(Fr);
-    size_t work = M * P.cols / 2;
-    unsigned threads = work >= 1024 ? 1024 : (work < 32 ? 32 : (unsigned)work);
+    size_t work = M * P.cols / 4;       // radix-4 units per stage pair
+    unsigned threads = work >= 1024 ? 1024 : (work < 32 ? 32 : (unsigned)work);   // 64 registers: measured faster than 512 x 92
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_fr_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
