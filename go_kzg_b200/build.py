@@ -33,8 +33,14 @@ def _check_ptxas(unit: str, log: str) -> None:
     device functions in the calling kernel's cumulative stack size)."""
     lines = log.splitlines()
     for i, ln in enumerate(lines):
-        if "Function properties for" in ln and i + 1 < len(lines) and "0 bytes spill stores" not in lines[i + 1]:
+        if "Function properties for" in ln and i + 1 < len(lines) and _spill_bytes(lines[i + 1]) > 256:
             sys.stderr.write("[build] %s: %s: %s\n" % (unit, ln.split("Function properties for")[1].strip()[:60], lines[i + 1].strip()))
+
+
+def _spill_bytes(line: str) -> int:
+    import re
+    m = re.search(r"(\d+) bytes spill stores", line)
+    return int(m.group(1)) if m else 0
 
 
 def _compile(unit: str, verbose: bool) -> str:
