@@ -86,6 +86,19 @@ static void keep_pool_memory() {
     done[dev] = true;
 }
 
+// one point at infinity per device (source of strided clears); never freed
+static int dev_infinity(G1J** out) {
+    static std::mutex mu;
+    static G1J* inf[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return B200_ERR_BAD_INPUT;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!inf[dev]) { CK(cudaMalloc(&inf[dev], sizeof(G1J))); CK(cudaMemset(inf[dev], 0, sizeof(G1J))); }
+    *out = inf[dev];
+    return B200_OK;
+}
+
 // RAII stream-ordered device buffer
 struct DevBuf {
     void* p = nullptr;
@@ -780,14 +793,9 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
     if (logk2 > 12) CKS(tmp.alloc(batch * l * k2 * sizeof(Fr), st));
     Fr scale = fr_inv_of_u64(k2);
     launch_fr_ntt(fs->dom, c.as<Fr>(), c.as<Fr>(), tmp.as<Fr>(), logk2, batch * l, false, &scale, st);
-    DevBuf eo;
     if (mode == 0) {
         // even entries carry 1/2 instead of 1/2k (see below): times k
-        Fr tab2[2] = {fr_from_u64(k), Fr::one()};
-        CKS(eo.alloc(sizeof tab2, st));
-        CK(cudaMemcpyAsync(eo.p, tab2, sizeof tab2, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));   // tab2 lives on this stack frame
-        launch_fr_mul_table(c.as<Fr>(), eo.as<Fr>(), 2, batch * l * k, st);
+        launch_fr_mul_even_odd(c.as<Fr>(), fr_from_u64(k), Fr::one(), batch * l * k2, st);
     }
     if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
     else launch_g1_mul_var(fk->d_x_ext_fft, 0, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
@@ -816,8 +824,8 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
     } else {
         CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, true, true, st));
         // clear the odd slots (the discarded upper half of the inverse transform): h ++ 0^k
-        static G1J* d_inf = nullptr;   // one infinity element per process (never freed)
-        if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }
+        G1J* d_inf = nullptr;
+        CKS(dev_infinity(&d_inf));
         launch_g1_copy(h.as<G1J>() + 1, 2, bstride, d_inf, 0, 0, k, batch, 0, 0, st);
         CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, batch, 1, bstride, false, false, st));
         if (d_comp) launch_g1_compress(h.as<G1J>(), d_comp, k2, batch, 1, bstride, mode == 2 ? 1 : 0, logk2, st);
@@ -937,8 +945,8 @@ extern "C" int b200_fk20_multi_finish_dev(b200_fk* fk, const void* d_h_ext_fft, 
     CKS(h.alloc(k2 * sizeof(G1J), st));
     launch_g1_from_abi((const uint64_t*)d_h_ext_fft, h.as<G1J>(), k2, st);
     CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, 1, 1, k2, true, true, st));     // fk20_multi.go:93 (1/2k already folded in)
-    static G1J* d_inf = nullptr;
-    if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }
+    G1J* d_inf = nullptr;
+    CKS(dev_infinity(&d_inf));
     launch_g1_copy(h.as<G1J>() + 1, 2, k2, d_inf, 0, 0, k, 1, 0, 0, st);          // fk20_multi.go:100-103
     CKS(dev_g1_fft_stages(fs, h.as<G1J>(), logk2, 1, 1, k2, false, false, st));   // fk20_multi.go:104
     launch_g1_to_abi(h.as<G1J>(), (uint64_t*)d_proofs, k2, 1, 1, k2, reverse_bits ? 1 : 0, logk2, st);
@@ -983,8 +991,8 @@ extern "C" int b200_fk20_multi_finish_local_dev(b200_fk* fk, const void* d_h_ext
     G1J* block = (G1J*)d_block;
     if (s == 0) CK(cudaMemcpyAsync(block, cur, k2 * sizeof(G1J), cudaMemcpyDeviceToDevice, st));
     for (size_t mm = blk / 2; mm >= 1; mm >>= 1) launch_g1_fft_stage(block, blk / 2, 1, mm, 1, blk, true, inv_progs, halfw / mm, st);
-    static G1J* d_inf = nullptr;
-    if (!d_inf) { CK(cudaMalloc(&d_inf, sizeof(G1J))); CK(cudaMemset(d_inf, 0, sizeof(G1J))); }
+    G1J* d_inf = nullptr;
+    CKS(dev_infinity(&d_inf));
     launch_g1_copy(block + 1, 2, blk, d_inf, 0, 0, blk / 2, 1, 0, 0, st);
     for (size_t mm = 1; mm <= blk / 2; mm <<= 1) launch_g1_fft_stage(block, blk / 2, 1, mm, 1, blk, false, fwd_progs, halfw / mm, st);
     (void)logblk;

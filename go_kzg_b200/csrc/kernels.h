@@ -2,6 +2,7 @@
 // translation units (kernels_fr.cu, kernels_g1.cu).  Internal; the public boundary is
 // include/b200_kzg.h.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -10,7 +11,7 @@
 namespace b200 {
 
 // every launcher bumps this (gpu_launches in bench.py)
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this process (any thread)
 
 // Optional per-kernel-class device timing (bench.py's roofline): when enabled, every launcher
 // brackets its launches with CUDA events on the launching stream.
@@ -81,6 +82,7 @@ void launch_eval_form_quotient(const FrDomain& dom, const uint64_t* f_canon, con
                                uint32_t* ok, cudaStream_t st);
 // pointwise helpers on Montgomery arrays
 void launch_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n, cudaStream_t st);   // dst = a * b
+void launch_fr_mul_even_odd(Fr* v, const Fr& even, const Fr& odd, size_t total, cudaStream_t st);   // v[i] *= i even ? even : odd
 
 // ---------------------------------------------------------------- G1
 void launch_g1_from_abi(const uint64_t* in, G1J* out, size_t n, cudaStream_t st);

@@ -14,6 +14,18 @@
 
 namespace b200 {
 
+// Function attributes belong to a device's context: remember per (kernel, device) whether the large dynamic
+// shared-memory opt-in has been made (a process may drive several GPUs through b200_set_device).
+static bool smem_attr_done(int which) {
+    static bool done[2][64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    bool was = done[which][dev];
+    done[which][dev] = true;
+    return was;
+}
+
+
 static inline unsigned grid_for(size_t total, unsigned block) { return (unsigned)((total + block - 1) / block); }
 __device__ __forceinline__ uint32_t brev_bits(uint32_t v, unsigned logn) { return logn ? (__brev(v) >> (32 - logn)) : 0u; }
 
@@ -188,11 +200,7 @@ static void run_pass(NttPass& P, size_t ngroups, size_t batch, cudaStream_t st) 
     size_t smem = M * P.cols * sizeof(Fr) + (M / 2) * sizeof(Fr);
     size_t work = M * P.cols / 4;       // radix-4 units per stage pair
     unsigned threads = work >= 1024 ? 1024 : (work < 32 ? 32 : (unsigned)work);   // 64 registers: measured faster than 512 x 92
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_fr_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
+    if (!smem_attr_done(0)) cudaFuncSetAttribute(k_fr_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid((unsigned)ngroups, (unsigned)batch);
     k_fr_ntt_pass<<<grid, threads, smem, st>>>(P);
     g_launch_count++;
@@ -323,8 +331,7 @@ void launch_das_fft_extension(const FrDomain& dom, Fr* vals, unsigned logn, size
     if (logn == 0) return;   // the reference panics ("bad usage") before this point; caller checks
     const unsigned logb = logn < DAS_LOG_BLOCK ? logn : DAS_LOG_BLOCK;
     const size_t B = (size_t)1 << logb;
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(k_das_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
+    if (!smem_attr_done(1)) cudaFuncSetAttribute(k_das_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 lgrid((unsigned)((n / 2 + 255) / 256), (unsigned)batch);
     for (size_t L = n; L > B; L >>= 1) { k_das_level<false><<<lgrid, 256, 0, st>>>(vals, n, L, dom.reverse, 0, inv_n); g_launch_count++; }
     unsigned threads = B / 2 >= 1024 ? 1024 : (B / 2 < 32 ? 32 : (unsigned)(B / 2));
@@ -510,6 +517,17 @@ __global__ void k_fr_mul_table(Fr* v, const Fr* __restrict__ table, size_t n, si
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     st_vec(v + i, fe_mul(ld_vec(v + i), ld_vec(table + (i % n))));
+}
+// v[i] *= (i even ? even : odd): constants by value, nothing to stage on the device
+__global__ void k_fr_mul_even_odd(Fr* v, Fr even, Fr odd, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    st_vec(v + i, fe_mul(ld_vec(v + i), (i & 1) ? odd : even));
+}
+void launch_fr_mul_even_odd(Fr* v, const Fr& even, const Fr& odd, size_t total, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!total) return;
+    k_fr_mul_even_odd<<<grid_for(total, 256), 256, 0, st>>>(v, even, odd, total); g_launch_count++;
 }
 void launch_fr_mul_table(Fr* v, const Fr* table, size_t n, size_t batch, cudaStream_t st) {
     ProfScope prof_scope(PROF_MISC, st);

@@ -12,7 +12,7 @@
 
 namespace b200 {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // Launch shape of the integer-pipe bound G1 kernels.  128 registers per thread hold the working
 // set of the out-of-line point operations without spills (ptxas -v), which lets 4 CTAs of 128
