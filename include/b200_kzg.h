@@ -151,7 +151,8 @@ int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_
 /* ------------------------------------------------------------------ compressed outputs, eth blobs --
  * The callers of the path consume 48-byte compressed points (bls/bls_kilic.go:114-116 ToCompressedG1;
  * eth/helpers.go:98-103, :199-202).  These entry points normalise and compress on the device (one
- * inversion per 16 points), so a third of the bytes travels back to the host. */
+ * inversion per 16 points), so a third of the bytes travels back to the host.  Device output pointers of the
+ * _dev forms must be 16-byte aligned (48-byte strings are written as three 128-bit stores). */
 int b200_commit_fk20_batch_compressed(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint8_t* commitments48,
                                       uint8_t* proofs48);
 int b200_commit_fk20_batch_compressed_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments48,
