@@ -556,7 +556,7 @@ extern "C" int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inve
 // d_k canonical ([batch][n]); result of blob b is left at work[b * n].
 static int dev_lincomb(const G1J* d_pts, size_t pts_bstride, const Fr* d_k, int k_is_mont, G1J* work, size_t n,
                        size_t batch, cudaStream_t st, const G1A* fb_table = nullptr) {
-    if (fb_table) launch_g1_mul_fixed_base(fb_table, d_k, k_is_mont, work, n, n, batch, st);
+    if (fb_table) launch_g1_mul_fixed_base(fb_table, 8, d_k, k_is_mont, work, n, n, batch, st);
     else launch_g1_mul_var(d_pts, pts_bstride, d_k, k_is_mont, work, n, n, batch, st);
     for (size_t cnt = n; cnt > 1;) {
         size_t half = (cnt + 1) / 2;
@@ -615,19 +615,33 @@ struct b200_ks {
 };
 
 // fixed-base tables are used while they stay below this many bytes per settings object
-static const size_t kFixedBaseBudget = (size_t)8 << 30;
+static const size_t kFixedBaseBudget8 = (size_t)8 << 30;      // 8-bit windows (384 KiB per base) up to here
+static const size_t kFixedBaseBudget4 = (size_t)128 << 30;    // else 4-bit windows (48 KiB per base) up to here / 70 % of the free HBM
 
-static int build_fixed_base(const G1J* d_pts, size_t n, G1A** out_table, cudaStream_t st) {
-    *out_table = nullptr;
-    if (n == 0 || fixed_base_table_bytes(n) > kFixedBaseBudget) return B200_OK;
+// Window table over d_pts[0..n): *out_w = 8 or 4 (window bits), *out_table = nullptr when nothing fits (the callers
+// then use the generic windowed multiplication).  Running out of memory is not an error either.
+static int build_fixed_base(const G1J* d_pts, size_t n, G1A** out_table, int* out_w, cudaStream_t st) {
+    *out_table = nullptr; *out_w = 8;
+    if (n == 0) return B200_OK;
+    int W = 0;
+    if (fixed_base_table_bytes(n, 8) <= kFixedBaseBudget8) W = 8;
+    else {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return B200_OK; }
+        size_t need = fixed_base_table_bytes(n, 4) + fixed_base_tmp_bytes(n, 4);
+        if (fixed_base_table_bytes(n, 4) <= kFixedBaseBudget4 && need <= free_b / 10 * 7) W = 4;
+    }
+    if (!W) return B200_OK;
     G1A* table = nullptr;
-    CK(cudaMalloc(&table, fixed_base_table_bytes(n)));
-    DevBuf tmp;
-    int rc = tmp.alloc(fixed_base_tmp_bytes(n), st);
-    if (!rc) { launch_fixed_base_table(d_pts, n, tmp.as<G1J>(), table, st); rc = check_launches(); }
+    if (cudaMalloc(&table, fixed_base_table_bytes(n, W)) != cudaSuccess) { cudaGetLastError(); return B200_OK; }
+    G1J* tmp = nullptr;
+    if (cudaMalloc(&tmp, fixed_base_tmp_bytes(n, W)) != cudaSuccess) { cudaGetLastError(); cudaFree(table); return B200_OK; }
+    launch_fixed_base_table(d_pts, n, tmp, table, W, st);
+    int rc = check_launches();
     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "fixed-base table build"; rc = B200_ERR_CUDA; }
+    cudaFree(tmp);
     if (rc) { cudaFree(table); return rc; }
-    *out_table = table;
+    *out_table = table; *out_w = W;
     return B200_OK;
 }
 // table covering SecretG1[:n] (or null when over budget)
@@ -636,7 +650,9 @@ static int ks_fixed_base(b200_ks* ks, size_t n, const G1A** table, cudaStream_t 
     if (ks->fb_n < n) {
         if (ks->d_fb_table) { cudaFree(ks->d_fb_table); ks->d_fb_table = nullptr; ks->fb_n = 0; }
         G1A* t = nullptr;
-        CKS(build_fixed_base(ks->d_secret_g1, n, &t, st));
+        int w = 8;
+        CKS(build_fixed_base(ks->d_secret_g1, n, &t, &w, st));
+        if (t && w != 8) { cudaFree(t); t = nullptr; }      // commitments use 8-bit windows or the generic path
         ks->d_fb_table = t;
         ks->fb_n = t ? n : 0;
         if (!t) { *table = nullptr; return B200_OK; }
@@ -705,6 +721,7 @@ struct b200_fk {
     size_t n2 = 0, chunk_len = 1;
     G1J* d_x_ext_fft = nullptr;   // [chunk_len][n2 / chunk_len], natural order (kzg.go:62,110-114)
     G1A* d_fb_table = nullptr;    // fixed-base window table over d_x_ext_fft (null when over budget)
+    int fb_w = 8;                 // its window bits (8, or 4 for very large settings)
     unsigned long long last_launches = 0;
 };
 
@@ -737,7 +754,7 @@ static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk**
         launch_g1_copy(fk->d_x_ext_fft, 1, k2, work.as<G1J>(), 1, k2, k2, l, 1, logk2, st);
         if ((rc = check_launches())) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "sync in fk20 settings"; rc = B200_ERR_CUDA; break; }
-        if ((rc = build_fixed_base(fk->d_x_ext_fft, l * k2, &fk->d_fb_table, st))) break;
+        if ((rc = build_fixed_base(fk->d_x_ext_fft, l * k2, &fk->d_fb_table, &fk->fb_w, st))) break;
     } while (0);
     if (rc) { b200_fk20_settings_free(fk); return rc; }
     *out = fk;
@@ -797,7 +814,7 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
         // even entries carry 1/2 instead of 1/2k (see below): times k
         launch_fr_mul_even_odd(c.as<Fr>(), fr_from_u64(k), Fr::one(), batch * l * k2, st);
     }
-    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
+    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table, fk->fb_w, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
     else launch_g1_mul_var(fk->d_x_ext_fft, 0, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
     for (size_t cnt = l; cnt > 1; cnt /= 2) launch_g1_fold(h.as<G1J>(), l * k2, (cnt / 2) * k2, cnt * k2, batch, st);
     CKS(check_launches());
@@ -907,7 +924,7 @@ extern "C" int b200_fk20_multi_partial_dev(b200_fk* fk, const void* d_poly, size
     Fr scale = fr_inv_of_u64(k2);     // the inverse transform's 1/2k, as in dev_fk20
     Fr* c_mine = c.as<Fr>() + off_begin * k2;
     launch_fr_ntt(fs->dom, c_mine, c_mine, tmp.as<Fr>(), logk2, m, false, &scale, st);
-    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table + off_begin * k2 * (size_t)(32 * 128), c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
+    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table + off_begin * k2 * fixed_base_row_entries(fk->fb_w), fk->fb_w, c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
     else launch_g1_mul_var(fk->d_x_ext_fft + off_begin * k2, 0, c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
     // sum the m files: fold the tail onto the head until one file is left (m need not be a power of two)
     for (size_t cnt = m; cnt > 1;) {

@@ -104,11 +104,12 @@ void launch_g1_dif_half_stage(const G1J* in, G1J* out, size_t m, int lower, cons
 // out[b * out_bstride + i] = k[b * n + i] * pts[b * pts_bstride + i]   (pts_bstride = 0: shared bases)
 void launch_g1_mul_var(const G1J* pts, size_t pts_bstride, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride,
                        size_t n, size_t batch, cudaStream_t st);
-// fixed-base window tables (signed 8-bit windows, affine entries): build and use
-size_t fixed_base_table_bytes(size_t n);
-size_t fixed_base_tmp_bytes(size_t n);
-void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* table, cudaStream_t st);
-void launch_g1_mul_fixed_base(const G1A* table, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
+// fixed-base window tables (signed W-bit windows, W = 8 or 4, affine entries): build and use
+size_t fixed_base_row_entries(int W);                 // table entries per base
+size_t fixed_base_table_bytes(size_t n, int W);
+size_t fixed_base_tmp_bytes(size_t n, int W);
+void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* table, int W, cudaStream_t st);
+void launch_g1_mul_fixed_base(const G1A* table, int W, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
                               cudaStream_t st);
 // out[b * bstride + i * estride] = progs[idx(i) * prog_stride] * same element (in place)
 void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,

@@ -261,81 +261,108 @@ void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, s
 // ------------------------------------------------------------------------------ fixed-base tables
 // The bases of ToeplitzPart2 (xExtFFT, fk20_single.go:72-74) and of CommitToPoly (SecretG1,
 // kzg_single_proofs.go:17-19) are fixed per settings object, so their scalar multiplications
-// become table look-ups: signed 8-bit windows, table[i][w][d-1] = d * 2^(8w) * P_i in affine
-// form (32 windows x 128 entries x 96 B = 384 KiB per base; 3 GiB for the 8192 bases of the
-// n = 4096 FK20 settings -- HBM is what a B200 has plenty of).  One product = 32 mixed additions
-// (~350 Fp multiplications) instead of ~2000.
-#define FB_WINDOWS 32
-#define FB_ENTRIES 128
-// bases[i][w] = 2^(8w) P_i (Jacobian)
-__global__ void __launch_bounds__(128) k_fb_bases(const G1J* __restrict__ pts, G1J* __restrict__ bases, size_t n) {
+// become table look-ups: signed W-bit windows, table[i][w][d-1] = d * 2^(W w) * P_i in affine
+// form.  W = 8: 32 windows x 128 entries x 96 B = 384 KiB per base (3 GiB for the 8192 bases of
+// the n = 4096 FK20 settings -- HBM is what a B200 has plenty of), one product = 32 mixed
+// additions (~350 Fp multiplications) instead of ~1900.  W = 4: 64 windows x 8 entries = 48 KiB
+// per base and 64 mixed additions, for settings whose W = 8 table would not fit (config 5: 2.1 M
+// bases).
+static inline unsigned fb_windows(int W) { return (unsigned)((256 + W - 1) / W); }
+static inline unsigned fb_entries(int W) { return 1u << (W - 1); }
+#define FB_CHUNK 16
+// bases[i][w] = 2^(W w) P_i (Jacobian)
+__global__ void __launch_bounds__(128) k_fb_bases(const G1J* __restrict__ pts, G1J* __restrict__ bases, size_t n, int W, unsigned nw) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     G1J p = ld_vec(pts + i);
-    for (int w = 0; w < FB_WINDOWS; w++) {
-        st_vec(bases + i * FB_WINDOWS + w, p);
-        if (w + 1 < FB_WINDOWS) for (int k = 0; k < 8; k++) g1_dbl_ni(&p, &p);
+    for (unsigned w = 0; w < nw; w++) {
+        st_vec(bases + i * nw + w, p);
+        if (w + 1 < nw) for (int k = 0; k < W; k++) g1_dbl_ni(&p, &p);
     }
 }
-// table[(i w) * 128 + d - 1] = affine(d * bases[i][w]), one entry per thread
-__global__ void __launch_bounds__(128) k_fb_entries(const G1J* __restrict__ bases, G1A* __restrict__ table, size_t n_rows) {
+// One thread fills FB_CHUNK consecutive entries of one (base, window) row: start = (c CH + 1) B by double-and-add,
+// then a chain of additions of B, then ONE inversion for the whole chunk (Montgomery's trick on the Z coordinates).
+// ~70 Fp products per entry instead of ~700 when every entry is built and inverted on its own.
+__global__ void __launch_bounds__(128) k_fb_entries(const G1J* __restrict__ bases, G1A* __restrict__ table, size_t n_rows, unsigned D) {
+    const unsigned CH = D < FB_CHUNK ? D : FB_CHUNK, chunks = D / CH;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_rows * FB_ENTRIES) return;
-    const unsigned d = (unsigned)(t % FB_ENTRIES) + 1;
-    G1J b = ld_vec(bases + t / FB_ENTRIES), acc = G1J::infinity();
+    if (t >= n_rows * chunks) return;
+    const size_t row = t / chunks;
+    const unsigned first = (unsigned)(t % chunks) * CH + 1;          // multiple of the first entry of this chunk
+    G1J b = ld_vec(bases + row), acc = G1J::infinity();
     for (int bit = 7; bit >= 0; bit--) {
         if (!acc.is_inf()) g1_dbl_ni(&acc, &acc);
-        if ((d >> bit) & 1u) g1_add_ni(&acc, &acc, &b);
+        if ((first >> bit) & 1u) g1_add_ni(&acc, &acc, &b);
     }
-    G1A a;
-    if (acc.is_inf()) { a.x = Fp::zero(); a.y = Fp::zero(); }
-    else {
-        Fp zi = fe_inv(acc.z), zi2 = fp_sqr(zi);
-        a.x = fp_mul(acc.x, zi2);
-        a.y = fp_mul(acc.y, fp_mul(zi2, zi));
+    G1J pts[FB_CHUNK];
+    Fp pre[FB_CHUNK];
+    Fp prod = Fp::one();
+    for (unsigned e = 0; e < CH; e++) {
+        pts[e] = acc;
+        pre[e] = prod;
+        if (!acc.is_inf()) prod = fp_mul(prod, acc.z);
+        if (e + 1 < CH) g1_add_ni(&acc, &acc, &b);
     }
-    st_vec(table + t, a);
+    Fp inv = fp_inv_fermat(&prod);
+    G1A* out = table + row * D + (first - 1);
+    for (int e = (int)CH - 1; e >= 0; e--) {
+        G1A a;
+        if (pts[e].is_inf()) { a.x = Fp::zero(); a.y = Fp::zero(); }
+        else {
+            Fp zi = fp_mul(inv, pre[e]);
+            inv = fp_mul(inv, pts[e].z);
+            Fp zi2 = fp_sqr(zi);
+            a.x = fp_mul(pts[e].x, zi2);
+            a.y = fp_mul(pts[e].y, fp_mul(zi2, zi));
+        }
+        st_vec(out + e, a);
+    }
 }
-void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* table, cudaStream_t st) {
+void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* table, int W, cudaStream_t st) {
     ProfScope prof_scope(PROF_MISC, st);
     if (!n) return;
-    k_fb_bases<<<grid_for(n, 128), 128, 0, st>>>(pts, bases_tmp, n);
-    k_fb_entries<<<grid_for(n * FB_WINDOWS * FB_ENTRIES, 128), 128, 0, st>>>(bases_tmp, table, n * FB_WINDOWS);
+    const unsigned nw = fb_windows(W), D = fb_entries(W), CH = D < FB_CHUNK ? D : FB_CHUNK;
+    k_fb_bases<<<grid_for(n, 128), 128, 0, st>>>(pts, bases_tmp, n, W, nw);
+    k_fb_entries<<<grid_for(n * nw * (D / CH), 128), 128, 0, st>>>(bases_tmp, table, n * nw, D);
     g_launch_count += 2;
 }
 // out[b * out_bstride + i] = k[b * n + i] * P_i through the table (thread <-> (i, blob), blob fastest:
-// a warp walks the same 12 KiB table row)
+// a warp walks the same table row)
+template <int W>
 __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
-                                                           G1J* out, size_t out_bstride, size_t n, size_t batch) {
+                                                                         G1J* out, size_t out_bstride, size_t n, size_t batch) {
+    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1), PER_LIMB = 32 / W, MASK = (1u << W) - 1u;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
     size_t b = t % batch, i = t / batch;
     Fr s = ld_vec(k + b * n + i);
     if (k_is_mont) s = fe_from_mont(s);
-    const G1A* row = table + i * (size_t)(FB_WINDOWS * FB_ENTRIES);
+    const G1A* row = table + i * (size_t)(NW * D);
     G1J acc = G1J::infinity();
     unsigned carry = 0;
-    for (int w = 0; w < FB_WINDOWS; w++) {
-        unsigned d = ((s.l[w >> 2] >> ((w & 3) * 8)) & 255u) + carry;
-        bool neg = d > 128;
-        if (neg) { d = 256 - d; carry = 1; } else carry = 0;
+    for (unsigned w = 0; w < NW; w++) {
+        unsigned d = ((s.l[w / PER_LIMB] >> ((w % PER_LIMB) * W)) & MASK) + carry;
+        bool neg = d > D;
+        if (neg) { d = (1u << W) - d; carry = 1; } else carry = 0;
         if (d) {
-            G1A p = ld_vec(row + w * FB_ENTRIES + (d - 1));
+            G1A p = ld_vec(row + w * D + (d - 1));
             if (neg) p.y = fe_neg(p.y);
             g1_add_mixed_ni(&acc, &acc, &p);
         }
     }
     st_vec(out + b * out_bstride + i, acc);
 }
-void launch_g1_mul_fixed_base(const G1A* table, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
+void launch_g1_mul_fixed_base(const G1A* table, int W, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
                               cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_MUL, st);
     if (!n || !batch) return;
-    k_g1_mul_fixed_base<<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+    if (W == 8) k_g1_mul_fixed_base<8><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+    else k_g1_mul_fixed_base<4><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     g_launch_count++;
 }
-size_t fixed_base_table_bytes(size_t n) { return n * (size_t)FB_WINDOWS * FB_ENTRIES * sizeof(G1A); }
-size_t fixed_base_tmp_bytes(size_t n) { return n * (size_t)FB_WINDOWS * sizeof(G1J); }
+size_t fixed_base_row_entries(int W) { return (size_t)fb_windows(W) * fb_entries(W); }
+size_t fixed_base_table_bytes(size_t n, int W) { return n * fixed_base_row_entries(W) * sizeof(G1A); }
+size_t fixed_base_tmp_bytes(size_t n, int W) { return n * (size_t)fb_windows(W) * sizeof(G1J); }
 
 // ------------------------------------------------------------------------------ folds / adds
 __global__ void __launch_bounds__(128) k_g1_fold(G1J* data, size_t bstride, size_t half, size_t cnt, size_t batch) {
