@@ -123,7 +123,7 @@ def fp_ops_model_per_blob():
     # effective-affine table (1 doubling, 7 mixed additions, 4 + 34 rescaling products of which 7 are
     # squares), 8 beta products, 1 product to leave the isomorphic curve
     wnaf5 = cost(n_dbl=129, n_mixed=2 * 128 / 6 + 7, m=3 + 27 + 8 + 1, s=1 + 7)
-    fixed_base = cost(n_mixed=32)                                           # 32 signed 8-bit windows
+    fixed_base = cost(n_mixed=22)                                           # 22 signed 12-bit windows
     butterfly = (14, 4)                                                     # shared-subexpression add/sub pair
     n = N_COEFFS
     stages = (n // 2) * (n.bit_length() - 1)

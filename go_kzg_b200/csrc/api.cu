@@ -555,8 +555,8 @@ extern "C" int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inve
 // sum_i k[b][i] * pts[i] for each blob b: per-term scalar multiplication, then a fold tree.
 // d_k canonical ([batch][n]); result of blob b is left at work[b * n].
 static int dev_lincomb(const G1J* d_pts, size_t pts_bstride, const Fr* d_k, int k_is_mont, G1J* work, size_t n,
-                       size_t batch, cudaStream_t st, const G1A* fb_table = nullptr) {
-    if (fb_table) launch_g1_mul_fixed_base(fb_table, 8, d_k, k_is_mont, work, n, n, batch, st);
+                       size_t batch, cudaStream_t st, const G1A* fb_table = nullptr, int fb_w = 8) {
+    if (fb_table) launch_g1_mul_fixed_base(fb_table, fb_w, d_k, k_is_mont, work, n, n, batch, st);
     else launch_g1_mul_var(d_pts, pts_bstride, d_k, k_is_mont, work, n, n, batch, st);
     for (size_t cnt = n; cnt > 1;) {
         size_t half = (cnt + 1) / 2;
@@ -611,10 +611,12 @@ struct b200_ks {
     G1J* d_secret_g1 = nullptr;   // Montgomery Jacobian
     std::mutex mu;
     G1A* d_fb_table = nullptr;    // fixed-base window table of SecretG1[:fb_n] (built on first commit)
+    int fb_w = 8;                 // its window bits
     size_t fb_n = 0;
 };
 
 // fixed-base tables are used while they stay below this many bytes per settings object
+static const size_t kFixedBaseBudget12 = (size_t)40 << 30;    // 12-bit windows (4.1 MiB per base) up to here / 40 % of the free HBM
 static const size_t kFixedBaseBudget8 = (size_t)8 << 30;      // 8-bit windows (384 KiB per base) up to here
 static const size_t kFixedBaseBudget4 = (size_t)128 << 30;    // else 4-bit windows (48 KiB per base) up to here / 70 % of the free HBM
 
@@ -623,19 +625,26 @@ static const size_t kFixedBaseBudget4 = (size_t)128 << 30;    // else 4-bit wind
 static int build_fixed_base(const G1J* d_pts, size_t n, G1A** out_table, int* out_w, cudaStream_t st) {
     *out_table = nullptr; *out_w = 8;
     if (n == 0) return B200_OK;
-    int W = 0;
-    if (fixed_base_table_bytes(n, 8) <= kFixedBaseBudget8) W = 8;
-    else {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return B200_OK; }
-        size_t need = fixed_base_table_bytes(n, 4) + fixed_base_tmp_bytes(n, 4);
-        if (fixed_base_table_bytes(n, 4) <= kFixedBaseBudget4 && need <= free_b / 10 * 7) W = 4;
-    }
-    if (!W) return B200_OK;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return B200_OK; }
+    // widest windows first: 12 bits while the table is a modest share of the free HBM, 8 bits up to 8 GiB, 4 bits as
+    // long as it fits at all; an allocation failure moves on to the next narrower choice
     G1A* table = nullptr;
-    if (cudaMalloc(&table, fixed_base_table_bytes(n, W)) != cudaSuccess) { cudaGetLastError(); return B200_OK; }
     G1J* tmp = nullptr;
-    if (cudaMalloc(&tmp, fixed_base_tmp_bytes(n, W)) != cudaSuccess) { cudaGetLastError(); cudaFree(table); return B200_OK; }
+    int W = 0;
+    const int choices[3] = {12, 8, 4};
+    for (int c = 0; c < 3 && !table; c++) {
+        const int w = choices[c];
+        const size_t tb = fixed_base_table_bytes(n, w), need = tb + fixed_base_tmp_bytes(n, w);
+        bool fits = w == 12 ? (tb <= kFixedBaseBudget12 && need <= free_b / 10 * 4)
+                  : w == 8  ? (tb <= kFixedBaseBudget8 && need <= free_b / 10 * 7)
+                            : (tb <= kFixedBaseBudget4 && need <= free_b / 10 * 7);
+        if (!fits) continue;
+        if (cudaMalloc(&table, tb) != cudaSuccess) { cudaGetLastError(); table = nullptr; continue; }
+        if (cudaMalloc(&tmp, fixed_base_tmp_bytes(n, w)) != cudaSuccess) { cudaGetLastError(); cudaFree(table); table = nullptr; tmp = nullptr; continue; }
+        W = w;
+    }
+    if (!table) return B200_OK;
     launch_fixed_base_table(d_pts, n, tmp, table, W, st);
     int rc = check_launches();
     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "fixed-base table build"; rc = B200_ERR_CUDA; }
@@ -652,7 +661,7 @@ static int ks_fixed_base(b200_ks* ks, size_t n, const G1A** table, cudaStream_t 
         G1A* t = nullptr;
         int w = 8;
         CKS(build_fixed_base(ks->d_secret_g1, n, &t, &w, st));
-        if (t && w != 8) { cudaFree(t); t = nullptr; }      // commitments use 8-bit windows or the generic path
+        ks->fb_w = w;
         ks->d_fb_table = t;
         ks->fb_n = t ? n : 0;
         if (!t) { *table = nullptr; return B200_OK; }
@@ -703,7 +712,7 @@ extern "C" int b200_commit_to_poly_batch(b200_ks* ks, const uint64_t* coeffs, si
     CK(cudaMemcpyAsync(k.p, coeffs, batch * n * 32, cudaMemcpyHostToDevice, st));
     const G1A* fb = nullptr;
     if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));     // worth a table only for real workloads
-    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, ks->fb_w));
     launch_g1_to_abi(work.as<G1J>(), res.as<uint64_t>(), 1, batch, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(out, res.p, batch * 144, cudaMemcpyDeviceToHost, st));
@@ -1087,7 +1096,7 @@ extern "C" int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size
         CKS(work.alloc(batch * n * sizeof(G1J), st));
         const G1A* fb = nullptr;
         CKS(ks_fixed_base(fk->ks, n, &fb, st));
-        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb));
+        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb, fk->ks->fb_w));
         launch_g1_to_abi(work.as<G1J>(), (uint64_t*)d_commitments, 1, batch, 1, n, 0, 0, st);
     }
     CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 0, (uint64_t*)d_proofs, st));
@@ -1122,7 +1131,7 @@ static int commit_fk20_compressed_dev(b200_fk* fk, const void* d_polys, size_t n
         CKS(work.alloc(batch * n * sizeof(G1J), st));
         const G1A* fb = nullptr;
         CKS(ks_fixed_base(fk->ks, n, &fb, st));
-        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb));
+        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb, fk->ks->fb_w));
         launch_g1_compress(work.as<G1J>(), d_commit48, 1, batch, 1, n, 0, 0, st);
     }
     CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 0, nullptr, st, d_proofs48));
@@ -1191,7 +1200,7 @@ extern "C" int b200_blob_to_kzg_commitment_batch(b200_ks* ks, const uint8_t* blo
     launch_fr_check_canonical(k.as<uint64_t>(), n, batch, flags.as<uint32_t>(), st);
     const G1A* fb = nullptr;
     if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));
-    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, ks->fb_w));
     launch_g1_compress(work.as<G1J>(), res.as<uint8_t>(), 1, batch, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(out48, res.p, batch * 48, cudaMemcpyDeviceToHost, st));
@@ -1232,7 +1241,7 @@ extern "C" int b200_compute_kzg_proof_batch(b200_ks* ks, const uint64_t* polys, 
                               ym.as<Fr>(), yc.as<uint64_t>(), q.as<uint64_t>(), flags.as<uint32_t>(), st);
     const G1A* fb = nullptr;
     if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));
-    CKS(dev_lincomb(ks->d_secret_g1, 0, q.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, q.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, ks->fb_w));
     launch_g1_compress(work.as<G1J>(), res.as<uint8_t>(), 1, batch, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(proofs48, res.p, batch * 48, cudaMemcpyDeviceToHost, st));

@@ -264,7 +264,9 @@ void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, s
 // become table look-ups: signed W-bit windows, table[i][w][d-1] = d * 2^(W w) * P_i in affine
 // form.  W = 8: 32 windows x 128 entries x 96 B = 384 KiB per base (3 GiB for the 8192 bases of
 // the n = 4096 FK20 settings -- HBM is what a B200 has plenty of), one product = 32 mixed
-// additions (~350 Fp multiplications) instead of ~1900.  W = 4: 64 windows x 8 entries = 48 KiB
+// additions (~350 Fp multiplications) instead of ~1900.  W = 12: 22 windows x 2048 entries = 4.1 MiB per
+// base and 22 mixed additions, used while the table stays small against HBM (the n = 4096 settings:
+// 17 + 35 GB).  W = 4: 64 windows x 8 entries = 48 KiB
 // per base and 64 mixed additions, for settings whose W = 8 table would not fit (config 5: 2.1 M
 // bases).
 static inline unsigned fb_windows(int W) { return (unsigned)((256 + W - 1) / W); }
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(128) k_fb_entries(const G1J* __restrict__ base
     const size_t row = t / chunks;
     const unsigned first = (unsigned)(t % chunks) * CH + 1;          // multiple of the first entry of this chunk
     G1J b = ld_vec(bases + row), acc = G1J::infinity();
-    for (int bit = 7; bit >= 0; bit--) {
+    for (int bit = 11; bit >= 0; bit--) {                             // first <= 2^11
         if (!acc.is_inf()) g1_dbl_ni(&acc, &acc);
         if ((first >> bit) & 1u) g1_add_ni(&acc, &acc, &b);
     }
@@ -331,7 +333,7 @@ void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* tabl
 template <int W>
 __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
                                                                          G1J* out, size_t out_bstride, size_t n, size_t batch) {
-    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1), PER_LIMB = 32 / W, MASK = (1u << W) - 1u;
+    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1), MASK = (1u << W) - 1u;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
     size_t b = t % batch, i = t / batch;
@@ -341,7 +343,10 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G
     G1J acc = G1J::infinity();
     unsigned carry = 0;
     for (unsigned w = 0; w < NW; w++) {
-        unsigned d = ((s.l[w / PER_LIMB] >> ((w % PER_LIMB) * W)) & MASK) + carry;
+        const unsigned off = w * W, li = off >> 5, sh = off & 31u;      // window bits may straddle two limbs (W = 12)
+        unsigned bits = s.l[li] >> sh;
+        if (sh + W > 32 && li + 1 < 8) bits |= s.l[li + 1] << (32 - sh);
+        unsigned d = (bits & MASK) + carry;
         bool neg = d > D;
         if (neg) { d = (1u << W) - d; carry = 1; } else carry = 0;
         if (d) {
@@ -356,7 +361,8 @@ void launch_g1_mul_fixed_base(const G1A* table, int W, const Fr* k, int k_is_mon
                               cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_MUL, st);
     if (!n || !batch) return;
-    if (W == 8) k_g1_mul_fixed_base<8><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+    if (W == 12) k_g1_mul_fixed_base<12><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+    else if (W == 8) k_g1_mul_fixed_base<8><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     else k_g1_mul_fixed_base<4><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     g_launch_count++;
 }
