@@ -503,14 +503,15 @@ extern "C" int b200_recover_poly_from_samples(b200_fs* fs, const uint64_t* s, co
 // In-place transform of `batch` vectors of n = 2^logn points (element i of blob b at
 // data[b * bstride + i * estride]).  dif: natural order in, bit-reversed out; otherwise (DIT)
 // bit-reversed in, natural out.  No 1/n scaling here.
+// skip_dif: leading decimation-in-frequency stages already done elsewhere (dev_fk20 folds two into ToeplitzPart2)
 static int dev_g1_fft_stages(b200_fs* fs, G1J* data, unsigned logn, size_t batch, size_t estride, size_t bstride,
-                             bool inverse, bool dif, cudaStream_t st) {
+                             bool inverse, bool dif, cudaStream_t st, unsigned skip_dif = 0) {
     if (logn == 0) return B200_OK;
     const ScalarProgram* progs;
     CKS(fs_programs(fs, inverse ? 1 : 0, program_mode_for_batch(batch), &progs));
     const size_t n = (size_t)1 << logn, halfw = fs->max_width / 2;
     if (dif) {
-        for (size_t m = n / 2; m >= 1; m >>= 1)
+        for (size_t m = (n / 2) >> skip_dif; m >= 1; m >>= 1)
             launch_g1_fft_stage(data, n / 2, batch, m, estride, bstride, true, progs, halfw / m, st);
     } else {
         for (size_t m = 1; m <= n / 2; m <<= 1)
@@ -823,7 +824,10 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
         // even entries carry 1/2 instead of 1/2k (see below): times k
         launch_fr_mul_even_odd(c.as<Fr>(), fr_from_u64(k), Fr::one(), batch * l * k2, st);
     }
-    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table, fk->fb_w, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
+    // FK20Single with a window table: ToeplitzPart2 and the first two inverse stages over the odd slots in one kernel
+    const bool fold2 = mode == 0 && l == 1 && fk->d_fb_table && k >= 8;
+    if (fold2) launch_fk20_part2_fold2(fk->d_fb_table, fk->fb_w, c.as<Fr>(), fs->dom.reverse, fs->max_width / k, h.as<G1J>(), k2, k, batch, st);
+    else if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table, fk->fb_w, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
     else launch_g1_mul_var(fk->d_x_ext_fft, 0, c.as<Fr>(), 1, h.as<G1J>(), l * k2, l * k2, batch, st);
     for (size_t cnt = l; cnt > 1; cnt /= 2) launch_g1_fold(h.as<G1J>(), l * k2, (cnt / 2) * k2, cnt * k2, batch, st);
     CKS(check_launches());
@@ -839,7 +843,7 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
         // twist by position, DIT forward; then the even slots are added.
         const unsigned logk = logk2 - 1;
         G1J* odd = h.as<G1J>() + 1;
-        CKS(dev_g1_fft_stages(fs, odd, logk, batch, 2, bstride, true, true, st));
+        CKS(dev_g1_fft_stages(fs, odd, logk, batch, 2, bstride, true, true, st, fold2 ? 2 : 0));
         const ScalarProgram* inv_progs;
         CKS(fs_programs(fs, 1, program_mode_for_batch(batch), &inv_progs));
         launch_g1_mul_programs(odd, k, batch, 2, bstride, inv_progs, (fs->max_width / 2) / k, 1, logk, st);

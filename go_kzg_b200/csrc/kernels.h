@@ -111,6 +111,10 @@ size_t fixed_base_tmp_bytes(size_t n, int W);
 void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* table, int W, cudaStream_t st);
 void launch_g1_mul_fixed_base(const G1A* table, int W, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
                               cudaStream_t st);
+// FK20Single: out[b][i] = c[b][i] X[i] for even i; the odd slots receive the result of the first two inverse DIF
+// stages over x[m] = c[2m+1] X[2m+1] (m < k, k >= 8), computed as 4-term fixed-base sums (see kernels_g1.cu)
+void launch_fk20_part2_fold2(const G1A* table, int W, const Fr* c_mont, const Fr* rev, size_t rstride, G1J* out, size_t out_bstride,
+                             size_t k, size_t batch, cudaStream_t st);
 // out[b * bstride + i * estride] = progs[idx(i) * prog_stride] * same element (in place)
 void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,
                             const ScalarProgram* progs, size_t prog_stride, int bitrev, unsigned logn, cudaStream_t st);

@@ -330,17 +330,10 @@ void launch_fixed_base_table(const G1J* pts, size_t n, G1J* bases_tmp, G1A* tabl
 }
 // out[b * out_bstride + i] = k[b * n + i] * P_i through the table (thread <-> (i, blob), blob fastest:
 // a warp walks the same table row)
+// acc += s * P through the window row of P (s canonical)
 template <int W>
-__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
-                                                                         G1J* out, size_t out_bstride, size_t n, size_t batch) {
+__device__ __forceinline__ void fb_accumulate(G1J* acc, const G1A* __restrict__ row, const Fr& s) {
     constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1), MASK = (1u << W) - 1u;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * batch) return;
-    size_t b = t % batch, i = t / batch;
-    Fr s = ld_vec(k + b * n + i);
-    if (k_is_mont) s = fe_from_mont(s);
-    const G1A* row = table + i * (size_t)(NW * D);
-    G1J acc = G1J::infinity();
     unsigned carry = 0;
     for (unsigned w = 0; w < NW; w++) {
         const unsigned off = w * W, li = off >> 5, sh = off & 31u;      // window bits may straddle two limbs (W = 12)
@@ -352,10 +345,71 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G
         if (d) {
             G1A p = ld_vec(row + w * D + (d - 1));
             if (neg) p.y = fe_neg(p.y);
-            g1_add_mixed_ni(&acc, &acc, &p);
+            g1_add_mixed_ni(acc, acc, &p);
+        }
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
+                                                                         G1J* out, size_t out_bstride, size_t n, size_t batch) {
+    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1);
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    size_t b = t % batch, i = t / batch;
+    Fr s = ld_vec(k + b * n + i);
+    if (k_is_mont) s = fe_from_mont(s);
+    G1J acc = G1J::infinity();
+    fb_accumulate<W>(&acc, table + i * (size_t)(NW * D), s);
+    st_vec(out + b * out_bstride + i, acc);
+}
+// ToeplitzPart2 of FK20Single fused with the first two stages of the inverse transform over the odd slots
+// (api.cu: dev_fk20).  The transform's inputs are x[m] = c[2m+1] X[2m+1] with FIXED points X, so two
+// decimation-in-frequency stages only mix the scalars: for q = k / 4, p < q and x_t = x[p + t q],
+//     out[p]       = x_0 + x_1 + x_2 + x_3
+//     out[p + q]   = u (x_0 - x_1 + x_2 - x_3)                       u  = w_(k/2)^-p
+//     out[p + 2q]  = v (x_0 - x_2) + v' (x_1 - x_3)                   v  = w_k^-p,  v' = w_k^-(p+q)
+//     out[p + 3q]  = u (v (x_0 - x_2) - v' (x_1 - x_3))
+// i.e. four 4-term fixed-base sums (4 x 22 mixed additions at W = 12) instead of 4 look-up products, 4 twiddle
+// products (~1450 Fp products each) and 4 butterflies.  Even slots i: plain c[i] X[i].  c is Montgomery,
+// rev[t rstride] = w_k^-t (Montgomery).  Threads <-> (slot, blob), blob fastest: a warp shares slot and scalars' roles.
+template <int W>
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_fk20_part2_fold2(const G1A* __restrict__ table, const Fr* __restrict__ c,
+                                                                        const Fr* __restrict__ rev, size_t rstride, G1J* out,
+                                                                        size_t out_bstride, size_t k, size_t batch) {
+    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1);
+    constexpr size_t ROW = (size_t)NW * D;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * k * batch) return;
+    const size_t b = t % batch, i = t / batch;
+    const Fr* cb = c + b * 2 * k;
+    G1J acc = G1J::infinity();
+    if (!(i & 1)) {
+        fb_accumulate<W>(&acc, table + i * ROW, fe_from_mont(ld_vec(cb + i)));
+    } else {
+        const size_t q = k / 4, m = i >> 1, o = m / q, p = m % q;
+        Fr u = ld_vec(rev + 2 * p * rstride), v = ld_vec(rev + p * rstride), v2 = ld_vec(rev + (p + q) * rstride);
+        for (unsigned tt = 0; tt < 4; tt++) {
+            const size_t src = 2 * (p + tt * q) + 1;
+            Fr s = ld_vec(cb + src);
+            bool neg = false;
+            if (o == 1) { s = fe_mul(s, u); neg = tt & 1; }
+            else if (o == 2) { s = fe_mul(s, (tt & 1) ? v2 : v); neg = tt >= 2; }
+            else if (o == 3) { s = fe_mul(fe_mul(s, (tt & 1) ? v2 : v), u); neg = (tt == 1 || tt == 2); }
+            if (neg) s = fe_neg(s);
+            fb_accumulate<W>(&acc, table + src * ROW, fe_from_mont(s));
         }
     }
     st_vec(out + b * out_bstride + i, acc);
+}
+void launch_fk20_part2_fold2(const G1A* table, int W, const Fr* c, const Fr* rev, size_t rstride, G1J* out, size_t out_bstride,
+                             size_t k, size_t batch, cudaStream_t st) {
+    ProfScope prof_scope(PROF_G1_MUL, st);
+    if (!k || !batch) return;
+    const unsigned grid = grid_for(2 * k * batch, G1_BLOCK);
+    if (W == 12) k_fk20_part2_fold2<12><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+    else if (W == 8) k_fk20_part2_fold2<8><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+    else k_fk20_part2_fold2<4><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+    g_launch_count++;
 }
 void launch_g1_mul_fixed_base(const G1A* table, int W, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
                               cudaStream_t st) {
