@@ -380,7 +380,9 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_fk20_part2_fold2(const G1
     constexpr size_t ROW = (size_t)NW * D;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * k * batch) return;
-    const size_t b = t % batch, i = t / batch;
+    // the odd slots (4-term sums) come first in grid order, the cheap even slots fill the tail of the launch
+    const size_t b = t % batch, ii = t / batch;
+    const size_t i = ii < k ? 2 * ii + 1 : 2 * (ii - k);
     const Fr* cb = c + b * 2 * k;
     G1J acc = G1J::infinity();
     if (!(i & 1)) {
