@@ -433,3 +433,67 @@ def fk20_multi_da_exponents(fs: FFTSettings, poly, secret, chunk_len):
     out = fs.fft(h + [0] * k, False)
     reverse_bit_order(out)
     return out
+
+
+# ----------------------------------------------------------------------------
+# package eth: the callers either side of the path
+# ----------------------------------------------------------------------------
+def valid_fr(le32: bytes) -> bool:
+    """bls/bignum_all.go:12-35 ValidFr: a little-endian uint256 is a field element iff it is < r."""
+    return int.from_bytes(le32, "little") < R_MOD
+
+
+def blob_to_polynomial(blob: bytes):
+    """eth/helpers.go:264-273 BlobToPolynomial: 32 little-endian bytes per element (bytesToBLSField ->
+    bls.FrFrom32, eth/helpers.go:105-109); returns (elements, ok), ok False if any element is >= r."""
+    out = []
+    for i in range(0, len(blob), 32):
+        chunk = blob[i:i + 32]
+        if not valid_fr(chunk):
+            return [], False
+        out.append(int.from_bytes(chunk, "little"))
+    return out, True
+
+
+def eth_domain(width: int):
+    """eth/globals.go:53-67: DomainFr[i] = ROOT_OF_UNITY^reverseBits(i), ROOT_OF_UNITY = 7^((r-1)/width)."""
+    w = pow(PRIMITIVE_ROOT, (R_MOD - 1) // width, R_MOD)
+    return [pow(w, reverse_bits_limited(width, i), R_MOD) for i in range(width)]
+
+
+def bit_reversal_permutation(values):
+    """eth/helpers.go:41-51: out[i] = l[reverseBits(i)] (applied to setup_G1_lagrange at eth/globals.go:48)."""
+    n = len(values)
+    return [values[reverse_bits_limited(n, i)] for i in range(n)]
+
+
+def evaluate_poly_in_evaluation_form(poly, x, roots, scale: int = 0):
+    """bls/globals.go:106-153 EvaluatePolyInEvaluationForm (barycentric formula; x outside the domain):
+    y = (x^n - 1) / n * sum_i poly[i] roots[i << scale] / (x - roots[i << scale])."""
+    n = len(poly)
+    if n != len(roots) >> scale:
+        raise ValueError("expected roots of unity to match polynomial size")      # bls/globals.go:107-109
+    inv_denom = [(x - roots[i << scale]) % R_MOD for i in range(n)]
+    inv_denom = [inv_fr(d) for d in inv_denom]                                   # BatchInvModFr, bls/globals.go:118-124
+    y = 0
+    for i in range(n):
+        y = (y + poly[i] * roots[i << scale] % R_MOD * inv_denom[i]) % R_MOD     # bls/globals.go:127-141
+    pow_b = (pow(x, n, R_MOD) - 1) % R_MOD                                       # bls/globals.go:143-146
+    return y * pow_b % R_MOD * inv_fr(n) % R_MOD                                 # bls/globals.go:147-152
+
+
+def compute_kzg_proof_quotient(poly, z, domain):
+    """eth/helpers.go:179-203 ComputeKZGProof, field side: returns (y, quotient in evaluation form); the proof is
+    LinCombG1(kzgSetupLagrange, quotient).  Raises for "invalid z challenge" (z in the domain) and for a
+    polynomial whose length differs from the domain's."""
+    if len(poly) != len(domain):
+        raise ValueError("polynomial has invalid length")                        # eth/helpers.go:186-188
+    y = evaluate_poly_in_evaluation_form(poly, z, domain, 0)                      # eth/helpers.go:180
+    q = []
+    for i in range(len(poly)):
+        if domain[i] == z:
+            raise ValueError("invalid z challenge")                              # eth/helpers.go:190-192
+        num = (poly[i] - y) % R_MOD                                              # eth/helpers.go:182-184
+        den = (domain[i] - z) % R_MOD                                            # eth/helpers.go:193
+        q.append(num * inv_fr(den) % R_MOD)                                      # eth/helpers.go:196-198 DivModFr
+    return y, q

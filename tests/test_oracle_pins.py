@@ -256,3 +256,85 @@ def test_c_das_ext_vs_py():
         assert all(c == 0 for c in coeffs[len(coeffs) // 2:])
     with pytest.raises(RuntimeError):       # das_extension.go:72-74
         cref.FFTSettings(3).das_fft_extension(cref.fr_to_limbs(list(range(8))))
+
+
+# ------------------------------------------------------------------------------ package eth restatements
+def test_eth_evaluation_form_restatements_are_self_consistent():
+    """oracle/pyref.py restates eth.BlobToPolynomial, EvaluatePolyInEvaluationForm and ComputeKZGProof's field
+    side (eth/helpers.go:179-203, 264-273; bls/globals.go:106-153).  Pins that need no group arithmetic: the
+    barycentric value equals Horner on the interpolating coefficients (inverse NTT over the bit-reversed
+    domain), and the quotient satisfies q_i (D_i - z) == p_i - y on the whole domain and interpolates
+    (p(X) - y) / (X - z)."""
+    import random
+    n = 64
+    rnd = random.Random(5)
+    dom = pyref.eth_domain(n)
+    w = pow(pyref.PRIMITIVE_ROOT, (pyref.R_MOD - 1) // n, pyref.R_MOD)
+    assert dom[0] == 1 and dom[1] == pow(w, n // 2, pyref.R_MOD)          # eth/globals.go:60-67: w^brp(i)
+    assert sorted(dom) == sorted(pow(w, i, pyref.R_MOD) for i in range(n))
+    coeffs = [rnd.randrange(pyref.R_MOD) for _ in range(n)]
+    evals_blob_order = [pyref.eval_poly(coeffs, d) for d in dom]
+    z = rnd.randrange(pyref.R_MOD)
+    y = pyref.evaluate_poly_in_evaluation_form(evals_blob_order, z, dom)
+    assert y == pyref.eval_poly(coeffs, z)
+    y2, q = pyref.compute_kzg_proof_quotient(evals_blob_order, z, dom)
+    assert y2 == y
+    assert all(qi * (d - z) % pyref.R_MOD == (p - y) % pyref.R_MOD for qi, d, p in zip(q, dom, evals_blob_order))
+    # q interpolates the polynomial quotient: synthetic division of p(X) - y by (X - z)
+    quo = [0] * (n - 1)
+    acc = 0
+    for i in range(n - 1, 0, -1):
+        acc = (coeffs[i] + acc * z) % pyref.R_MOD
+        quo[i - 1] = acc
+    assert q == [pyref.eval_poly(quo, d) for d in dom]
+    with pytest.raises(ValueError):
+        pyref.compute_kzg_proof_quotient(evals_blob_order, dom[5], dom)     # "invalid z challenge"
+    with pytest.raises(ValueError):
+        pyref.compute_kzg_proof_quotient(evals_blob_order[:-1], z, dom)     # "polynomial has invalid length"
+    # BlobToPolynomial / ValidFr
+    good = b"".join(v.to_bytes(32, "little") for v in coeffs)
+    assert pyref.blob_to_polynomial(good) == (coeffs, True)
+    bad = good[:32 * 7] + pyref.R_MOD.to_bytes(32, "little") + good[32 * 8:]
+    assert pyref.blob_to_polynomial(bad) == ([], False)
+    assert pyref.valid_fr((pyref.R_MOD - 1).to_bytes(32, "little")) and not pyref.valid_fr(b"\xff" * 32)
+    assert pyref.bit_reversal_permutation(list(range(8))) == [0, 4, 2, 6, 1, 5, 3, 7]
+
+
+def test_eth_lagrange_commitment_relation(trusted_setup_bytes):
+    """PolynomialToKZGCommitment (eth/helpers.go:98-103) over the shipped fixture: with the bit-reversed
+    Lagrange setup, committing to the evaluations of p on the bit-reversed domain gives p(s) G -- checked for a
+    sparse polynomial with the C oracle's LinCombG1 against the known secret 1337 (eth/trusted_setup.json)."""
+    import numpy as np
+    s1, lag = trusted_setup_bytes
+    n = 4096
+    lag_pts = cref.g1_decompress(lag)
+    perm = [pyref.reverse_bits_limited(n, i) for i in range(n)]
+    dom = pyref.eth_domain(n)
+    coeffs = {0: 5, 1: 7, 4095: 11}                                        # p = 5 + 7 X + 11 X^4095
+    evals = [sum(c * pow(d, e, pyref.R_MOD) for e, c in coeffs.items()) % pyref.R_MOD for d in dom]
+    got = cref.lincomb_g1(lag_pts[perm], cref.fr_to_limbs(evals))
+    want = cref.g1_mul_gen([sum(c * pow(1337, e, pyref.R_MOD) for e, c in coeffs.items()) % pyref.R_MOD])
+    assert np.array_equal(cref.g1_compress(got[None, :]), cref.g1_compress(want))
+
+
+def test_eth_compute_kzg_proof_restatement_vs_known_secret(trusted_setup_bytes):
+    """ComputeKZGProof restated (oracle/pyref.py quotient + the C oracle's LinCombG1 over the bit-reversed
+    Lagrange setup) == ((p(s) - y) / (s - z)) G for the fixture's known secret s = 1337: the same closed form
+    the GPU parity test holds the CUDA path to (tests/test_gpu_parity.py::test_compute_kzg_proof_evaluation_form)."""
+    import numpy as np
+    s1, lag = trusted_setup_bytes
+    n, R = 4096, pyref.R_MOD
+    perm = [pyref.reverse_bits_limited(n, i) for i in range(n)]
+    lag_brp = cref.g1_decompress(lag)[perm]
+    dom = pyref.eth_domain(n)
+    rnd = random.Random(11)
+    coeffs = [rnd.randrange(R) for _ in range(n)]
+    nat = cref.limbs_to_fr(cref.FFTSettings(12).fft(cref.fr_to_limbs(coeffs)))        # evaluations on w^i
+    blob = [nat[perm[i]] for i in range(n)]                                            # blob order: w^brp(i)
+    assert blob[:3] == [pyref.eval_poly(coeffs, d) for d in dom[:3]]
+    z = rnd.randrange(R)
+    y, q = pyref.compute_kzg_proof_quotient(blob, z, dom)
+    assert y == pyref.eval_poly(coeffs, z)
+    proof = cref.lincomb_g1(lag_brp, cref.fr_to_limbs(q))
+    want = cref.g1_mul_gen([(pyref.eval_poly(coeffs, 1337) - y) * pow((1337 - z) % R, -1, R) % R])
+    assert np.array_equal(cref.g1_compress(proof[None, :]), cref.g1_compress(want))
