@@ -32,6 +32,12 @@ def point_range(rank: int, world: int, n: int) -> range:
     return offset_range(rank, world, n)
 
 
+def block_sharded_transforms(world: int, k2: int) -> bool:
+    """Whether the two size-k2 G1 transforms of FK20 multi are spread over the ranks (b200_fk20_multi_finish_local_dev /
+    _merge_dev): power-of-two worlds with at least two points per block; otherwise every rank runs them in full."""
+    return world > 1 and world & (world - 1) == 0 and 2 * world <= k2
+
+
 def _stream_ptr(torch):
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -63,7 +69,7 @@ def da_using_fk20_multi_sharded(fk: "kzg.FK20MultiSettings", poly: np.ndarray, d
     else:
         d_sum = d_part
     d_out = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
-    if world > 1 and world & (world - 1) == 0 and 2 * world <= k2:
+    if block_sharded_transforms(world, k2):
         # the two G1 transforms, block-sharded: local stages, one all-gather of the blocks, the last log2(world) stages
         d_block = torch.zeros((k2 // world, 18), dtype=torch.int64, device="cuda")
         _check(L.b200_fk20_multi_finish_local_dev(fk.h, d_sum.data_ptr(), rank, world, d_block.data_ptr(), sp), "FK20 multi finish (local)")

@@ -74,3 +74,10 @@ def test_offset_and_point_ranges_partition():
     assert list(multi_gpu.offset_range(1, 8, 16)) == [2, 3]
     with pytest.raises(ValueError):
         multi_gpu.point_range(4, 4, 10)
+
+
+def test_block_sharded_transform_rule():
+    """the G1 transforms of FK20 multi are block-sharded for power-of-two worlds only (the library refuses others)"""
+    from go_kzg_b200 import multi_gpu
+    assert [w for w in range(1, 20) if multi_gpu.block_sharded_transforms(w, 1 << 17)] == [2, 4, 8, 16]
+    assert not multi_gpu.block_sharded_transforms(8, 8) and multi_gpu.block_sharded_transforms(4, 8)
