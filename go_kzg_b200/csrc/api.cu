@@ -3,6 +3,8 @@
 // LinCombG1, FK20 single / multi).  Every compute entry point runs on the GPU; there is no CPU
 // fallback (a missing device is an error).
 #include <cuda_runtime.h>
+#include <atomic>
+#include <stdlib.h>
 #include <mutex>
 #include <new>
 #include <string>
@@ -86,6 +88,32 @@ static void keep_pool_memory() {
     done[dev] = true;
 }
 
+// Host-buffer entry points run on a pooled non-blocking stream leased for the duration of the call (one pool per
+// device): callers on different threads (goroutines migrate across OS threads) overlap instead of serialising on
+// the legacy default stream.  Streams are never destroyed; a lease taken after cudaSetDevice belongs to that device.
+struct StreamLease {
+    cudaStream_t st = nullptr;
+    int dev = -1;
+    static std::mutex& mu() { static std::mutex m; return m; }
+    static std::vector<cudaStream_t>& pool(int d) { static std::vector<cudaStream_t> p[64]; return p[d]; }
+    int acquire() {
+        CK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64) return B200_ERR_BAD_INPUT;
+        {
+            std::lock_guard<std::mutex> lk(mu());
+            auto& p = pool(dev);
+            if (!p.empty()) { st = p.back(); p.pop_back(); return B200_OK; }
+        }
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        return B200_OK;
+    }
+    ~StreamLease() {
+        if (!st) return;
+        std::lock_guard<std::mutex> lk(mu());
+        pool(dev).push_back(st);
+    }
+};
+
 // one point at infinity per device (source of strided clears); never freed
 static int dev_infinity(G1J** out) {
     static std::mutex mu;
@@ -94,7 +122,7 @@ static int dev_infinity(G1J** out) {
     CK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return B200_ERR_BAD_INPUT;
     std::lock_guard<std::mutex> lk(mu);
-    if (!inf[dev]) { CK(cudaMalloc(&inf[dev], sizeof(G1J))); CK(cudaMemset(inf[dev], 0, sizeof(G1J))); }
+    if (!inf[dev]) { CK(cudaMalloc(&inf[dev], sizeof(G1J))); CK(cudaMemset(inf[dev], 0, sizeof(G1J))); CK(cudaDeviceSynchronize()); }
     *out = inf[dev];
     return B200_OK;
 }
@@ -277,6 +305,7 @@ static inline int program_mode_for_batch(size_t batch) { return batch >= 16 ? 1 
 
 // ------------------------------------------------------------------------------ Fr FFT
 static int dev_fr_fft(b200_fs* fs, const Fr* d_in, Fr* d_out, unsigned logn, size_t batch, bool inverse, cudaStream_t st) {
+    if (logn > 24) return B200_ERR_TOO_LARGE;   // two passes of at most 2^12 points each (kernels_fr.cu: launch_fr_ntt)
     DevBuf tmp;
     if (logn > 12) CKS(tmp.alloc(((size_t)batch << logn) * sizeof(Fr), st));
     Fr scale;
@@ -291,7 +320,7 @@ extern "C" int b200_fft_fr_batch(b200_fs* fs, const uint64_t* vals, size_t n, si
     CK(cudaSetDevice(fs->device));
     const uint64_t np = next_pow2(n);                              // fft_fr.go:60
     const unsigned logn = log2u(np);
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw, buf;
     CKS(raw.alloc(batch * np * 32, st));
     CKS(buf.alloc(batch * np * sizeof(Fr), st));
@@ -308,14 +337,23 @@ extern "C" int b200_fft_fr_batch(b200_fs* fs, const uint64_t* vals, size_t n, si
 extern "C" int b200_fft_fr(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out) {
     return b200_fft_fr_batch(fs, vals, n, 1, inverse, out);
 }
+// fft_fr.go:76-105 InplaceFFT: no padding -- a length that is not a power of two is an error (:81-83); n == 0
+// passes both checks and then divides by n (:89,100), a run-time panic.  vals and out may be the same buffer.
+extern "C" int b200_inplace_fft_fr(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out) {
+    if (n > fs->max_width) return B200_ERR_TOO_LARGE;              // fft_fr.go:78-80
+    if (n == 0) return B200_ERR_BAD_INPUT;
+    if (!is_pow2(n)) return B200_ERR_NOT_POW2;                     // fft_fr.go:81-83
+    return b200_fft_fr_batch(fs, vals, n, 1, inverse, out);
+}
 
 // ------------------------------------------------------------------------------ DAS extension
 extern "C" int b200_das_fft_extension_batch(b200_fs* fs, uint64_t* vals, size_t n, size_t batch) {
     if (n * 2 > fs->max_width) return B200_ERR_TOO_SMALL;   // das_extension.go:72-74
     if (n < 2 || !is_pow2(n)) return B200_ERR_BAD_INPUT;    // das_extension.go:22-24 "bad usage"
     if (batch == 0) return B200_OK;
+    if (batch > 65535) return B200_ERR_TOO_LARGE;           // the batch rides on grid.y
     CK(cudaSetDevice(fs->device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw, buf;
     CKS(raw.alloc(batch * n * 32, st)); CKS(buf.alloc(batch * n * sizeof(Fr), st));
     CK(cudaMemcpyAsync(raw.p, vals, batch * n * 32, cudaMemcpyHostToDevice, st));
@@ -407,7 +445,7 @@ extern "C" int b200_zero_poly_via_multiplication(b200_fs* fs, const uint64_t* mi
     }
     if (!zero_poly_sizes_ok(n_missing, length)) return B200_ERR_BAD_INPUT;
     CK(cudaSetDevice(fs->device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf ze, zp, raw;
     CKS(ze.alloc(length * sizeof(Fr), st)); CKS(zp.alloc(length * sizeof(Fr), st)); CKS(raw.alloc(2 * length * 32, st));
     CKS(dev_zero_poly(fs, m, cnt, n_missing, length, 1, ze.as<Fr>(), zp.as<Fr>(), st));
@@ -442,6 +480,7 @@ static int fs_shift_tables(b200_fs* fs, const Fr** inv_pows, const Fr** pows) {
 extern "C" int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t* samples, const uint8_t* present, size_t n,
                                                     size_t batch, uint64_t* out) {
     if (batch == 0) return B200_OK;
+    if (batch > 65535) return B200_ERR_TOO_LARGE;                  // the batch rides on grid.y / grid.z
     // missing index lists (recover_from_samples.go:45-50)
     std::vector<uint32_t> miss(batch * n), cnt(batch);
     for (size_t b = 0; b < batch; b++) {
@@ -461,7 +500,7 @@ extern "C" int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t*
     CKS(fs_shift_tables(fs, &shift_inv, &shift_fwd));
     const unsigned logn = log2u(n);
     const size_t total = batch * n;
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw, s, ze, zp, a, c, pres, flags;
     CKS(raw.alloc(total * 32, st)); CKS(s.alloc(total * sizeof(Fr), st)); CKS(ze.alloc(total * sizeof(Fr), st));
     CKS(zp.alloc(total * sizeof(Fr), st)); CKS(a.alloc(total * sizeof(Fr), st)); CKS(c.alloc(total * sizeof(Fr), st));
@@ -522,11 +561,12 @@ static int dev_g1_fft_stages(b200_fs* fs, G1J* data, unsigned logn, size_t batch
 
 extern "C" int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out) {
     if (n > fs->max_width) return B200_ERR_TOO_LARGE;     // fft_g1.go:60-62
+    if (n == 0) return B200_ERR_BAD_INPUT;                // bls.IsPowerOfTwo(0) holds, then fft_g1.go:78,88 divides by n: panic
     if (!is_pow2(n)) return B200_ERR_NOT_POW2;            // fft_g1.go:63-65
     if (batch == 0) return B200_OK;
     CK(cudaSetDevice(fs->device));
     const unsigned logn = log2u(n);
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw, buf;
     CKS(raw.alloc(batch * n * 144, st));
     CKS(buf.alloc(batch * n * sizeof(G1J), st));
@@ -571,7 +611,7 @@ extern "C" int b200_g1_lincomb(const uint64_t* points, const uint64_t* scalars, 
     if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
     if (n == 0) { memset(out, 0, 144); return B200_OK; }     // bls/bls_test.go:69-77: empty sum is infinity
     CK(cudaSetDevice(g_device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw, pts, k, work;
     CKS(raw.alloc(n * 144, st)); CKS(pts.alloc(n * sizeof(G1J), st)); CKS(k.alloc(n * 32, st)); CKS(work.alloc(n * sizeof(G1J), st));
     CK(cudaMemcpyAsync(raw.p, points, n * 144, cudaMemcpyHostToDevice, st));
@@ -589,7 +629,7 @@ extern "C" int b200_g1_mul_many(const uint64_t* points, const uint64_t* scalars,
     if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
     if (n == 0) return B200_OK;
     CK(cudaSetDevice(g_device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw, pts, k;
     CKS(raw.alloc(n * 144, st)); CKS(pts.alloc(n * sizeof(G1J), st)); CKS(k.alloc(n * 32, st));
     CK(cudaMemcpyAsync(raw.p, points, n * 144, cudaMemcpyHostToDevice, st));
@@ -614,30 +654,51 @@ struct b200_ks {
     G1A* d_fb_table = nullptr;    // fixed-base window table of SecretG1[:fb_n] (built on first commit)
     int fb_w = 8;                 // its window bits
     size_t fb_n = 0;
+    std::vector<G1A*> retired;    // smaller tables superseded by d_fb_table (freed with the settings)
 };
 
-// fixed-base tables are used while they stay below this many bytes per settings object
-static const size_t kFixedBaseBudget12 = (size_t)40 << 30;    // 12-bit windows (4.1 MiB per base) up to here / 40 % of the free HBM
+// Fixed-base window tables.  Window bits: 8 by default (384 KiB per base: 1.5 GiB for the 4096 commitment bases,
+// 3 GiB for the 8192 bases of the n = 4096 FK20 settings); wider windows trade HBM for additions and are opt-in
+// (b200_set_fixed_base_window / B200_FB_WINDOW = 10 or 12: 1.3 / 4.1 MiB per base); 4 bits (48 KiB per base) when
+// the preferred table does not fit (config 5: 2.1 M bases).
+static std::atomic<int> g_fb_window{0};   // 0: not set -> environment -> 8
+static int preferred_fb_window() {
+    int w = g_fb_window.load();
+    if (w == 0) {
+        const char* e = getenv("B200_FB_WINDOW");
+        w = e ? atoi(e) : 8;
+        if (w != 4 && w != 8 && w != 10 && w != 12) w = 8;
+        g_fb_window = w;
+    }
+    return w;
+}
+extern "C" int b200_set_fixed_base_window(int bits) {
+    if (bits != 4 && bits != 8 && bits != 10 && bits != 12) return B200_ERR_BAD_INPUT;
+    g_fb_window = bits;
+    return B200_OK;
+}
+static const size_t kFixedBaseBudgetWide = (size_t)40 << 30;  // 10 / 12-bit windows up to here and 40 % of the free HBM
 static const size_t kFixedBaseBudget8 = (size_t)8 << 30;      // 8-bit windows (384 KiB per base) up to here
 static const size_t kFixedBaseBudget4 = (size_t)128 << 30;    // else 4-bit windows (48 KiB per base) up to here / 70 % of the free HBM
 
-// Window table over d_pts[0..n): *out_w = 8 or 4 (window bits), *out_table = nullptr when nothing fits (the callers
-// then use the generic windowed multiplication).  Running out of memory is not an error either.
+// Window table over d_pts[0..n): *out_w = window bits, *out_table = nullptr when nothing fits (the callers
+// then use the bucket MSM / generic windowed multiplication).  Running out of memory is not an error either.
 static int build_fixed_base(const G1J* d_pts, size_t n, G1A** out_table, int* out_w, cudaStream_t st) {
     *out_table = nullptr; *out_w = 8;
     if (n == 0) return B200_OK;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return B200_OK; }
-    // widest windows first: 12 bits while the table is a modest share of the free HBM, 8 bits up to 8 GiB, 4 bits as
-    // long as it fits at all; an allocation failure moves on to the next narrower choice
+    // the preferred width first, then the narrower ones; an allocation failure moves on to the next choice
     G1A* table = nullptr;
     G1J* tmp = nullptr;
     int W = 0;
-    const int choices[3] = {12, 8, 4};
-    for (int c = 0; c < 3 && !table; c++) {
+    const int pref = preferred_fb_window();
+    const int choices[4] = {12, 10, 8, 4};
+    for (int c = 0; c < 4 && !table; c++) {
         const int w = choices[c];
+        if (w > pref) continue;
         const size_t tb = fixed_base_table_bytes(n, w), need = tb + fixed_base_tmp_bytes(n, w);
-        bool fits = w == 12 ? (tb <= kFixedBaseBudget12 && need <= free_b / 10 * 4)
+        bool fits = w >= 10 ? (tb <= kFixedBaseBudgetWide && need <= free_b / 10 * 4)
                   : w == 8  ? (tb <= kFixedBaseBudget8 && need <= free_b / 10 * 7)
                             : (tb <= kFixedBaseBudget4 && need <= free_b / 10 * 7);
         if (!fits) continue;
@@ -654,20 +715,22 @@ static int build_fixed_base(const G1J* d_pts, size_t n, G1A** out_table, int* ou
     *out_table = table; *out_w = W;
     return B200_OK;
 }
-// table covering SecretG1[:n] (or null when over budget)
-static int ks_fixed_base(b200_ks* ks, size_t n, const G1A** table, cudaStream_t st) {
+// Table covering SecretG1[:n] (null when over budget) and its window width, handed out together under the lock.
+// Tables only ever grow: a table superseded by a larger one stays allocated until the settings are freed, because
+// a concurrent call on another thread may still have kernels in flight that read it.
+static int ks_fixed_base(b200_ks* ks, size_t n, const G1A** table, int* w, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(ks->mu);
     if (ks->fb_n < n) {
-        if (ks->d_fb_table) { cudaFree(ks->d_fb_table); ks->d_fb_table = nullptr; ks->fb_n = 0; }
         G1A* t = nullptr;
-        int w = 8;
-        CKS(build_fixed_base(ks->d_secret_g1, n, &t, &w, st));
-        ks->fb_w = w;
+        int tw = 8;
+        CKS(build_fixed_base(ks->d_secret_g1, n, &t, &tw, st));
+        if (!t) { *table = nullptr; *w = 8; return B200_OK; }
+        if (ks->d_fb_table) ks->retired.push_back(ks->d_fb_table);
+        ks->fb_w = tw;
         ks->d_fb_table = t;
-        ks->fb_n = t ? n : 0;
-        if (!t) { *table = nullptr; return B200_OK; }
+        ks->fb_n = n;
     }
-    *table = ks->d_fb_table;
+    *table = ks->d_fb_table; *w = ks->fb_w;
     return B200_OK;
 }
 
@@ -676,10 +739,10 @@ extern "C" int b200_kzg_settings_new(b200_fs* fs, const uint64_t* secret_g1, siz
     if (n_g1 != n_g2) return B200_ERR_LEN_MISMATCH;      // kzg.go:22-24
     if (n_g1 < fs->max_width) return B200_ERR_TOO_SMALL;  // kzg.go:25-27
     CK(cudaSetDevice(fs->device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     b200_ks* ks = new (std::nothrow) b200_ks();
     if (!ks) return B200_ERR_CUDA;
     ks->fs = fs; ks->n_g1 = n_g1; ks->device = fs->device;
-    cudaStream_t st = nullptr;
     DevBuf raw;
     int rc = raw.alloc(n_g1 * 144, st);
     if (!rc && cudaMalloc(&ks->d_secret_g1, (n_g1 ? n_g1 : 1) * sizeof(G1J)) != cudaSuccess) rc = B200_ERR_CUDA;
@@ -699,6 +762,7 @@ extern "C" void b200_kzg_settings_free(b200_ks* ks) {
     cudaSetDevice(ks->device);
     cudaFree(ks->d_secret_g1);
     cudaFree(ks->d_fb_table);
+    for (G1A* t : ks->retired) cudaFree(t);
     delete ks;
 }
 
@@ -707,13 +771,14 @@ extern "C" int b200_commit_to_poly_batch(b200_ks* ks, const uint64_t* coeffs, si
     if (batch == 0) return B200_OK;
     if (n == 0) { memset(out, 0, batch * 144); return B200_OK; }
     CK(cudaSetDevice(ks->fs->device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf k, work, res;
     CKS(k.alloc(batch * n * 32, st)); CKS(work.alloc(batch * n * sizeof(G1J), st)); CKS(res.alloc(batch * 144, st));
     CK(cudaMemcpyAsync(k.p, coeffs, batch * n * 32, cudaMemcpyHostToDevice, st));
     const G1A* fb = nullptr;
-    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));     // worth a table only for real workloads
-    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, ks->fb_w));
+    int fbw = 8;
+    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, &fbw, st));     // worth a table only for real workloads
+    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, fbw));
     launch_g1_to_abi(work.as<G1J>(), res.as<uint64_t>(), 1, batch, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(out, res.p, batch * 144, cudaMemcpyDeviceToHost, st));
@@ -732,7 +797,6 @@ struct b200_fk {
     G1J* d_x_ext_fft = nullptr;   // [chunk_len][n2 / chunk_len], natural order (kzg.go:62,110-114)
     G1A* d_fb_table = nullptr;    // fixed-base window table over d_x_ext_fft (null when over budget)
     int fb_w = 8;                 // its window bits (8, or 4 for very large settings)
-    unsigned long long last_launches = 0;
 };
 
 // kzg.go:43-64 / 73-116 + fk20_single.go:40-56 toeplitzPart1
@@ -744,13 +808,14 @@ static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk**
     if (n2 < 2) return B200_ERR_TOO_SMALL;                   // kzg.go:50-52 / 80-82
     if (chunk_len > n2 / 2) return B200_ERR_TOO_LARGE;       // kzg.go:83-85
     if (!is_pow2(chunk_len)) return B200_ERR_NOT_POW2;       // kzg.go:86-91
+    if (n2 / chunk_len > ((size_t)1 << 24)) return B200_ERR_TOO_LARGE;   // Fr NTT limit of this library (launch_fr_ntt)
     CK(cudaSetDevice(fs->device));
     const size_t n = n2 / 2, l = chunk_len, k = n / l, k2 = 2 * k;
     const unsigned logk2 = log2u(k2);
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     b200_fk* fk = new (std::nothrow) b200_fk();
     if (!fk) return B200_ERR_CUDA;
     fk->ks = ks; fk->n2 = n2; fk->chunk_len = l; fk->device = fs->device;
-    cudaStream_t st = nullptr;
     int rc = B200_OK;
     do {
         if (cudaMalloc(&fk->d_x_ext_fft, l * k2 * sizeof(G1J)) != cudaSuccess) { rc = B200_ERR_CUDA; break; }
@@ -786,7 +851,7 @@ extern "C" int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out) {
     if (file >= fk->chunk_len) return B200_ERR_BAD_INPUT;
     CK(cudaSetDevice(fk->ks->fs->device));
     const size_t k2 = fk->n2 / fk->chunk_len;
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw;
     CKS(raw.alloc(k2 * 144, st));
     launch_g1_to_abi(fk->d_x_ext_fft + file * k2, raw.as<uint64_t>(), k2, 1, 1, k2, 0, 0, st);
@@ -795,7 +860,10 @@ extern "C" int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out) {
     CK(cudaStreamSynchronize(st));
     return B200_OK;
 }
-extern "C" uint64_t b200_fk20_last_launch_count(const b200_fk* fk) { return fk->last_launches; }
+// kernels launched by the last FK20 / commit+FK20 call made on the calling thread (handles stay immutable)
+static thread_local unsigned long long t_last_launches = 0;
+extern "C" uint64_t b200_last_launch_count(void) { return t_last_launches; }
+extern "C" uint64_t b200_fk20_last_launch_count(const b200_fk*) { return t_last_launches; }
 
 // The FK20 pipeline on device buffers, for `batch` polynomials of n coefficients (canonical):
 //   c      = toeplitz coefficients (per chunk offset)                      fk20_single.go:89-119
@@ -868,13 +936,13 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
 static int host_fk20(b200_fk* fk, const uint64_t* poly, size_t n, int mode, uint64_t* proofs) {
     CK(cudaSetDevice(fk->ks->fs->device));
     const size_t n_out = mode == 0 ? n / fk->chunk_len : 2 * n / fk->chunk_len;
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf dp, dout;
     CKS(dp.alloc(n * 32, st)); CKS(dout.alloc(n_out * 144, st));
     CK(cudaMemcpyAsync(dp.p, poly, n * 32, cudaMemcpyHostToDevice, st));
     unsigned long long before = g_launch_count;
     CKS(dev_fk20(fk, dp.as<uint64_t>(), n, 1, mode, dout.as<uint64_t>(), st));
-    fk->last_launches = g_launch_count - before;
+    t_last_launches = g_launch_count - before;
     CK(cudaMemcpyAsync(proofs, dout.p, n_out * 144, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return B200_OK;
@@ -1064,7 +1132,7 @@ extern "C" int b200_generate_testing_setup_g1(const uint64_t* secret, size_t n, 
     if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
     if (n == 0) return B200_OK;
     CK(cudaSetDevice(g_device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     Fr sq[40];
     sq[0] = fr_from_abi_mont(secret);
     for (int j = 1; j < 40; j++) sq[j] = fe_mul(sq[j - 1], sq[j - 1]);
@@ -1099,19 +1167,20 @@ extern "C" int b200_commit_fk20_batch_dev(b200_fk* fk, const void* d_polys, size
         DevBuf work;
         CKS(work.alloc(batch * n * sizeof(G1J), st));
         const G1A* fb = nullptr;
-        CKS(ks_fixed_base(fk->ks, n, &fb, st));
-        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb, fk->ks->fb_w));
+        int fbw = 8;
+        CKS(ks_fixed_base(fk->ks, n, &fb, &fbw, st));
+        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb, fbw));
         launch_g1_to_abi(work.as<G1J>(), (uint64_t*)d_commitments, 1, batch, 1, n, 0, 0, st);
     }
     CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 0, (uint64_t*)d_proofs, st));
-    fk->last_launches = g_launch_count - before;
+    t_last_launches = g_launch_count - before;
     return B200_OK;
 }
 extern "C" int b200_commit_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint64_t* commitments,
                                       uint64_t* proofs) {
     if (batch == 0) return B200_OK;
     CK(cudaSetDevice(fk->ks->fs->device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf dp, dc, dout;
     CKS(dp.alloc(batch * n * 32, st)); CKS(dc.alloc(batch * 144, st)); CKS(dout.alloc(batch * n * 144, st));
     CK(cudaMemcpyAsync(dp.p, polys, batch * n * 32, cudaMemcpyHostToDevice, st));
@@ -1134,12 +1203,13 @@ static int commit_fk20_compressed_dev(b200_fk* fk, const void* d_polys, size_t n
         DevBuf work;
         CKS(work.alloc(batch * n * sizeof(G1J), st));
         const G1A* fb = nullptr;
-        CKS(ks_fixed_base(fk->ks, n, &fb, st));
-        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb, fk->ks->fb_w));
+        int fbw = 8;
+        CKS(ks_fixed_base(fk->ks, n, &fb, &fbw, st));
+        CKS(dev_lincomb(fk->ks->d_secret_g1, 0, (const Fr*)d_polys, 0, work.as<G1J>(), n, batch, st, fb, fbw));
         launch_g1_compress(work.as<G1J>(), d_commit48, 1, batch, 1, n, 0, 0, st);
     }
     CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 0, nullptr, st, d_proofs48));
-    fk->last_launches = g_launch_count - before;
+    t_last_launches = g_launch_count - before;
     return B200_OK;
 }
 extern "C" int b200_commit_fk20_batch_compressed_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_commitments48,
@@ -1151,7 +1221,7 @@ extern "C" int b200_commit_fk20_batch_compressed(b200_fk* fk, const uint64_t* po
                                                  uint8_t* proofs48) {
     if (batch == 0) return B200_OK;
     CK(cudaSetDevice(fk->ks->fs->device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf dp, dc, dout;
     CKS(dp.alloc(batch * n * 32, st)); CKS(dc.alloc(batch * 48, st)); CKS(dout.alloc(batch * n * 48, st));
     CK(cudaMemcpyAsync(dp.p, polys, batch * n * 32, cudaMemcpyHostToDevice, st));
@@ -1177,7 +1247,7 @@ extern "C" int b200_g1_to_compressed_batch(const uint64_t* points, size_t n, uin
     if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
     if (n == 0) return B200_OK;
     CK(cudaSetDevice(g_device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf in, out;
     CKS(in.alloc(n * 144, st)); CKS(out.alloc(n * 48, st));
     CK(cudaMemcpyAsync(in.p, points, n * 144, cudaMemcpyHostToDevice, st));
@@ -1193,7 +1263,7 @@ extern "C" int b200_blob_to_kzg_commitment_batch(b200_ks* ks, const uint8_t* blo
     if (n > ks->n_g1) return B200_ERR_LEN_MISMATCH;
     if (batch == 0) return B200_OK;
     CK(cudaSetDevice(ks->fs->device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     if (n == 0) { for (size_t b = 0; b < batch; b++) { memset(out48 + 48 * b, 0, 48); out48[48 * b] = 0xC0; ok[b] = 1; } return B200_OK; }
     DevBuf k, work, res, flags;
     CKS(k.alloc(batch * n * 32, st)); CKS(work.alloc(batch * n * sizeof(G1J), st)); CKS(res.alloc(batch * 48, st));
@@ -1203,8 +1273,9 @@ extern "C" int b200_blob_to_kzg_commitment_batch(b200_ks* ks, const uint8_t* blo
     CK(cudaMemcpyAsync(k.p, blobs, batch * n * 32, cudaMemcpyHostToDevice, st));
     launch_fr_check_canonical(k.as<uint64_t>(), n, batch, flags.as<uint32_t>(), st);
     const G1A* fb = nullptr;
-    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));
-    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, ks->fb_w));
+    int fbw = 8;
+    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, &fbw, st));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, k.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, fbw));
     launch_g1_compress(work.as<G1J>(), res.as<uint8_t>(), 1, batch, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(out48, res.p, batch * 48, cudaMemcpyDeviceToHost, st));
@@ -1228,7 +1299,7 @@ extern "C" int b200_compute_kzg_proof_batch(b200_ks* ks, const uint64_t* polys, 
     if (n > ks->n_g1) return B200_ERR_LEN_MISMATCH;          // "polynomial has invalid length"
     if (batch == 0) return B200_OK;
     CK(cudaSetDevice(fs->device));
-    cudaStream_t st = nullptr;
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     const unsigned logn = log2u(n);
     DevBuf f, dz, inv, part, ym, yc, q, work, res, flags;
     CKS(f.alloc(batch * n * 32, st)); CKS(dz.alloc(batch * 32, st)); CKS(inv.alloc(batch * n * 32, st));
@@ -1244,8 +1315,9 @@ extern "C" int b200_compute_kzg_proof_batch(b200_ks* ks, const uint64_t* polys, 
     launch_eval_form_quotient(fs->dom, f.as<uint64_t>(), dz.as<uint64_t>(), logn, batch, fr_inv_of_u64(n), inv.as<Fr>(), part.as<Fr>(),
                               ym.as<Fr>(), yc.as<uint64_t>(), q.as<uint64_t>(), flags.as<uint32_t>(), st);
     const G1A* fb = nullptr;
-    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, st));
-    CKS(dev_lincomb(ks->d_secret_g1, 0, q.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, ks->fb_w));
+    int fbw = 8;
+    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, &fbw, st));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, q.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, fbw));
     launch_g1_compress(work.as<G1J>(), res.as<uint8_t>(), 1, batch, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(proofs48, res.p, batch * 48, cudaMemcpyDeviceToHost, st));
@@ -1261,18 +1333,27 @@ extern "C" int b200_compute_kzg_proof_batch(b200_ks* ks, const uint64_t* polys, 
 
 // ------------------------------------------------------------------------------ profiling
 namespace b200 {
-bool g_prof_on = false;
-struct ProfRec { int cat; cudaEvent_t e0, e1; };
+std::atomic<bool> g_prof_on{false};
+struct ProfRec { int cat; cudaEvent_t e0, e1; bool closed; };
 static std::vector<ProfRec> g_prof_recs;
-void prof_begin_event(int cat, cudaStream_t st) {
-    ProfRec r; r.cat = cat;
-    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+static std::mutex g_prof_mu;
+long prof_begin_event(int cat, cudaStream_t st) {
+    ProfRec r; r.cat = cat; r.closed = false;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); return -1; }
     cudaEventRecord(r.e0, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_recs.push_back(r);
+    return (long)g_prof_recs.size() - 1;
 }
-void prof_end_event(cudaStream_t st) { cudaEventRecord(g_prof_recs.back().e1, st); }
+void prof_end_event(long rec, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (rec < 0 || (size_t)rec >= g_prof_recs.size()) return;     // a profile_begin/end in between dropped the record
+    cudaEventRecord(g_prof_recs[rec].e1, st);
+    g_prof_recs[rec].closed = true;
+}
 }  // namespace b200
 extern "C" int b200_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof_recs.clear();
     g_prof_on = true;
@@ -1281,13 +1362,14 @@ extern "C" int b200_profile_begin(void) {
 extern "C" int b200_profile_end(double* ms_per_class, uint64_t* launches_per_class) {
     g_prof_on = false;
     CK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (int c = 0; c < PROF_NCAT; c++) { ms_per_class[c] = 0; launches_per_class[c] = 0; }
     for (auto& r : g_prof_recs) {
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
-        ms_per_class[r.cat] += ms; launches_per_class[r.cat]++;
+        if (r.closed && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { ms_per_class[r.cat] += ms; launches_per_class[r.cat]++; }
         cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
     }
+    cudaGetLastError();
     g_prof_recs.clear();
     return B200_OK;
 }

@@ -111,8 +111,8 @@ inline void g1_compress(uint8_t out[48], const G1J& p) {
     out[0] |= 0x80;
     if (fp_canon_gt_half(y)) out[0] |= 0x20;
 }
-// 0 ok, 1 malformed flags / x >= p, 2 not on curve.  (No subgroup check: neither the
-// reference's callers nor its tests depend on one for the hot path.)
+// 0 ok, 1 malformed flags / x >= p, 2 not on curve, 3 not in the prime-order subgroup (kilic's FromCompressed,
+// reached through bls/bls_kilic.go:118-121, rejects all three).
 inline int g1_decompress(G1J& p, const uint8_t in[48]) {
     if (!(in[0] & 0x80)) return 1;
     if (in[0] & 0x40) {
@@ -141,6 +141,7 @@ inline int g1_decompress(G1J& p, const uint8_t in[48]) {
     Fp yc = fe_from_mont(y);
     if (fp_canon_gt_half(yc) != !!(in[0] & 0x20)) y = fe_neg(y);
     p.x = xm; p.y = y; p.z = Fp::one();
+    if (!g1_in_subgroup(p)) return 3;
     return 0;
 }
 

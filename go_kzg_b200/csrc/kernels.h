@@ -10,20 +10,21 @@
 
 namespace b200 {
 
-// every launcher bumps this (gpu_launches in bench.py)
-extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this process (any thread)
+// every launcher bumps this (gpu_launches in bench.py): kernels launched by the calling thread, so that a
+// before/after difference around a call is exact whatever other threads do
+extern thread_local unsigned long long g_launch_count;
 
 // Optional per-kernel-class device timing (bench.py's roofline): when enabled, every launcher
 // brackets its launches with CUDA events on the launching stream.
-enum ProfCat { PROF_FR_NTT = 0, PROF_G1_FFT_STAGE, PROF_G1_MUL, PROF_G1_FOLD, PROF_MISC, PROF_NCAT };
-extern bool g_prof_on;
-void prof_begin_event(int cat, cudaStream_t st);
-void prof_end_event(cudaStream_t st);
+enum ProfCat { PROF_FR_NTT = 0, PROF_G1_FFT_STAGE, PROF_G1_MUL, PROF_G1_FOLD, PROF_MISC, PROF_G1_LOOKUP, PROF_G1_MSM, PROF_NCAT };
+extern std::atomic<bool> g_prof_on;
+long prof_begin_event(int cat, cudaStream_t st);   // returns the record's index (-1: not recorded)
+void prof_end_event(long rec, cudaStream_t st);
 struct ProfScope {
     cudaStream_t st;
-    bool on;
-    ProfScope(int cat, cudaStream_t s) : st(s), on(g_prof_on) { if (on) prof_begin_event(cat, st); }
-    ~ProfScope() { if (on) prof_end_event(st); }
+    long rec;
+    ProfScope(int cat, cudaStream_t s) : st(s), rec(g_prof_on.load(std::memory_order_relaxed) ? prof_begin_event(cat, s) : -1) {}
+    ~ProfScope() { if (rec >= 0) prof_end_event(rec, st); }
 };
 
 // ---------------------------------------------------------------- Fr

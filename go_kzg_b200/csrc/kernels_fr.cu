@@ -201,9 +201,18 @@ static void run_pass(NttPass& P, size_t ngroups, size_t batch, cudaStream_t st) 
     size_t work = M * P.cols / 4;       // radix-4 units per stage pair
     unsigned threads = work >= 1024 ? 1024 : (work < 32 ? 32 : (unsigned)work);   // 64 registers: measured faster than 512 x 92
     if (!smem_attr_done(0)) cudaFuncSetAttribute(k_fr_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    dim3 grid((unsigned)ngroups, (unsigned)batch);
-    k_fr_ntt_pass<<<grid, threads, smem, st>>>(P);
-    g_launch_count++;
+    // the batch rides on grid.y (at most 65535): larger batches (the product tree of the zero polynomial has
+    // batch * roots / 32 nodes) go in chunks
+    const Fr* in0 = P.in;
+    Fr* out0 = P.out;
+    for (size_t b0 = 0; b0 < batch; b0 += 65535) {
+        const size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        P.in = in0 + b0 * P.n; P.out = out0 + b0 * P.n;
+        dim3 grid((unsigned)ngroups, (unsigned)nb);
+        k_fr_ntt_pass<<<grid, threads, smem, st>>>(P);
+        g_launch_count++;
+    }
+    P.in = in0; P.out = out0;
 }
 
 void launch_fr_ntt(const FrDomain& dom, const Fr* in, Fr* out, Fr* tmp, unsigned logn, size_t batch, bool inverse,

@@ -12,7 +12,7 @@
 
 namespace b200 {
 
-std::atomic<unsigned long long> g_launch_count{0};
+thread_local unsigned long long g_launch_count = 0;
 
 // Launch shape of the integer-pipe bound G1 kernels.  128 registers per thread hold the working
 // set of the out-of-line point operations without spills (ptxas -v), which lets 4 CTAs of 128
@@ -405,19 +405,21 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_fk20_part2_fold2(const G1
 }
 void launch_fk20_part2_fold2(const G1A* table, int W, const Fr* c, const Fr* rev, size_t rstride, G1J* out, size_t out_bstride,
                              size_t k, size_t batch, cudaStream_t st) {
-    ProfScope prof_scope(PROF_G1_MUL, st);
+    ProfScope prof_scope(PROF_G1_LOOKUP, st);
     if (!k || !batch) return;
     const unsigned grid = grid_for(2 * k * batch, G1_BLOCK);
     if (W == 12) k_fk20_part2_fold2<12><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+    else if (W == 10) k_fk20_part2_fold2<10><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
     else if (W == 8) k_fk20_part2_fold2<8><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
     else k_fk20_part2_fold2<4><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
     g_launch_count++;
 }
 void launch_g1_mul_fixed_base(const G1A* table, int W, const Fr* k, int k_is_mont, G1J* out, size_t out_bstride, size_t n, size_t batch,
                               cudaStream_t st) {
-    ProfScope prof_scope(PROF_G1_MUL, st);
+    ProfScope prof_scope(PROF_G1_LOOKUP, st);
     if (!n || !batch) return;
     if (W == 12) k_g1_mul_fixed_base<12><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+    else if (W == 10) k_g1_mul_fixed_base<10><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     else if (W == 8) k_g1_mul_fixed_base<8><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     else k_g1_mul_fixed_base<4><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     g_launch_count++;

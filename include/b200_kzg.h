@@ -16,7 +16,9 @@
  *
  * Ownership: the caller allocates all inputs and outputs; the library never keeps a caller
  * pointer after return.  Device tables live in the opaque handles.  Handles are immutable
- * after creation and may be used from any thread; each call sets its CUDA device itself.
+ * after creation (lazily built tables are published under a lock and never freed or moved while the handle
+ * lives) and may be used from any thread concurrently; each call sets its CUDA device itself and runs on a
+ * pooled non-blocking stream of its own, so concurrent callers do not serialise on the default stream.
  *
  * Errors: every function returns a b200_status.  The Go shim maps them back to the
  * reference's error/panic split.  There is NO CPU fallback: without a
@@ -78,7 +80,9 @@ void b200_g1_to_compressed_many(uint8_t* out, const uint64_t* pts, size_t n);
 int b200_g1_from_compressed_many(uint64_t* out, const uint8_t* in, size_t n);
 
 /* Device MSM.  bls/bls_kilic.go:132-150 LinCombG1: sum_i scalars[i] * points[i]; n == 0 gives
- * infinity (bls/bls_test.go:69-77).  Pippenger, 8-bit windows. */
+ * infinity (bls/bls_test.go:69-77).  Pippenger bucket method (kernels_msm.cu): GLV halves, signed windows,
+ * per-window buckets accumulated in shared memory, warp-shuffle running-sum reduction; below 32 terms the
+ * per-term windowed multiplication + fold tree is used instead. */
 int b200_g1_lincomb(const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t out[18]);
 /* Device batch MulG1: out[i] = scalars[i] * points[i] (the loop at fk20_single.go:72-74). */
 int b200_g1_mul_many(const uint64_t* points, const uint64_t* scalars, size_t n, uint64_t* out);
@@ -93,6 +97,9 @@ int b200_fs_roots(const b200_fs* fs, int reverse, uint64_t* out);
 /* fft_fr.go:55-74 FFT: n <= MaxWidth values, zero-padded to the next power of two;
  * out holds next_pow2(n) entries, natural order in and out. */
 int b200_fft_fr(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out);
+/* fft_fr.go:76-105 InplaceFFT: no padding; n not a power of two -> B200_ERR_NOT_POW2 (:81-83); n == 0 ->
+ * B200_ERR_BAD_INPUT (the reference divides by n: run-time panic).  vals may equal out. */
+int b200_inplace_fft_fr(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out);
 /* `batch` independent transforms of identical length n (contiguous). */
 int b200_fft_fr_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out);
 /* fft_g1.go:58-94 FFTG1: n must be a power of two <= MaxWidth. */
@@ -196,13 +203,19 @@ int b200_commit_partial_dev(b200_ks* ks, const void* d_coeffs, size_t begin, siz
 /* setup.go:9-26 GenerateTestingSetup, G1 half: out[i] = secret^i * G (host buffer, device compute). */
 int b200_generate_testing_setup_g1(const uint64_t secret[4], size_t n, uint64_t* out);
 
-/* Number of kernels the last batch call on this handle launched (bench.py gpu_launches). */
+/* Number of kernels launched by the last FK20 / commit+FK20 call made on the CALLING THREAD (bench.py
+ * gpu_launches).  Kept per thread so that handles stay immutable; the fk argument is ignored. */
+uint64_t b200_last_launch_count(void);
 uint64_t b200_fk20_last_launch_count(const b200_fk* fk);
+/* Window width (bits) of fixed-base tables built from now on: 8 (default; 384 KiB per base), 10, 12 (1.3 / 4.1 MiB
+ * per base, fewer additions per look-up) or 4.  Also settable with the environment variable B200_FB_WINDOW. */
+int b200_set_fixed_base_window(int bits);
 
 /* Per-kernel-class device timing for bench.py's roofline: between begin and end every launch is
  * bracketed by CUDA events on its stream.  Classes: 0 Fr NTT, 1 G1 FFT butterfly stage,
- * 2 G1 scalar multiplication, 3 G1 fold/add, 4 conversions and copies.  Not thread safe. */
-#define B200_PROFILE_CLASSES 5
+ * 2 G1 scalar multiplication by programs / variable scalars, 3 G1 fold/add, 4 conversions and copies,
+ * 5 fixed-base table look-up sums (ToeplitzPart2, commitment terms), 6 bucket MSM. */
+#define B200_PROFILE_CLASSES 7
 int b200_profile_begin(void);
 int b200_profile_end(double ms_per_class[B200_PROFILE_CLASSES], uint64_t launches_per_class[B200_PROFILE_CLASSES]);
 

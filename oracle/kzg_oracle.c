@@ -481,6 +481,10 @@ static int g1_decompress(g1_t *p, const uint8_t in[48]) /* bls/bls_kilic.go:118 
     p->x = x;
     p->y = y;
     memcpy(p->z.l, FP_ONE, sizeof p->z.l);
+    /* kilic's FromCompressed also rejects points outside the prime-order subgroup: r * P must be infinity */
+    g1_t rp;
+    g1_mul_canon(&rp, p, FR_P);
+    if (!g1_is_inf(&rp)) return -3;
     return 0;
 }
 

@@ -216,3 +216,34 @@ def test_karatsuba_product_matches_integer_product_on_the_host(tmp_path):
                               stderr=subprocess.DEVNULL)
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
+
+
+def test_from_compressed_rejects_points_outside_the_subgroup(L):
+    """kilic's FromCompressed (behind bls/bls_kilic.go:118-121) rejects encodings of curve points that are not in
+    the prime-order subgroup.  The library tests membership with the endomorphism ([z^2] P == (beta x, -y)), the
+    oracle with r P == infinity: two independent routes that must agree on every candidate x."""
+    P_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    found_bad = 0
+    for x in range(1, 40):
+        rhs = (x * x * x + 4) % P_MOD
+        if pow(rhs, (P_MOD - 1) // 2, P_MOD) != 1:
+            continue                                     # not on the curve: both reject (checked below)
+        enc = np.frombuffer(bytes([0x80]) + x.to_bytes(48, "big")[1:], dtype=np.uint8).copy()
+        out = np.zeros(18, dtype=np.uint64)
+        rc = L.b200_g1_from_compressed(_p(out), _p(enc))
+        try:
+            cref.g1_decompress(enc[None, :])
+            oracle_ok = True
+        except ValueError:
+            oracle_ok = False
+        assert (rc == 0) == oracle_ok
+        found_bad += rc != 0
+    assert found_bad >= 5                                # the cofactor is ~2^126: small x never land in G1
+    # members are still accepted: the generator and a few multiples round-trip
+    pts = cref.g1_mul_gen([1, 2, 1337, R - 1])
+    enc = cref.g1_compress(pts)
+    assert np.array_equal(kzg.g1_to_compressed(kzg.g1_from_compressed(enc)), enc)
+    off = np.frombuffer(bytes([0x80]) + (3).to_bytes(48, "big")[1:], dtype=np.uint8).copy()
+    if L.b200_g1_from_compressed(_p(np.zeros(18, dtype=np.uint64)), _p(off)) != 0:
+        with pytest.raises(kzg.KZGError):
+            kzg.g1_from_compressed(off[None, :])
