@@ -593,10 +593,19 @@ extern "C" int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inve
 }
 
 // ------------------------------------------------------------------------------ LinCombG1
-// sum_i k[b][i] * pts[i] for each blob b: per-term scalar multiplication, then a fold tree.
-// d_k canonical ([batch][n]); result of blob b is left at work[b * n].
+// sum_i k[b][i] * pts[i] for each blob b; result of blob b is left at work[b * n].  d_k canonical or Montgomery
+// ([batch][n]).  Three routes: fixed-base window table (settings-owned bases), Pippenger bucket MSM (variable bases,
+// kernels_msm.cu), and for a handful of terms per-term windowed multiplication + fold tree.
+static const size_t kMsmMinTerms = 32;
 static int dev_lincomb(const G1J* d_pts, size_t pts_bstride, const Fr* d_k, int k_is_mont, G1J* work, size_t n,
                        size_t batch, cudaStream_t st, const G1A* fb_table = nullptr, int fb_w = 8) {
+    if (!fb_table && n >= kMsmMinTerms) {
+        DevBuf ws;
+        CKS(ws.alloc(msm_workspace_bytes(n), st));
+        for (size_t b = 0; b < batch; b++)
+            launch_g1_msm(d_pts + b * pts_bstride, d_k + b * n, k_is_mont, n, ws.p, work + b * n, st);
+        return check_launches();
+    }
     if (fb_table) launch_g1_mul_fixed_base(fb_table, fb_w, d_k, k_is_mont, work, n, n, batch, st);
     else launch_g1_mul_var(d_pts, pts_bstride, d_k, k_is_mont, work, n, n, batch, st);
     for (size_t cnt = n; cnt > 1;) {

@@ -130,6 +130,9 @@ void launch_g1_copy(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J*
 // kzg.go:57-61 / 103-109: work[off * 2k + i] = S[n - l - 1 - off - i l] for i < k - 1 (k = n / l);
 // the rest of work (pre-filled) stays infinity
 void launch_fk20_gather_x(const G1J* secret_g1, G1J* work, size_t n, size_t l, cudaStream_t st);
+// Pippenger bucket MSM over variable bases (kernels_msm.cu): *out = sum_i k[i] pts[i]; workspace of msm_workspace_bytes(n)
+size_t msm_workspace_bytes(size_t n);
+void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* workspace, G1J* out, cudaStream_t st);
 // self test: device field + group law against portable forms; returns mismatches
 void launch_selftest(size_t n, uint64_t seed, unsigned long long* d_mismatch, G1J* d_scratch /* 4 n points */, cudaStream_t st);
 void launch_selftest_programs(size_t n, const ScalarProgram* progs, const Fr* scalars_canon, unsigned long long* d_mismatch, cudaStream_t st);

@@ -1,0 +1,194 @@
+// kernels_msm.cu -- Pippenger bucket MSM for variable bases (bls.LinCombG1, bls/bls_kilic.go:132-150):
+// the kernels around the per-thread bodies of msm.cuh.  Integer-pipe bound like every G1 kernel; the design
+// goal is parallel slack: n = 4096 gives 8192 GLV terms x 13 windows, spread over (bucket, slice) threads so
+// that no thread adds more than a handful of points, with warp-shuffle trees for every partial-sum reduction.
+#include "kernels.h"
+#include "msm.cuh"
+
+namespace b200 {
+
+static inline unsigned grid_for(size_t total, unsigned block) { return (unsigned)((total + block - 1) / block); }
+
+// ---- warp-shuffle helpers: a Jacobian point is 36 words ---------------------------------------------------
+__device__ __forceinline__ G1J g1_shfl_xor(const G1J& p, unsigned lane_mask) {
+    G1J r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        r.x.l[i] = __shfl_xor_sync(0xffffffffu, p.x.l[i], lane_mask);
+        r.y.l[i] = __shfl_xor_sync(0xffffffffu, p.y.l[i], lane_mask);
+        r.z.l[i] = __shfl_xor_sync(0xffffffffu, p.z.l[i], lane_mask);
+    }
+    return r;
+}
+// butterfly sum over groups of `width` adjacent lanes (power of two): every lane ends with the group's sum
+__device__ __forceinline__ void g1_warp_sum(G1J& acc, unsigned width) {
+    for (unsigned off = width >> 1; off >= 1; off >>= 1) {
+        G1J other = g1_shfl_xor(acc, off);
+        g1_add_ni(&acc, &acc, &other);
+    }
+}
+
+// ---- step 1 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_msm_recode(MsmPlan p, const G1J* __restrict__ pts, const Fr* __restrict__ k, int k_is_mont,
+                                                    int16_t* digits, uint32_t* counts, Fp* bx, uint32_t* not_affine) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    Fr s = ld_vec(k + i);
+    if (k_is_mont) s = fe_from_mont(s);
+    G1J pt = ld_vec(pts + i);
+    msm_recode_point(p, i, pt, s, digits, counts, bx, not_affine);
+}
+
+// ---- step 2: exclusive prefix of counts[w][0..B] (entry 0, the zero digit, is never counted) --------------
+__global__ void __launch_bounds__(1024) k_msm_scan(MsmPlan p, const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t part[1024];
+    const unsigned w = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const unsigned len = p.B + 1, per = (len + T - 1) / T;
+    const uint32_t* c = counts + (size_t)w * len;
+    uint32_t* o = offsets + (size_t)w * len;
+    const unsigned lo = tid * per, hi = lo + per < len ? lo + per : len;
+    uint32_t s = 0;
+    for (unsigned j = lo; j < hi; j++) s += c[j];
+    part[tid] = s;
+    __syncthreads();
+    for (unsigned d = 1; d < T; d <<= 1) {            // Hillis-Steele inclusive scan of the per-thread totals
+        uint32_t v = tid >= d ? part[tid - d] : 0u;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = tid ? part[tid - 1] : 0u;
+    for (unsigned j = lo; j < hi; j++) { o[j] = run; run += c[j]; }
+}
+
+// ---- step 3 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_msm_scatter(MsmPlan p, const int16_t* __restrict__ digits, const uint32_t* __restrict__ offsets,
+                                                     uint32_t* cursors, uint32_t* sorted) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)p.W * p.T) return;
+    msm_scatter_term(p, (unsigned)(g / p.T), g % p.T, digits, offsets, cursors, sorted);
+}
+
+// ---- step 4: thread = (window, bucket, slice); the S slices of a bucket are adjacent lanes -----------------
+__global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan p, const G1J* __restrict__ pts, const Fp* __restrict__ bx,
+                                                           const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
+                                                           const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ not_affine,
+                                                           G1J* __restrict__ buckets) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nb = (size_t)p.W * p.B;
+    const size_t bucket = g / p.S;                 // w * B + (b - 1)
+    const unsigned slice = (unsigned)(g % p.S);
+    G1J acc = G1J::infinity();
+    if (bucket < nb) {
+        const unsigned w = (unsigned)(bucket / p.B), b = (unsigned)(bucket % p.B) + 1;
+        const size_t slot = (size_t)w * (p.B + 1) + b;
+        const uint32_t len = counts[slot], off = offsets[slot];
+        const uint32_t per = (len + p.S - 1) / p.S;
+        uint32_t begin = slice * per, end = begin + per;
+        if (begin > len) begin = len;
+        if (end > len) end = len;
+        msm_accumulate_slice(p, pts, bx, sorted + (size_t)w * p.T, off + begin, off + end, *not_affine == 0, &acc);
+    }
+    if (p.S > 1) g1_warp_sum(acc, p.S);            // whole warps reach this point (no early return above)
+    if (bucket < nb && slice == 0) st_vec(buckets + bucket, acc);
+}
+
+// ---- step 5: thread = (window, segment of L buckets) -----------------------------------------------------
+__global__ void __launch_bounds__(128, 4) k_msm_segments(MsmPlan p, const G1J* __restrict__ buckets, G1J* __restrict__ segs) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nseg = p.B / p.L;
+    if (g >= (size_t)p.W * nseg) return;
+    const unsigned w = (unsigned)(g / nseg), s = (unsigned)(g % nseg);
+    G1J out;
+    msm_reduce_segment(buckets + (size_t)w * p.B, s * p.L + 1, p.L, &out);
+    st_vec(segs + g, out);
+}
+
+// ---- step 6: one CTA per window: tree sum of the window's segments, then c w doublings --------------------
+__global__ void __launch_bounds__(128) k_msm_windows(MsmPlan p, const G1J* __restrict__ segs, G1J* __restrict__ wsums) {
+    __shared__ G1J part[4];
+    const unsigned w = blockIdx.x, tid = threadIdx.x, nseg = p.B / p.L;
+    G1J acc = G1J::infinity();
+    for (unsigned s = tid; s < nseg; s += blockDim.x) {
+        G1J v = ld_vec(segs + (size_t)w * nseg + s);
+        g1_add_ni(&acc, &acc, &v);
+    }
+    g1_warp_sum(acc, 32);
+    if ((tid & 31) == 0) part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        for (unsigned j = 1; j < blockDim.x / 32; j++) g1_add_ni(&acc, &acc, &part[j]);
+        for (unsigned d = 0; d < p.c * w; d++) {
+            if (acc.is_inf()) break;
+            g1_dbl_ni(&acc, &acc);
+        }
+        st_vec(wsums + w, acc);
+    }
+}
+
+// ---- step 7: sum of the W <= 33 weighted window sums ------------------------------------------------------
+__global__ void __launch_bounds__(32) k_msm_final(MsmPlan p, const G1J* __restrict__ wsums, G1J* __restrict__ out) {
+    const unsigned lane = threadIdx.x;
+    G1J acc = G1J::infinity();
+    for (unsigned w = lane; w < p.W; w += 32) {
+        G1J v = ld_vec(wsums + w);
+        g1_add_ni(&acc, &acc, &v);
+    }
+    g1_warp_sum(acc, 32);
+    if (lane == 0) st_vec(out, acc);
+}
+
+// ---- workspace layout -------------------------------------------------------------------------------------
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+struct MsmWorkspace {
+    int16_t* digits; uint32_t* counts; uint32_t* offsets; uint32_t* cursors; uint32_t* flag; uint32_t* sorted;
+    Fp* bx; G1J* buckets; G1J* segs; G1J* wsums;
+    size_t zero_bytes;      // counts + cursors + flag are contiguous at `counts` and cleared per call
+};
+static size_t msm_layout(const MsmPlan& p, char* base, MsmWorkspace* ws) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align256(bytes); return base ? base + at : (char*)nullptr; };
+    const size_t slots = (size_t)p.W * (p.B + 1);
+    char* counts = take(slots * 4);
+    char* cursors = take(slots * 4);
+    char* flag = take(4);
+    const size_t zero_end = o;
+    char* offsets = take(slots * 4);
+    char* digits = take((size_t)p.W * p.T * 2);
+    char* sorted = take((size_t)p.W * p.T * 4);
+    char* bx = take(p.n * sizeof(Fp));
+    char* buckets = take((size_t)p.W * p.B * sizeof(G1J));
+    char* segs = take((size_t)p.W * (p.B / p.L) * sizeof(G1J));
+    char* wsums = take((size_t)p.W * sizeof(G1J));
+    if (ws) {
+        ws->counts = (uint32_t*)counts; ws->cursors = (uint32_t*)cursors; ws->flag = (uint32_t*)flag; ws->offsets = (uint32_t*)offsets;
+        ws->digits = (int16_t*)digits; ws->sorted = (uint32_t*)sorted; ws->bx = (Fp*)bx; ws->buckets = (G1J*)buckets;
+        ws->segs = (G1J*)segs; ws->wsums = (G1J*)wsums; ws->zero_bytes = zero_end;
+    }
+    return o;
+}
+size_t msm_workspace_bytes(size_t n) {
+    if (n == 0) return 256;
+    MsmPlan p = msm_plan(n);
+    return msm_layout(p, nullptr, nullptr);
+}
+
+// out (one internal Jacobian point) = sum_i k[i] pts[i]
+void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* workspace, G1J* out, cudaStream_t st) {
+    ProfScope prof_scope(PROF_G1_MSM, st);
+    if (n == 0) { launch_g1_fill_infinity(out, 1, st); return; }
+    MsmPlan p = msm_plan(n);
+    MsmWorkspace ws;
+    msm_layout(p, (char*)workspace, &ws);
+    cudaMemsetAsync(ws.counts, 0, ws.zero_bytes, st);
+    k_msm_recode<<<grid_for(n, 128), 128, 0, st>>>(p, pts, k, k_is_mont, ws.digits, ws.counts, ws.bx, ws.flag);
+    k_msm_scan<<<p.W, 1024, 0, st>>>(p, ws.counts, ws.offsets);
+    k_msm_scatter<<<grid_for((size_t)p.W * p.T, 256), 256, 0, st>>>(p, ws.digits, ws.offsets, ws.cursors, ws.sorted);
+    k_msm_accumulate<<<grid_for((size_t)p.W * p.B * p.S, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
+    k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L), 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
+    k_msm_windows<<<p.W, 128, 0, st>>>(p, ws.segs, ws.wsums);
+    k_msm_final<<<1, 32, 0, st>>>(p, ws.wsums, out);
+    g_launch_count += 7;
+}
+
+}  // namespace b200

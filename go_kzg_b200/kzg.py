@@ -94,6 +94,7 @@ def lib():
     L.b200_fs_roots.argtypes = [vp, i32, vp]
     L.b200_fft_fr.argtypes = [vp, vp, sz, i32, vp]
     L.b200_fft_fr_batch.argtypes = [vp, vp, sz, sz, i32, vp]
+    L.b200_inplace_fft_fr.argtypes = [vp, vp, sz, i32, vp]
     L.b200_fft_g1.argtypes = [vp, vp, sz, i32, vp]
     L.b200_fft_g1_batch.argtypes = [vp, vp, sz, sz, i32, vp]
     L.b200_das_fft_extension.argtypes = [vp, vp, sz]
@@ -133,6 +134,8 @@ def lib():
     L.b200_generate_testing_setup_g1.argtypes = [vp, sz, vp]
     L.b200_fk20_last_launch_count.argtypes = [vp]
     L.b200_fk20_last_launch_count.restype = u64
+    L.b200_last_launch_count.restype = u64
+    L.b200_set_fixed_base_window.argtypes = [i32]
     L.b200_selftest_field.argtypes = [sz, u64, C.POINTER(u64)]
     L.b200_probe_fp_mul.argtypes = [sz, i32, C.POINTER(C.c_float)]
     L.b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(u64)]
@@ -263,6 +266,14 @@ class FFTSettings:
         npow = 1 if n == 0 else 1 << (n - 1).bit_length()
         out = np.zeros((npow, 4), dtype=np.uint64)
         _raise(lib().b200_fft_fr(self.h, _p(v), n, int(inv), _p(out)), errors=(TOO_LARGE, NOT_POW2), what="FFT")
+        return out
+
+    def inplace_fft(self, vals, inv: bool = False) -> np.ndarray:
+        """fft_fr.go:76-105 InplaceFFT: no padding; error when the length is not a power of two (:81-83) or too
+        large (:78-80); a zero length makes the reference divide by zero (panic)."""
+        v = _fr(vals)
+        out = np.zeros_like(v)
+        _raise(lib().b200_inplace_fft_fr(self.h, _p(v), v.shape[0], int(inv), _p(out)), errors=(TOO_LARGE, NOT_POW2), what="InplaceFFT")
         return out
 
     def fft_batch(self, vals, inv: bool = False) -> np.ndarray:

@@ -18,7 +18,7 @@ from go_kzg_b200.synth import random_fr_limbs   # noqa: E402
 
 L = kzg.lib()
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-CLASSES = ["fr_ntt", "g1_fft_stage", "g1_mul", "g1_fold", "misc"]
+CLASSES = ["fr_ntt", "g1_fft_stage", "g1_mul", "g1_fold", "misc", "g1_lookup", "g1_msm"]
 
 
 def timed(fn, reps=3):
@@ -27,8 +27,8 @@ def timed(fn, reps=3):
     for _ in range(reps):
         L.b200_profile_begin()
         fn()
-        ms = (C.c_double * 5)()
-        n = (C.c_uint64 * 5)()
+        ms = (C.c_double * len(CLASSES))()
+        n = (C.c_uint64 * len(CLASSES))()
         L.b200_profile_end(ms, n)
         cur = {k: ms[i] for i, k in enumerate(CLASSES)}
         cur["launches"] = int(sum(n))
@@ -89,10 +89,46 @@ def main():
     ks = kzg.KZGSettings(fs12, pts)
     co = np.stack([random_fr_limbs(4096, 100 + b) for b in range(256)])
     t = timed(lambda: ks.commit_to_poly_batch(co))
-    out.append(row("commit_to_poly n=4096 (fixed-base tables) batch=256", 256, 721_040, t, ["g1_mul", "g1_fold"]))
+    out.append(row("commit_to_poly n=4096 (fixed-base tables) batch=256", 256, 721_040, t, ["g1_lookup", "g1_fold"]))
     sc = random_fr_limbs(4096, 7)
     t = timed(lambda: kzg.lincomb_g1(pts, sc))
-    out.append(row("lincomb_g1 n=4096 generic (no tables), single", 1, 721_040, t, ["g1_mul", "g1_fold"]))
+    out.append(row("lincomb_g1 n=4096 generic (bucket MSM, affine points), single", 1, 721_040, t, ["g1_msm"]))
+    # Jacobian inputs (Z != 1): general additions in the buckets
+    gen = np.zeros((1, 18), dtype=np.uint64)
+    L.b200_g1_generator(gen.ctypes.data)
+    jac = kzg.g1_mul_many(np.repeat(gen, 4096, axis=0), random_fr_limbs(4096, 8))
+    t = timed(lambda: kzg.lincomb_g1(jac, sc))
+    out.append(row("lincomb_g1 n=4096 generic (bucket MSM, Jacobian points), single", 1, 721_040, t, ["g1_msm"]))
+    big_n = 1 << 16
+    big = np.concatenate([pts] * (big_n // 4096))
+    bsc = random_fr_limbs(big_n, 9)
+    t = timed(lambda: kzg.lincomb_g1(big, bsc), reps=2)
+    r_msm = row("lincomb_g1 n=65536 generic (bucket MSM), single", 1, big_n * 176 + 144, t, ["g1_msm"])
+    r_msm["terms_per_s"] = round(big_n / (r_msm["device_ms"] / 1e3), 1)
+    out.append(r_msm)
+    t = timed(lambda: kzg.g1_mul_many(big, bsc), reps=2)
+    r_var = row("g1_mul_many n=65536 (k_g1_mul_var: per-term windowed GLV multiplication)", 1, big_n * 320, t, ["g1_mul"])
+    r_var["terms_per_s"] = round(big_n / (r_var["device_ms"] / 1e3), 1)
+    out.append(r_var)
+    # one polynomial per call (the reference API): FK20Single / DAUsingFK20 latency at n = 4096
+    import time
+    first = pts
+    from go_kzg_b200.kzg import R_MOD
+    rest = kzg.g1_mul_many(np.repeat(gen, 4096, axis=0), kzg.fr_from_ints([pow(1337, i, R_MOD) for i in range(4096, 8192)]))
+    fs13 = kzg.FFTSettings(13)
+    fk = kzg.FK20SingleSettings(kzg.KZGSettings(fs13, np.concatenate([first, rest])), 8192)
+    poly = random_fr_limbs(4096, 11)
+    for name, fn in (("fk20_single n=4096, one polynomial per call", lambda: fk.fk20_single(poly)),
+                     ("da_using_fk20 n=4096, one polynomial per call", lambda: fk.da_using_fk20(poly))):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        wall = (time.perf_counter() - t0) / 3
+        t = timed(fn, reps=2)
+        r1 = row(name, 1, 1_900_544, t, ["fr_ntt", "g1_fft_stage", "g1_mul", "g1_fold", "g1_lookup", "misc"])
+        r1["wall_ms_per_call"] = round(wall * 1e3, 3)
+        out.append(r1)
     print(json.dumps(out, indent=1))
 
 
