@@ -21,6 +21,12 @@ from .kzg import (  # noqa: F401
     g1_to_compressed,
     g1_to_compressed_device,
     g1_from_compressed,
+    g1_from_compressed_device,
+    g1_marshal_text,
+    g1_unmarshal_text,
+    bit_reversal_permutation,
+    load_trusted_setup,
+    check_proof_single_g1,
     lincomb_g1,
     g1_mul_many,
     generate_testing_setup_g1,

@@ -257,10 +257,13 @@ extern "C" int b200_fft_settings_new(uint8_t max_scale, b200_fs** out) {
         CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Fr), cudaMemcpyHostToDevice));
         return B200_OK;
     };
+    // cudaMemcpy from pageable memory may return before the DMA has landed; the calls that use these tables run on
+    // non-blocking streams with no implicit ordering against it, hence the device-wide synchronisation below
     int rc = up(&d.expanded, fs->h_expanded);
     if (!rc) rc = up(&d.reverse, rev);
     if (!rc) rc = up(&d.tw_fwd, twf);
     if (!rc) rc = up(&d.tw_inv, twi);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { g_cuda_err = "sync after the domain tables"; rc = B200_ERR_CUDA; }
     if (rc) { b200_fft_settings_free(fs); return rc; }
     *out = fs;
     return B200_OK;
@@ -294,6 +297,7 @@ static int fs_programs(b200_fs* fs, int inverse, int mode, const ScalarProgram**
         ScalarProgram* d = nullptr;
         CK(cudaMalloc(&d, half * sizeof(ScalarProgram)));
         CK(cudaMemcpy(d, h.data(), half * sizeof(ScalarProgram), cudaMemcpyHostToDevice));
+        CK(cudaDeviceSynchronize());   // the copy must have landed before a non-blocking stream reads the table
         fs->progs[inverse][mode] = d;
     }
     *out = fs->progs[inverse][mode];
@@ -472,6 +476,7 @@ static int fs_shift_tables(b200_fs* fs, const Fr** inv_pows, const Fr** pows) {
             CK(cudaMalloc(&fs->d_shift[which], W * sizeof(Fr)));
             CK(cudaMemcpy(fs->d_shift[which], t.data(), W * sizeof(Fr), cudaMemcpyHostToDevice));
         }
+        CK(cudaDeviceSynchronize());   // as in fs_programs
     }
     *inv_pows = fs->d_shift[0]; *pows = fs->d_shift[1];
     return B200_OK;
@@ -559,7 +564,8 @@ static int dev_g1_fft_stages(b200_fs* fs, G1J* data, unsigned logn, size_t batch
     return check_launches();
 }
 
-extern "C" int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out) {
+// FFTG1 of `batch` host vectors; only the first out_count <= n outputs of every transform are returned
+static int host_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out, size_t out_count) {
     if (n > fs->max_width) return B200_ERR_TOO_LARGE;     // fft_g1.go:60-62
     if (n == 0) return B200_ERR_BAD_INPUT;                // bls.IsPowerOfTwo(0) holds, then fft_g1.go:78,88 divides by n: panic
     if (!is_pow2(n)) return B200_ERR_NOT_POW2;            // fft_g1.go:63-65
@@ -582,14 +588,22 @@ extern "C" int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, si
         CK(cudaStreamSynchronize(st));   // sp lives on this stack frame
         launch_g1_mul_programs(buf.as<G1J>(), n, batch, 1, n, prog.as<ScalarProgram>(), 0, 0, logn, st);
     }
+    // natural-order output i sits at bit-reversed position rev(i) after the decimation-in-frequency stages
     launch_g1_to_abi(buf.as<G1J>(), raw.as<uint64_t>(), n, batch, 1, n, 1, logn, st);
     CKS(check_launches());
-    CK(cudaMemcpyAsync(out, raw.p, batch * n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpy2DAsync(out, out_count * 144, raw.p, n * 144, out_count * 144, batch, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return B200_OK;
 }
+extern "C" int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out) {
+    return host_fft_g1(fs, vals, n, batch, inverse, out, n);
+}
 extern "C" int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out) {
-    return b200_fft_g1_batch(fs, vals, n, 1, inverse, out);
+    return host_fft_g1(fs, vals, n, 1, inverse, out, n);
+}
+// fk20_single.go:80-87 ToeplitzPart3: inverse FFTG1, first half of the result (n2 / 2 points)
+extern "C" int b200_toeplitz_part3(b200_fs* fs, const uint64_t* h_ext_fft, size_t n2, uint64_t* out) {
+    return host_fft_g1(fs, h_ext_fft, n2, 1, 1, out, n2 / 2);
 }
 
 // ------------------------------------------------------------------------------ LinCombG1
@@ -649,6 +663,105 @@ extern "C" int b200_g1_mul_many(const uint64_t* points, const uint64_t* scalars,
     launch_g1_to_abi(pts.as<G1J>(), raw.as<uint64_t>(), n, 1, 1, n, 0, 0, st);
     CKS(check_launches());
     CK(cudaMemcpyAsync(out, raw.p, n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// fk20_single.go:59-77 ToeplitzPart2 with caller-held points: hExtFFT[i] = FFT(toeplitzCoeffs)[i] * xExtFFT[i].
+// (The FK20 entry points run a fused form over the settings' resident xExtFFT; this is the stand-alone method.)
+extern "C" int b200_toeplitz_part2(b200_fs* fs, const uint64_t* toeplitz_coeffs, size_t n_coeffs, const uint64_t* x_ext_fft, size_t n_points,
+                                   uint64_t* h_ext_fft) {
+    if (n_coeffs != n_points) return B200_ERR_LEN_MISMATCH;          // fk20_single.go:60-62 (panic)
+    if (n_coeffs > fs->max_width) return B200_ERR_TOO_LARGE;         // FFT error -> panic (:63-66)
+    const size_t np = next_pow2(n_coeffs);
+    if (np != n_points) return B200_ERR_LEN_MISMATCH;                // FFT pads (fft_fr.go:60); xExtFFT[i] would run out of range
+    CK(cudaSetDevice(fs->device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    const unsigned logn = log2u(np);
+    DevBuf raw, c, pts;
+    CKS(raw.alloc(np * 144, st)); CKS(c.alloc(np * sizeof(Fr), st)); CKS(pts.alloc(np * sizeof(G1J), st));
+    CK(cudaMemcpyAsync(raw.p, toeplitz_coeffs, np * 32, cudaMemcpyHostToDevice, st));
+    launch_fr_to_mont(raw.as<uint64_t>(), c.as<Fr>(), np, st);
+    CKS(dev_fr_fft(fs, c.as<Fr>(), c.as<Fr>(), logn, 1, false, st));
+    CK(cudaMemcpyAsync(raw.p, x_ext_fft, np * 144, cudaMemcpyHostToDevice, st));
+    launch_g1_from_abi(raw.as<uint64_t>(), pts.as<G1J>(), np, st);
+    launch_g1_mul_var(pts.as<G1J>(), 1, c.as<Fr>(), 1, pts.as<G1J>(), 1, 1, np, st);   // per-lane scalars
+    launch_g1_to_abi(pts.as<G1J>(), raw.as<uint64_t>(), np, 1, 1, np, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(h_ext_fft, raw.p, np * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// bls/bls_kilic.go:118-121 FromCompressedG1 over an array, on the device (square root + subgroup check per point).
+// ok (may be NULL) receives 1 per accepted encoding; any rejected encoding makes the call return B200_ERR_BAD_INPUT
+// (the reference returns an error for that element), with all-zero output for the rejected points.
+extern "C" int b200_g1_from_compressed_batch(const uint8_t* in48, size_t n, uint64_t* out, uint8_t* ok) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    if (n == 0) return B200_OK;
+    CK(cudaSetDevice(g_device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    DevBuf in, res, stt;
+    CKS(in.alloc(n * 48, st)); CKS(res.alloc(n * 144, st)); CKS(stt.alloc(n * 4, st));
+    CK(cudaMemcpyAsync(in.p, in48, n * 48, cudaMemcpyHostToDevice, st));
+    launch_g1_decompress(in.as<uint8_t>(), res.as<uint64_t>(), stt.as<uint32_t>(), n, st);
+    CKS(check_launches());
+    std::vector<uint32_t> h(n);
+    CK(cudaMemcpyAsync(out, res.p, n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.data(), stt.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int rc = B200_OK;
+    for (size_t i = 0; i < n; i++) {
+        if (ok) ok[i] = h[i] == 0;
+        if (h[i]) rc = B200_ERR_BAD_INPUT;
+    }
+    return rc;
+}
+
+// bls/globals.go:106-153 EvaluatePolyInEvaluationForm for a batch: polys[b] = n evaluations on the settings' domain of
+// order n (natural order, or reverse bit order like eth's DomainFr), xs[b] the evaluation point; y[b] canonical.
+// A point inside the domain gives 0, as in the reference (BatchInvModFr leaves the zero denominator, x^n - 1 = 0).
+extern "C" int b200_evaluate_poly_in_evaluation_form_batch(b200_fs* fs, const uint64_t* polys, const uint64_t* xs, size_t n, size_t batch,
+                                                           int reverse_bit_order, uint64_t* y) {
+    if (n > fs->max_width || n == 0 || !is_pow2(n)) return B200_ERR_LEN_MISMATCH;   // bls/globals.go:107-109 (panic): no such roots
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fs->device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    const unsigned logn = log2u(n);
+    DevBuf f, dx, inv, part, ym, yc;
+    CKS(f.alloc(batch * n * 32, st)); CKS(dx.alloc(batch * 32, st)); CKS(inv.alloc(batch * n * 32, st));
+    CKS(part.alloc(batch * (n / 16 + 1) * 32, st)); CKS(ym.alloc(batch * 32, st)); CKS(yc.alloc(batch * 32, st));
+    CK(cudaMemcpyAsync(f.p, polys, batch * n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dx.p, xs, batch * 32, cudaMemcpyHostToDevice, st));
+    launch_eval_form_quotient(fs->dom, f.as<uint64_t>(), dx.as<uint64_t>(), logn, batch, reverse_bit_order ? 1 : 0, fr_inv_of_u64(n), inv.as<Fr>(),
+                              part.as<Fr>(), ym.as<Fr>(), yc.as<uint64_t>(), nullptr, nullptr, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(y, yc.p, batch * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// kzg_single_proofs.go:57-75 CheckProofSingle, G1 side for a batch: out[i] = commitment[i] - y[i] G (:63-67).
+// The caller finishes with its pairing backend: e(out[i], [1]_2) == e(proof[i], [s - x[i]]_2).
+extern "C" int b200_check_proof_single_g1_batch(const uint64_t* commitments, const uint64_t* ys, size_t batch, uint64_t* out) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(g_device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    G1J gen = g1_generator();
+    DevBuf raw, c, k, dg, yg;
+    CKS(raw.alloc(batch * 144, st)); CKS(c.alloc(batch * sizeof(G1J), st)); CKS(k.alloc(batch * 32, st));
+    CKS(dg.alloc(sizeof(G1J), st)); CKS(yg.alloc(batch * sizeof(G1J), st));
+    CK(cudaMemcpyAsync(raw.p, commitments, batch * 144, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k.p, ys, batch * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dg.p, &gen, sizeof gen, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                                   // gen lives on this stack frame
+    launch_g1_from_abi(raw.as<uint64_t>(), c.as<G1J>(), batch, st);
+    launch_g1_mul_var(dg.as<G1J>(), 0, k.as<Fr>(), 0, yg.as<G1J>(), 1, 1, batch, st);   // y[i] G: one shared base
+    launch_g1_sub_arrays(c.as<G1J>(), yg.as<G1J>(), 1, batch, st);
+    launch_g1_to_abi(c.as<G1J>(), raw.as<uint64_t>(), batch, 1, 1, batch, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, batch * 144, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return B200_OK;
 }
@@ -796,6 +909,44 @@ extern "C" int b200_commit_to_poly_batch(b200_ks* ks, const uint64_t* coeffs, si
 }
 extern "C" int b200_commit_to_poly(b200_ks* ks, const uint64_t* coeffs, size_t n, uint64_t* out) {
     return b200_commit_to_poly_batch(ks, coeffs, n, 1, out);
+}
+
+// kzg_multi_proofs.go:47-88 CheckProofMulti for a batch of samples, everything but the G2 arithmetic and the pairing:
+// interpolation of the n = len(ys) values on the coset x <w_n> (inverse FFT, coefficient i divided by x^i, :50-70),
+// [interpolation_polynomial(s)]_1 as an MSM over SecretG1[:n] (:78) and out_g1[b] = commitment[b] - that (:80-81);
+// x_pow_n[b] = x[b]^n for the caller's [s^n - x^n]_2 (:71-76).  The caller finishes with
+// e(out_g1[b], [1]_2) == e(proof[b], [s^n - x^n]_2).
+extern "C" int b200_check_proof_multi_g1_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* xs, const uint64_t* ys, size_t n,
+                                               size_t batch, uint64_t* out_g1, uint64_t* x_pow_n) {
+    b200_fs* fs = ks->fs;
+    if (n > fs->max_width) return B200_ERR_TOO_LARGE;        // FFT error -> panic("ys is bad") :52-54
+    if (n == 0 || !is_pow2(n)) return B200_ERR_NOT_POW2;     // "The ys must have a power of 2 length" (:46)
+    if (n >= ks->n_g1) return B200_ERR_LEN_MISMATCH;         // SecretG2[len(ys)] / SecretG1[:n] out of range (:76,78)
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fs->device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    const unsigned logn = log2u(n);
+    DevBuf raw, v, dx, xn, c, work;
+    CKS(raw.alloc(batch * (n * 32 > 144 ? n * 32 : 144), st)); CKS(v.alloc(batch * n * sizeof(Fr), st)); CKS(dx.alloc(batch * 32, st));
+    CKS(xn.alloc(batch * 32, st)); CKS(c.alloc(batch * sizeof(G1J), st)); CKS(work.alloc(batch * n * sizeof(G1J), st));
+    CK(cudaMemcpyAsync(raw.p, ys, batch * n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dx.p, xs, batch * 32, cudaMemcpyHostToDevice, st));
+    launch_fr_to_mont(raw.as<uint64_t>(), v.as<Fr>(), batch * n, st);
+    CKS(dev_fr_fft(fs, v.as<Fr>(), v.as<Fr>(), logn, batch, true, st));
+    launch_unscale_coset(v.as<Fr>(), dx.as<uint64_t>(), logn, batch, xn.as<uint64_t>(), st);      // canonical coefficients now
+    const G1A* fb = nullptr;
+    int fbw = 8;
+    if (batch * n >= 4096) CKS(ks_fixed_base(ks, n, &fb, &fbw, st));
+    CKS(dev_lincomb(ks->d_secret_g1, 0, v.as<Fr>(), 0, work.as<G1J>(), n, batch, st, fb, fbw));
+    CK(cudaMemcpyAsync(raw.p, commitments, batch * 144, cudaMemcpyHostToDevice, st));
+    launch_g1_from_abi(raw.as<uint64_t>(), c.as<G1J>(), batch, st);
+    launch_g1_sub_arrays(c.as<G1J>(), work.as<G1J>(), n, batch, st);                                  // blob b's sum sits at work[b n]
+    launch_g1_to_abi(c.as<G1J>(), raw.as<uint64_t>(), batch, 1, 1, batch, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(out_g1, raw.p, batch * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(x_pow_n, xn.p, batch * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
 }
 
 // ------------------------------------------------------------------------------ FK20
@@ -1321,7 +1472,7 @@ extern "C" int b200_compute_kzg_proof_batch(b200_ks* ks, const uint64_t* polys, 
     CK(cudaMemcpyAsync(dz.p, z, batch * 32, cudaMemcpyHostToDevice, st));
     launch_fr_check_canonical(f.as<uint64_t>(), n, batch, flags.as<uint32_t>(), st);
     launch_fr_check_canonical(dz.as<uint64_t>(), 1, batch, flags.as<uint32_t>(), st);
-    launch_eval_form_quotient(fs->dom, f.as<uint64_t>(), dz.as<uint64_t>(), logn, batch, fr_inv_of_u64(n), inv.as<Fr>(), part.as<Fr>(),
+    launch_eval_form_quotient(fs->dom, f.as<uint64_t>(), dz.as<uint64_t>(), logn, batch, 1, fr_inv_of_u64(n), inv.as<Fr>(), part.as<Fr>(),
                               ym.as<Fr>(), yc.as<uint64_t>(), q.as<uint64_t>(), flags.as<uint32_t>(), st);
     const G1A* fb = nullptr;
     int fbw = 8;

@@ -77,10 +77,13 @@ void launch_fr_powers(const Fr* d_sq, Fr* out_canon, size_t n, cudaStream_t st);
 // an element of blob b is >= r  (eth/helpers.go:264-273 BlobToPolynomial)
 void launch_fr_check_canonical(const uint64_t* vals, size_t n, size_t batch, uint32_t* ok, cudaStream_t st);
 // eth/helpers.go:179-203 ComputeKZGProof, field side: y[b] = f_b(z_b) (bls/globals.go:106-153) and the quotient
-// q[b][i] = (f[b][i] - y[b]) / (D[i] - z[b]) on the bit-reversed domain of size 2^logn >= 16; ok[b] cleared if z[b] is in the domain
-void launch_eval_form_quotient(const FrDomain& dom, const uint64_t* f_canon, const uint64_t* z_canon, unsigned logn, size_t batch,
+// q[b][i] = (f[b][i] - y[b]) / (D[i] - z[b]) on the domain of size 2^logn in reverse bit order (bitrev != 0: eth DomainFr) or
+// natural order; ok[b] (may be null) cleared if z[b] is in the domain; q_canon == null: evaluation only
+void launch_eval_form_quotient(const FrDomain& dom, const uint64_t* f_canon, const uint64_t* z_canon, unsigned logn, size_t batch, int bitrev,
                                const Fr& inv_n, Fr* inv_den, Fr* partial, Fr* y_mont, uint64_t* y_canon_or_null, uint64_t* q_canon,
                                uint32_t* ok, cudaStream_t st);
+// kzg_multi_proofs.go:57-71: coeffs[b][i] (Montgomery in, canonical out) /= x[b]^i; x_pow_n[b] = x[b]^(2^logn) (canonical)
+void launch_unscale_coset(Fr* coeffs, const uint64_t* x_canon, unsigned logn, size_t batch, uint64_t* x_pow_n_canon, cudaStream_t st);
 // pointwise helpers on Montgomery arrays
 void launch_fr_mul_arrays(Fr* dst, const Fr* a, const Fr* b, size_t n, cudaStream_t st);   // dst = a * b
 void launch_fr_mul_even_odd(Fr* v, const Fr& even, const Fr& odd, size_t total, cudaStream_t st);   // v[i] *= i even ? even : odd
@@ -124,6 +127,11 @@ void launch_g1_fold(G1J* data, size_t bstride, size_t half, size_t cnt, size_t b
 // dst[b*dst_bstride + i*dst_estride] += src[b*src_bstride + i*src_estride]
 void launch_g1_add_arrays(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J* src, size_t src_estride,
                           size_t src_bstride, size_t n, size_t batch, cudaStream_t st);
+// dst[i] -= src[i * src_stride]   (contiguous dst; src_stride in points)
+void launch_g1_sub_arrays(G1J* dst, const G1J* src, size_t src_stride, size_t n, cudaStream_t st);
+// bls/bls_kilic.go:118-121 FromCompressedG1 over an array: flags, x < p, curve equation, prime-order subgroup;
+// out[i] = ABI point (canonical, Z = 1; all zero for infinity and for rejected encodings), status[i] = 0 ok / 1 / 2 / 3
+void launch_g1_decompress(const uint8_t* in48, uint64_t* out_abi, uint32_t* status, size_t n, cudaStream_t st);
 // dst[b*dst_bstride + i*dst_estride] = src[b*src_bstride + idx(i)*src_estride]
 void launch_g1_copy(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J* src, size_t src_estride,
                     size_t src_bstride, size_t n, size_t batch, int bitrev, unsigned logn, cudaStream_t st);

@@ -675,28 +675,32 @@ void launch_fr_check_canonical(const uint64_t* vals, size_t n, size_t batch, uin
 // Pass 1 inverts the n denominators (Montgomery's trick, EVAL_CHUNK per lane) and leaves a partial sum
 // per lane; pass 2 folds the partial sums into y; pass 3 forms the quotient (canonical, ready for the MSM).
 #define EVAL_CHUNK 16
-__device__ __forceinline__ size_t eval_domain_index(size_t i, unsigned logn, size_t stride) { return (size_t)(__brev((uint32_t)i) >> (32 - logn)) * stride; }
+// domain element of position i: reverse bit order (eth DomainFr, eth/globals.go:60-67) or natural order
+__device__ __forceinline__ size_t eval_domain_index(size_t i, unsigned logn, size_t stride, int bitrev) {
+    return (bitrev ? (size_t)(logn ? __brev((uint32_t)i) >> (32 - logn) : 0u) : i) * stride;
+}
+// ch = min(n, EVAL_CHUNK) elements per lane
 __global__ void __launch_bounds__(128) k_eval_form_pass1(const Fr* __restrict__ f_canon, const Fr* __restrict__ z_canon,
                                                          const Fr* __restrict__ expanded, size_t stride, size_t n, unsigned logn,
-                                                         size_t batch, Fr* inv_den, Fr* partial, uint32_t* ok) {
-    const size_t chunks = n / EVAL_CHUNK;
+                                                         size_t batch, int bitrev, int ch, Fr* inv_den, Fr* partial, uint32_t* ok) {
+    const size_t chunks = n / ch;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= chunks * batch) return;
-    size_t b = t / chunks, lo = (t % chunks) * EVAL_CHUNK;
+    size_t b = t / chunks, lo = (t % chunks) * ch;
     Fr z = fe_to_mont(ld_vec(z_canon + b));
     Fr pre[EVAL_CHUNK];
     Fr acc = Fr::one();
     bool hit = false;
-    for (int k = 0; k < EVAL_CHUNK; k++) {
-        Fr d = fe_sub(ld_vec(expanded + eval_domain_index(lo + k, logn, stride)), z);    // D_i - z
+    for (int k = 0; k < ch; k++) {
+        Fr d = fe_sub(ld_vec(expanded + eval_domain_index(lo + k, logn, stride, bitrev)), z);    // D_i - z
         pre[k] = acc;
         if (d.is_zero()) hit = true; else acc = fe_mul(acc, d);
     }
-    if (hit) atomicAnd(ok + b, 0u);                                                       // "invalid z challenge"
+    if (hit && ok) atomicAnd(ok + b, 0u);                                                 // "invalid z challenge"
     acc = fe_inv(acc);
     Fr sum = Fr::zero();
-    for (int k = EVAL_CHUNK - 1; k >= 0; k--) {
-        Fr dom = ld_vec(expanded + eval_domain_index(lo + k, logn, stride));
+    for (int k = ch - 1; k >= 0; k--) {
+        Fr dom = ld_vec(expanded + eval_domain_index(lo + k, logn, stride, bitrev));
         Fr d = fe_sub(dom, z);
         Fr inv = Fr::zero();
         if (!d.is_zero()) { inv = fe_mul(acc, pre[k]); acc = fe_mul(acc, d); }
@@ -735,18 +739,46 @@ __global__ void k_eval_form_pass3(const Fr* __restrict__ f_canon, const Fr* __re
     Fr q = fe_mul(fe_sub(fi, ld_vec(y_mont + t / n)), ld_vec(inv_den + t));
     st_vec(q_canon + t, fe_from_mont(q));
 }
-void launch_eval_form_quotient(const FrDomain& dom, const uint64_t* f_canon, const uint64_t* z_canon, unsigned logn, size_t batch,
+void launch_eval_form_quotient(const FrDomain& dom, const uint64_t* f_canon, const uint64_t* z_canon, unsigned logn, size_t batch, int bitrev,
                                const Fr& inv_n, Fr* inv_den /* batch n */, Fr* partial /* batch n / 16 */, Fr* y_mont /* batch */,
-                               uint64_t* y_canon_or_null, uint64_t* q_canon /* batch n */, uint32_t* ok, cudaStream_t st) {
+                               uint64_t* y_canon_or_null, uint64_t* q_canon /* batch n, or null: evaluation only */, uint32_t* ok, cudaStream_t st) {
     ProfScope prof_scope(PROF_MISC, st);
-    const size_t n = (size_t)1 << logn, chunks = n / EVAL_CHUNK;
+    const size_t n = (size_t)1 << logn;
+    const int ch = n < EVAL_CHUNK ? (int)n : EVAL_CHUNK;
+    const size_t chunks = n / ch;
     if (!batch) return;
     const Fr* f = reinterpret_cast<const Fr*>(f_canon);
     const Fr* z = reinterpret_cast<const Fr*>(z_canon);
-    k_eval_form_pass1<<<grid_for(chunks * batch, 128), 128, 0, st>>>(f, z, dom.expanded, dom.max_width >> logn, n, logn, batch, inv_den, partial, ok);
+    k_eval_form_pass1<<<grid_for(chunks * batch, 128), 128, 0, st>>>(f, z, dom.expanded, dom.max_width >> logn, n, logn, batch, bitrev, ch, inv_den, partial, ok);
     k_eval_form_pass2<<<(unsigned)batch, 256, 0, st>>>(partial, chunks, z, logn, inv_n, y_mont, reinterpret_cast<Fr*>(y_canon_or_null));
-    k_eval_form_pass3<<<grid_for(n * batch, 256), 256, 0, st>>>(f, inv_den, y_mont, n, batch, reinterpret_cast<Fr*>(q_canon));
-    g_launch_count += 3;
+    g_launch_count += 2;
+    if (q_canon) { k_eval_form_pass3<<<grid_for(n * batch, 256), 256, 0, st>>>(f, inv_den, y_mont, n, batch, reinterpret_cast<Fr*>(q_canon)); g_launch_count++; }
+}
+
+// kzg_multi_proofs.go:57-71 for a batch of samples: coefficient i of sample b is divided by x_b^i (InvModFr(0) = 0, so x = 0
+// clears every coefficient but the first, as in the reference), and x_b^n is returned for the caller's [x^n]_2.
+// coeffs: [batch][n] Montgomery in, canonical out; x canonical; n = 2^logn.
+__global__ void k_unscale_coset(Fr* coeffs, const Fr* __restrict__ x_canon, size_t n, unsigned logn, size_t batch, Fr* x_pow_n_canon) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    const size_t b = t / n, i = t % n;
+    const Fr x = fe_to_mont(ld_vec(x_canon + b));
+    const Fr xi = fe_inv(x);                                   // 0 -> 0
+    Fr p = Fr::one(), sq = xi;                                 // xi^i by square and multiply
+    for (size_t e = i; e; e >>= 1) { if (e & 1) p = fe_mul(p, sq); sq = fe_mul(sq, sq); }
+    st_vec(coeffs + t, fe_from_mont(fe_mul(ld_vec(coeffs + t), p)));
+    if (i == 0) {
+        Fr xn = x;
+        for (unsigned k = 0; k < logn; k++) xn = fe_mul(xn, xn);
+        st_vec(x_pow_n_canon + b, fe_from_mont(xn));
+    }
+}
+void launch_unscale_coset(Fr* coeffs, const uint64_t* x_canon, unsigned logn, size_t batch, uint64_t* x_pow_n_canon, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    const size_t n = (size_t)1 << logn;
+    if (!batch) return;
+    k_unscale_coset<<<grid_for(n * batch, 128), 128, 0, st>>>(coeffs, reinterpret_cast<const Fr*>(x_canon), n, logn, batch, reinterpret_cast<Fr*>(x_pow_n_canon));
+    g_launch_count++;
 }
 
 }  // namespace b200

@@ -152,6 +152,74 @@ void launch_g1_compress(const G1J* in, uint8_t* out48, size_t n, size_t batch, s
     g_launch_count++;
 }
 
+// ------------------------------------------------------------------------------ decompression
+// FromCompressedG1 (bls/bls_kilic.go:118-121 -> kilic FromCompressed) for whole arrays: setup files hold thousands to
+// millions of 48-byte points and every one costs a square root (a 381-bit exponentiation) and a subgroup check.
+// One point per thread: flags, x < p, y = (x^3 + 4)^((p + 1) / 4) with y^2 verified, sign from bit 5, then the
+// subgroup test [z^2] P == (beta x, -y) (g1.cuh: g1_in_subgroup; a 128-bit multiplication).
+__global__ void __launch_bounds__(128) k_g1_decompress(const Comp48* __restrict__ in, G1J* __restrict__ out_abi, uint32_t* __restrict__ status, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Comp48 c = in[i];
+    const uint32_t b0 = c.w[0] & 0xffu;
+    G1J res = G1J::infinity();                                        // all-zero limbs: infinity in the ABI encoding too
+    uint32_t rc = 0;
+    if (!(b0 & 0x80u)) rc = 1;
+    else if (b0 & 0x40u) {
+        uint32_t rest = c.w[0] & 0xffffff3fu;                         // every other bit of an infinity encoding must be clear
+#pragma unroll
+        for (int j = 1; j < 12; j++) rest |= c.w[j];
+        if (rest) rc = 1;
+    } else {
+        Fp x;
+#pragma unroll
+        for (int j = 0; j < 12; j++) x.l[11 - j] = __byte_perm(c.w[j], 0u, 0x0123);
+        x.l[11] &= 0x1fffffffu;
+        uint32_t cf = 0, t;
+        t = sub_cc(x.l[0], FpParams::mod(0), cf);
+#pragma unroll
+        for (int j = 1; j < 12; j++) t = subc_cc(x.l[j], FpParams::mod(j), cf);
+        (void)t;
+        if (subc(0u, 0u, cf) == 0) rc = 1;                            // no borrow: x >= p
+        else {
+            const Fp xm = fp_mul(x, Fp::r2());
+            const Fp rhs = fe_add(fp_mul(fp_sqr(xm), xm), fp_const_four());
+            constexpr uint32_t e[12] = B200_FP_SQRT_EXP;               // (p + 1) / 4, 379 bits
+            Fp y = rhs;
+            int top = 383;
+            while (top > 0 && !((e[top >> 5] >> (top & 31)) & 1u)) top--;
+            for (int bit = top - 1; bit >= 0; bit--) {
+                y = fp_sqr(y);
+                if ((e[bit >> 5] >> (bit & 31)) & 1u) y = fp_mul(y, rhs);
+            }
+            if (fp_sqr(y) != rhs) rc = 2;
+            else {
+                Fp raw_one = Fp::zero(); raw_one.l[0] = 1;
+                Fp yc = fp_mul(y, raw_one);
+                if (fp_canon_gt_half_dev(yc) != ((b0 & 0x20u) != 0)) { y = fe_neg(y); yc = fp_mul(y, raw_one); }
+                G1A pa; pa.x = xm; pa.y = y;
+                G1J acc; acc.x = xm; acc.y = y; acc.z = Fp::one();
+                constexpr uint32_t z2[4] = B200_GLV_Z2;               // top bit is bit 127
+                for (int bit = 126; bit >= 0; bit--) {
+                    g1_dbl_ni(&acc, &acc);
+                    if ((z2[bit >> 5] >> (bit & 31)) & 1u) g1_add_mixed_ni(&acc, &acc, &pa);
+                }
+                G1J pj; pj.x = xm; pj.y = y; pj.z = Fp::one();
+                if (!g1_equal(acc, g1_endo(pj))) rc = 3;
+                else { res.x = x; res.y = yc; res.z = Fp::zero(); res.z.l[0] = 1; }
+            }
+        }
+    }
+    st_vec(out_abi + i, res);
+    status[i] = rc;
+}
+void launch_g1_decompress(const uint8_t* in48, uint64_t* out_abi, uint32_t* status, size_t n, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n) return;
+    k_g1_decompress<<<grid_for(n, 128), 128, 0, st>>>(reinterpret_cast<const Comp48*>(in48), reinterpret_cast<G1J*>(out_abi), status, n);
+    g_launch_count++;
+}
+
 // ------------------------------------------------------------------------------ FFT stage
 // thread <-> (butterfly q, blob b) with b fastest: when batch is a multiple of 32 every lane of a
 // warp runs the same twiddle program on a different blob, so the digit branches are uniform.
@@ -461,6 +529,21 @@ void launch_g1_add_arrays(G1J* dst, size_t dst_estride, size_t dst_bstride, cons
     ProfScope prof_scope(PROF_G1_FOLD, st);
     if (!n || !batch) return;
     k_g1_add_arrays<<<grid_for(n * batch, 128), 128, 0, st>>>(dst, dst_estride, dst_bstride, src, src_estride, src_bstride, n, batch);
+    g_launch_count++;
+}
+
+__global__ void __launch_bounds__(128) k_g1_sub_arrays(G1J* dst, const G1J* src, size_t src_stride, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1J x = ld_vec(dst + i), y = ld_vec(src + i * src_stride), r;
+    y.y = fe_neg(y.y);
+    g1_add_ni(&r, &x, &y);
+    st_vec(dst + i, r);
+}
+void launch_g1_sub_arrays(G1J* dst, const G1J* src, size_t src_stride, size_t n, cudaStream_t st) {
+    ProfScope prof_scope(PROF_G1_FOLD, st);
+    if (!n) return;
+    k_g1_sub_arrays<<<grid_for(n, 128), 128, 0, st>>>(dst, src, src_stride, n);
     g_launch_count++;
 }
 

@@ -4,6 +4,7 @@
 // that no thread adds more than a handful of points, with warp-shuffle trees for every partial-sum reduction.
 #include "kernels.h"
 #include "msm.cuh"
+#include "quad.cuh"
 
 namespace b200 {
 
@@ -69,12 +70,17 @@ __global__ void __launch_bounds__(256) k_msm_scatter(MsmPlan p, const int16_t* _
     msm_scatter_term(p, (unsigned)(g / p.T), g % p.T, digits, offsets, cursors, sorted);
 }
 
-// ---- step 4: thread = (window, bucket, slice); the S slices of a bucket are adjacent lanes -----------------
+// ---- step 4: (window, bucket, slice) units; the S slices of a bucket are adjacent -------------------------------
+// QUAD = false: one thread per unit (large problems: every lane has a list of its own, throughput bound).
+// QUAD = true:  one quad per unit (quad.cuh: an addition in 5 dependent products instead of 11 / 16) for problems that
+//               cannot fill the chip anyway, where the depth of the chain of additions is what is waited for.
+template <bool QUAD>
 __global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan p, const G1J* __restrict__ pts, const Fp* __restrict__ bx,
                                                            const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ not_affine,
                                                            G1J* __restrict__ buckets) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g = QUAD ? tid >> 2 : tid;
     const size_t nb = (size_t)p.W * p.B;
     const size_t bucket = g / p.S;                 // w * B + (b - 1)
     const unsigned slice = (unsigned)(g % p.S);
@@ -87,56 +93,104 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan p, const G1J*
         uint32_t begin = slice * per, end = begin + per;
         if (begin > len) begin = len;
         if (end > len) end = len;
-        msm_accumulate_slice(p, pts, bx, sorted + (size_t)w * p.T, off + begin, off + end, *not_affine == 0, &acc);
+        if (!QUAD) {
+            msm_accumulate_slice(p, pts, bx, sorted + (size_t)w * p.T, off + begin, off + end, *not_affine == 0, &acc);
+        } else {
+            const bool affine = *not_affine == 0;
+            const uint32_t* sw = sorted + (size_t)w * p.T;
+            for (uint32_t e = off + begin; e < off + end; e++) {
+                const uint32_t u = sw[e];
+                const size_t t = u & 0x7fffffffu;
+                const bool second = t >= p.n;
+                const size_t i = second ? t - p.n : t;
+                const bool neg = ((u >> 31) != 0) != second;
+                G1J q;
+                q.x = second ? ld_vec(bx + i) : ld_vec(&pts[i].x);
+                q.y = ld_vec(&pts[i].y);
+                if (neg) q.y = fe_neg(q.y);
+                if (affine) {
+                    G1A qa; qa.x = q.x; qa.y = q.y;
+                    quad_add_mixed(&acc, &acc, &qa);
+                } else {
+                    q.z = ld_vec(&pts[i].z);
+                    quad_add(&acc, &acc, &q);
+                }
+            }
+        }
     }
-    if (p.S > 1) g1_warp_sum(acc, p.S);            // whole warps reach this point (no early return above)
-    if (bucket < nb && slice == 0) st_vec(buckets + bucket, acc);
+    // the slices of a bucket: adjacent lanes (thread units) or adjacent quads (quad units); whole warps get here
+    if (!QUAD) {
+        if (p.S > 1) g1_warp_sum(acc, p.S);
+    } else {
+        for (unsigned off = (p.S * 4) >> 1; off >= 4; off >>= 1) {
+            G1J other = quad_shfl_xor(acc, off);
+            quad_add(&acc, &acc, &other);
+        }
+    }
+    if (bucket < nb && slice == 0 && (!QUAD || (threadIdx.x & 3u) == 0)) st_vec(buckets + bucket, acc);
 }
 
-// ---- step 5: thread = (window, segment of L buckets) -----------------------------------------------------
+// ---- step 5: quad = (window, segment of L buckets) -----------------------------------------------------------
 __global__ void __launch_bounds__(128, 4) k_msm_segments(MsmPlan p, const G1J* __restrict__ buckets, G1J* __restrict__ segs) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const unsigned nseg = p.B / p.L;
-    if (g >= (size_t)p.W * nseg) return;
+    if (g >= (size_t)p.W * nseg) return;             // whole quads leave together
     const unsigned w = (unsigned)(g / nseg), s = (unsigned)(g % nseg);
-    G1J out;
-    msm_reduce_segment(buckets + (size_t)w * p.B, s * p.L + 1, p.L, &out);
-    st_vec(segs + g, out);
+    const G1J* bkt = buckets + (size_t)w * p.B;
+    const unsigned b0 = s * p.L + 1;
+    G1J running = G1J::infinity(), acc = G1J::infinity();
+    for (int j = (int)p.L - 1; j >= 0; j--) {        // msm_reduce_segment with quad operations
+        G1J v = ld_vec(bkt + (b0 - 1 + j));
+        quad_add(&running, &running, &v);
+        quad_add(&acc, &acc, &running);
+    }
+    if (b0 > 1 && !running.is_inf()) {
+        G1J m;
+        quad_small_mul(&m, &running, b0 - 1);
+        quad_add(&acc, &acc, &m);
+    }
+    if ((threadIdx.x & 3u) == 0) st_vec(segs + g, acc);
 }
 
-// ---- step 6: one CTA per window: tree sum of the window's segments, then c w doublings --------------------
+// ---- step 6: one CTA (32 quads) per window: sum of the window's segments ----------------------------------------
 __global__ void __launch_bounds__(128) k_msm_windows(MsmPlan p, const G1J* __restrict__ segs, G1J* __restrict__ wsums) {
     __shared__ G1J part[4];
-    const unsigned w = blockIdx.x, tid = threadIdx.x, nseg = p.B / p.L;
+    const unsigned w = blockIdx.x, tid = threadIdx.x, quad = tid >> 2, nseg = p.B / p.L;
     G1J acc = G1J::infinity();
-    for (unsigned s = tid; s < nseg; s += blockDim.x) {
+    for (unsigned s = quad; s < nseg; s += 32) {
         G1J v = ld_vec(segs + (size_t)w * nseg + s);
-        g1_add_ni(&acc, &acc, &v);
+        quad_add(&acc, &acc, &v);
     }
-    g1_warp_sum(acc, 32);
+    quad_warp_sum(acc);
     if ((tid & 31) == 0) part[tid >> 5] = acc;
     __syncthreads();
-    if (tid == 0) {
-        for (unsigned j = 1; j < blockDim.x / 32; j++) g1_add_ni(&acc, &acc, &part[j]);
-        for (unsigned d = 0; d < p.c * w; d++) {
-            if (acc.is_inf()) break;
-            g1_dbl_ni(&acc, &acc);
-        }
-        st_vec(wsums + w, acc);
+    if (tid < 4) {                                   // quad 0
+        for (unsigned j = 1; j < 4; j++) { G1J v = part[j]; quad_add(&acc, &acc, &v); }
+        if (tid == 0) st_vec(wsums + w, acc);
     }
 }
 
-// ---- step 7: sum of the W <= 33 weighted window sums ------------------------------------------------------
-__global__ void __launch_bounds__(32) k_msm_final(MsmPlan p, const G1J* __restrict__ wsums, G1J* __restrict__ out) {
-    const unsigned lane = threadIdx.x;
+// ---- step 7: one CTA, quad w doubles the sum of window w  c w  times; then the sum over the windows -------------
+__global__ void __launch_bounds__(160) k_msm_horner(MsmPlan p, const G1J* __restrict__ wsums, G1J* __restrict__ out) {
+    __shared__ G1J part[5];
+    const unsigned tid = threadIdx.x, w = tid >> 2;
     G1J acc = G1J::infinity();
-    for (unsigned w = lane; w < p.W; w += 32) {
-        G1J v = ld_vec(wsums + w);
-        g1_add_ni(&acc, &acc, &v);
+    if (w < p.W) {
+        acc = ld_vec(wsums + w);
+        for (unsigned d = 0; d < p.c * w && !acc.is_inf(); d++) quad_dbl(&acc, &acc);
     }
-    g1_warp_sum(acc, 32);
-    if (lane == 0) st_vec(out, acc);
+    quad_warp_sum(acc);
+    const unsigned nwarp = blockDim.x >> 5;
+    if ((tid & 31) == 0) part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid < 4) {
+        for (unsigned j = 1; j < nwarp; j++) { G1J v = part[j]; quad_add(&acc, &acc, &v); }
+        if (tid == 0) st_vec(out, acc);
+    }
 }
+
+// a quad per (bucket, slice) unit while the accumulation then still fits about one wave of the chip
+static const size_t kMsmQuadUnits = (size_t)148 * 2048;
 
 // ---- workspace layout -------------------------------------------------------------------------------------
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -184,10 +238,12 @@ void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* w
     k_msm_recode<<<grid_for(n, 128), 128, 0, st>>>(p, pts, k, k_is_mont, ws.digits, ws.counts, ws.bx, ws.flag);
     k_msm_scan<<<p.W, 1024, 0, st>>>(p, ws.counts, ws.offsets);
     k_msm_scatter<<<grid_for((size_t)p.W * p.T, 256), 256, 0, st>>>(p, ws.digits, ws.offsets, ws.cursors, ws.sorted);
-    k_msm_accumulate<<<grid_for((size_t)p.W * p.B * p.S, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
-    k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L), 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
+    const size_t units = (size_t)p.W * p.B * p.S;
+    if (units * 4 <= kMsmQuadUnits && p.S <= 8) k_msm_accumulate<true><<<grid_for(units * 4, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
+    else k_msm_accumulate<false><<<grid_for(units, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
+    k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L) * 4, 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
     k_msm_windows<<<p.W, 128, 0, st>>>(p, ws.segs, ws.wsums);
-    k_msm_final<<<1, 32, 0, st>>>(p, ws.wsums, out);
+    k_msm_horner<<<1, (unsigned)((p.W * 4 + 31) / 32 * 32), 0, st>>>(p, ws.wsums, out);
     g_launch_count += 7;
 }
 

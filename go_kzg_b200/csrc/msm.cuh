@@ -10,11 +10,13 @@
 //   1 recode    per point: GLV split, digits of both halves, digit histogram per window, beta x
 //   2 scan      per window: exclusive prefix of the histogram -> start of every bucket's term list
 //   3 scatter   counting sort of the terms by (window, bucket); sign in bit 31
-//   4 accumulate  thread = (bucket, slice): sums its share of the bucket's list; the S slices of a bucket sit
+//   4 accumulate  unit = (bucket, slice): sums its share of the bucket's list; the S slices of a bucket sit
 //               in adjacent lanes and are combined with a warp-shuffle tree
-//   5 segments  thread = L consecutive buckets: sum_j (b0 + j) Bucket[b0 + j] with a running sum
-//   6 windows   one CTA per window: tree sum of its segments, then c w doublings
-//   7 final     sum of the W weighted window sums
+//   5 segments  unit = L consecutive buckets: sum_j (b0 + j) Bucket[b0 + j] with a running sum
+//   6 windows   one CTA per window: tree sum of its segments
+//   7 horner    window w doubled c w times, then the sum of the W weighted window sums
+// Steps 5-7 (and step 4 when the problem is too small to fill the chip) run one unit per QUAD of lanes (quad.cuh):
+// they are waited for because of the depth of their chains of point operations, and a quad walks a chain 2-3x faster.
 // Terms: t < n is (k1 digit, P_t), t >= n is (k2 digit, z^2 P_(t - n)).
 #pragma once
 #include "g1_dev.cuh"

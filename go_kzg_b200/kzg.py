@@ -84,6 +84,12 @@ def lib():
     L.b200_g1_to_compressed_many.argtypes = [vp, vp, sz]
     L.b200_g1_to_compressed_many.restype = None
     L.b200_g1_from_compressed_many.argtypes = [vp, vp, sz]
+    L.b200_g1_from_compressed_batch.argtypes = [vp, sz, vp, vp]
+    L.b200_toeplitz_part2.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.b200_toeplitz_part3.argtypes = [vp, vp, sz, vp]
+    L.b200_evaluate_poly_in_evaluation_form_batch.argtypes = [vp, vp, vp, sz, sz, i32, vp]
+    L.b200_check_proof_single_g1_batch.argtypes = [vp, vp, sz, vp]
+    L.b200_check_proof_multi_g1_batch.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp]
     L.b200_g1_lincomb.argtypes = [vp, vp, sz, vp]
     L.b200_g1_mul_many.argtypes = [vp, vp, sz, vp]
     L.b200_fft_settings_new.argtypes = [C.c_uint8, C.POINTER(vp)]
@@ -206,6 +212,89 @@ def g1_from_compressed(b) -> np.ndarray:
     return out
 
 
+def g1_from_compressed_device(b, return_ok: bool = False):
+    """FromCompressedG1 over an array on the GPU (b200_g1_from_compressed_batch): square root and subgroup check per
+    point on the device.  Raises KZGError on a bad encoding unless return_ok, which hands back (points, ok)."""
+    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 48)
+    out = np.zeros((b.shape[0], 18), dtype=np.uint64)
+    ok = np.zeros(b.shape[0], dtype=np.uint8)
+    rc = lib().b200_g1_from_compressed_batch(_p(b), b.shape[0], _p(out), _p(ok))
+    if return_ok and rc in (OK, BAD_INPUT):
+        return out, ok.astype(bool)
+    _raise(rc, errors=(BAD_INPUT,), what="FromCompressedG1 (device)")
+    return out
+
+
+def g1_marshal_text(pts) -> list:
+    """bls/bls_all.go:20-23 (*G1Point).MarshalText: hex of the compressed encoding, no 0x prefix."""
+    return [bytes(row).hex() for row in g1_to_compressed(pts)]
+
+
+def g1_unmarshal_text(texts, device: bool = True) -> np.ndarray:
+    """bls/bls_all.go:25-39 (*G1Point).UnmarshalText over a list: hex (no 0x prefix) -> FromCompressedG1; error on bad
+    hex, a wrong length or a bad point."""
+    raw = []
+    for t in texts:
+        if isinstance(t, bytes):
+            t = t.decode()
+        try:
+            v = bytes.fromhex(t)
+        except ValueError as e:
+            raise KZGError(BAD_INPUT, "UnmarshalText: %s" % e)
+        if len(v) != 48:
+            raise KZGError(BAD_INPUT, "UnmarshalText: %d bytes, want 48" % len(v))
+        raw.append(v)
+    arr = np.frombuffer(b"".join(raw), dtype=np.uint8).reshape(-1, 48) if raw else np.zeros((0, 48), dtype=np.uint8)
+    return g1_from_compressed_device(arr) if device else g1_from_compressed(arr)
+
+
+def bit_reversal_permutation(a: np.ndarray) -> np.ndarray:
+    """eth/helpers.go bitReversalPermutation on the first axis (length a power of two)."""
+    n = a.shape[0]
+    bits = n.bit_length() - 1
+    idx = np.arange(n, dtype=np.uint64)
+    rev = np.zeros(n, dtype=np.uint64)
+    for k in range(bits):
+        rev |= ((idx >> np.uint64(k)) & np.uint64(1)) << np.uint64(bits - 1 - k)
+    return a[rev.astype(np.int64)]
+
+
+def load_trusted_setup(source, device: bool = True) -> dict:
+    """eth/globals.go:33-49: parses a trusted_setup.json-shaped document ({"setup_G1": [...], "setup_G2": [...],
+    "setup_G1_lagrange": [...]}, hex strings without 0x).  Returns {"setup_G1": (n, 18) points,
+    "setup_G1_lagrange": (n, 18) points ALREADY in reverse bit order (eth/globals.go:48 kzgSetupLagrange),
+    "setup_G2": (m, 96) raw compressed bytes -- G2 stays with the caller's pairing backend}.
+    `source` is a path, a JSON string / bytes, or an already parsed dict."""
+    import json
+    if isinstance(source, dict):
+        doc = source
+    else:
+        if isinstance(source, bytes):
+            source = source.decode()
+        if isinstance(source, str) and not source.lstrip().startswith("{"):
+            with open(source) as f:
+                source = f.read()
+        doc = json.loads(source)
+    g1 = g1_unmarshal_text(doc.get("setup_G1", []), device)
+    lag = g1_unmarshal_text(doc.get("setup_G1_lagrange", []), device)
+    g2 = doc.get("setup_G2", [])
+    for t in g2:
+        if len(bytes.fromhex(t)) != 96:
+            raise KZGError(BAD_INPUT, "setup_G2: want 96-byte compressed points")
+    g2b = np.frombuffer(b"".join(bytes.fromhex(t) for t in g2), dtype=np.uint8).reshape(-1, 96) if g2 else np.zeros((0, 96), dtype=np.uint8)
+    return {"setup_G1": g1, "setup_G1_lagrange": bit_reversal_permutation(lag) if lag.shape[0] else lag, "setup_G2": g2b}
+
+
+def check_proof_single_g1(commitments, ys) -> np.ndarray:
+    """kzg_single_proofs.go:57-75 CheckProofSingle, G1 side for a batch: commitment - y G.  The pairing
+    e(result, [1]_2) == e(proof, [s - x]_2) stays with the caller's backend."""
+    c, y = _g1(commitments), _fr(ys)
+    assert c.shape[0] == y.shape[0]
+    out = np.zeros_like(c)
+    _raise(lib().b200_check_proof_single_g1_batch(_p(c), _p(y), c.shape[0], _p(out)), what="CheckProofSingle (G1 side)")
+    return out
+
+
 def lincomb_g1(points, scalars) -> np.ndarray:
     """bls/bls_kilic.go:132-150 LinCombG1 (device MSM); panics on a length mismatch."""
     pts, sc = _g1(points), _fr(scalars)
@@ -290,6 +379,33 @@ class FFTSettings:
         out = np.zeros_like(v)
         _raise(lib().b200_fft_g1(self.h, _p(v), v.shape[0], int(inv), _p(out)), errors=(TOO_LARGE, NOT_POW2), what="FFTG1")
         return out
+
+    def toeplitz_part2(self, toeplitz_coeffs, x_ext_fft) -> np.ndarray:
+        """fk20_single.go:59-77 (method of KZGSettings in the reference; it only needs the FFT settings)."""
+        c, x = _fr(toeplitz_coeffs), _g1(x_ext_fft)
+        out = np.zeros_like(x)
+        _raise(lib().b200_toeplitz_part2(self.h, _p(c), c.shape[0], _p(x), x.shape[0], _p(out)), what="ToeplitzPart2")
+        return out
+
+    def toeplitz_part3(self, h_ext_fft) -> np.ndarray:
+        """fk20_single.go:80-87: first half of the inverse FFTG1"""
+        h = _g1(h_ext_fft)
+        out = np.zeros((h.shape[0] // 2, 18), dtype=np.uint64)
+        _raise(lib().b200_toeplitz_part3(self.h, _p(h), h.shape[0], _p(out)), what="ToeplitzPart3")
+        return out
+
+    def evaluate_poly_in_evaluation_form(self, polys, xs, reverse_bit_order: bool = False) -> np.ndarray:
+        """bls/globals.go:106-153 for a batch: polys (batch, n, 4) evaluations on this settings' order-n domain
+        (natural order, or reverse bit order like eth.DomainFr), xs (batch, 4) -> y (batch, 4)."""
+        p = np.ascontiguousarray(polys, dtype=np.uint64)
+        if p.ndim == 2:
+            p = p[None]
+        x = _fr(xs)
+        assert x.shape[0] == p.shape[0]
+        y = np.zeros((p.shape[0], 4), dtype=np.uint64)
+        _raise(lib().b200_evaluate_poly_in_evaluation_form_batch(self.h, _p(p), _p(x), p.shape[1], p.shape[0], int(reverse_bit_order), _p(y)),
+               what="EvaluatePolyInEvaluationForm")
+        return y
 
     def fft_g1_batch(self, vals, inv: bool = False) -> np.ndarray:
         v = np.ascontiguousarray(vals, dtype=np.uint64)
@@ -388,6 +504,21 @@ class KZGSettings:
         _raise(lib().b200_compute_kzg_proof_batch(self.h, _p(p), _p(z), n, batch, _p(proofs), _p(y), _p(ok)),
                errors=(TOO_LARGE, NOT_POW2, LEN_MISMATCH), what="ComputeKZGProof")
         return proofs, y, ok.astype(bool)
+
+    def check_proof_multi_g1(self, commitments, xs, ys):
+        """kzg_multi_proofs.go:47-88 CheckProofMulti without the G2 arithmetic and the pairing, for a batch of samples:
+        ys (batch, n, 4).  Returns (commitment - [interpolation_polynomial(s)]_1 (batch, 18), x^n (batch, 4)); the
+        caller checks e(first, [1]_2) == e(proof, SecretG2[n] - [x^n]_2)."""
+        c, x = _g1(commitments), _fr(xs)
+        y = np.ascontiguousarray(ys, dtype=np.uint64)
+        if y.ndim == 2:
+            y = y[None]
+        batch, n = y.shape[0], y.shape[1]
+        assert c.shape[0] == batch and x.shape[0] == batch
+        out = np.zeros((batch, 18), dtype=np.uint64)
+        xn = np.zeros((batch, 4), dtype=np.uint64)
+        _raise(lib().b200_check_proof_multi_g1_batch(self.h, _p(c), _p(x), _p(y), n, batch, _p(out), _p(xn)), what="CheckProofMulti (G1 side)")
+        return out, xn
 
     def commit_to_poly_batch(self, coeffs) -> np.ndarray:
         c = np.ascontiguousarray(coeffs, dtype=np.uint64)

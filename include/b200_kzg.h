@@ -79,6 +79,11 @@ int b200_g1_from_compressed(uint64_t out[18], const uint8_t in[48]);            
 void b200_g1_to_compressed_many(uint8_t* out, const uint64_t* pts, size_t n);
 int b200_g1_from_compressed_many(uint64_t* out, const uint8_t* in, size_t n);
 
+/* bls/bls_kilic.go:118-121 FromCompressedG1 over an array ON THE DEVICE (eth/globals.go:33-49 decodes 3 x 4096 points
+ * at start-up; larger setups hold millions): flags, x < p, curve equation, prime-order subgroup.  ok (may be NULL)
+ * gets 1 per accepted point; a rejected encoding -> B200_ERR_BAD_INPUT with that output zeroed. */
+int b200_g1_from_compressed_batch(const uint8_t* in48, size_t n, uint64_t* out, uint8_t* ok);
+
 /* Device MSM.  bls/bls_kilic.go:132-150 LinCombG1: sum_i scalars[i] * points[i]; n == 0 gives
  * infinity (bls/bls_test.go:69-77).  Pippenger bucket method (kernels_msm.cu): GLV halves, signed windows,
  * per-window buckets accumulated in shared memory, warp-shuffle running-sum reduction; below 32 terms the
@@ -105,6 +110,18 @@ int b200_fft_fr_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch,
 /* fft_g1.go:58-94 FFTG1: n must be a power of two <= MaxWidth. */
 int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out);
 int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, size_t batch, int inverse, uint64_t* out);
+/* fk20_single.go:59-77 ToeplitzPart2 as a stand-alone method: hExtFFT[i] = FFT(toeplitzCoeffs)[i] * xExtFFT[i] for
+ * caller-held points; n_coeffs != n_points -> B200_ERR_LEN_MISMATCH (panic :60-62).  The FK20 entry points below run
+ * a fused form over the settings' resident xExtFFT instead. */
+int b200_toeplitz_part2(b200_fs* fs, const uint64_t* toeplitz_coeffs, size_t n_coeffs, const uint64_t* x_ext_fft, size_t n_points,
+                        uint64_t* h_ext_fft);
+/* fk20_single.go:80-87 ToeplitzPart3: FFTG1(hExtFFT, inverse)[:n2 / 2]; out holds n2 / 2 points. */
+int b200_toeplitz_part3(b200_fs* fs, const uint64_t* h_ext_fft, size_t n2, uint64_t* out);
+/* bls/globals.go:106-153 EvaluatePolyInEvaluationForm for `batch` polynomials of n = 2^k evaluations on the settings'
+ * order-n domain, natural order (rootsOfUnity = ExpandedRootsOfUnity, scale = log2(MaxWidth / n)) or reverse bit order
+ * (eth DomainFr, eth/globals.go:60-67); xs[b] = evaluation point, y[b] = result (canonical). */
+int b200_evaluate_poly_in_evaluation_form_batch(b200_fs* fs, const uint64_t* polys, const uint64_t* xs, size_t n, size_t batch,
+                                                int reverse_bit_order, uint64_t* y);
 /* das_extension.go:71-84 DASFFTExtension: in place; requires 2 n <= MaxWidth (and, as in the
  * reference, is only meaningful for MaxWidth == 2 n). */
 int b200_das_fft_extension(b200_fs* fs, uint64_t* vals, size_t n);
@@ -126,6 +143,16 @@ void b200_kzg_settings_free(b200_ks* ks);
 /* kzg_single_proofs.go:17-19 CommitToPoly = LinCombG1(SecretG1[:n], coeffs) */
 int b200_commit_to_poly(b200_ks* ks, const uint64_t* coeffs, size_t n, uint64_t out[18]);
 int b200_commit_to_poly_batch(b200_ks* ks, const uint64_t* coeffs, size_t n, size_t batch, uint64_t* out);
+
+/* ------------------------------------------------------------------ verification, G1 side ---
+ * kzg_single_proofs.go:57-75 CheckProofSingle: out[i] = commitment[i] - y[i] G.  The G2 arithmetic and the pairing
+ * stay with the caller's backend (bls.PairingsVerify): e(out[i], [1]_2) == e(proof[i], [s - x[i]]_2). */
+int b200_check_proof_single_g1_batch(const uint64_t* commitments, const uint64_t* ys, size_t batch, uint64_t* out);
+/* kzg_multi_proofs.go:47-88 CheckProofMulti for `batch` samples of n = len(ys) values each (power of two):
+ * out_g1[b] = commitment[b] - [interpolation_polynomial_b(s)]_1, x_pow_n[b] = x[b]^n; the caller checks
+ * e(out_g1[b], [1]_2) == e(proof[b], SecretG2[n] - [x^n]_2).  n > MaxWidth -> TOO_LARGE (the reference panics). */
+int b200_check_proof_multi_g1_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* xs, const uint64_t* ys, size_t n,
+                                    size_t batch, uint64_t* out_g1, uint64_t* x_pow_n);
 
 /* ------------------------------------------------------------------ FK20 ------------------- */
 /* kzg.go:43-64 NewFK20SingleSettings(ks, n2) */

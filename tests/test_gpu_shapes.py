@@ -195,3 +195,175 @@ def test_inplace_fft_error_split():
         fs.inplace_fft(np.zeros((0, 4), dtype=np.uint64))
     with pytest.raises(kzg.KZGPanic):                     # same in FFTG1 (fft_g1.go:78,88)
         fs.fft_g1(np.zeros((0, 18), dtype=np.uint64))
+
+
+# ------------------------------------------------------------------------------ SURVEY.md 8f ranks 2-4
+def test_from_compressed_on_device(trusted_setup_bytes):
+    """bls/bls_kilic.go:118-121 over arrays on the GPU == the host level-1 decoder == the oracle: the 4096 + 4096
+    points of eth/trusted_setup.json, infinity, and the rejections (bad flags, x >= p, not on the curve, on the curve
+    but outside the prime-order subgroup)."""
+    s1, lag = trusted_setup_bytes
+    both = np.concatenate([s1, lag])
+    got = kzg.g1_from_compressed_device(both)
+    assert np.array_equal(got, cref.g1_decompress(both))
+    assert np.array_equal(got[:64], kzg.g1_from_compressed(both[:64]))
+    assert (got[:, 12] == 1).all() and not got[:, 13:].any()            # Z = 1
+    P_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    inf = np.zeros(48, dtype=np.uint8); inf[0] = 0xC0
+    cases, want_ok = [s1[1], inf], [True, True]
+    bad_inf = inf.copy(); bad_inf[47] = 1
+    no_flag = s1[1].copy(); no_flag[0] &= 0x7F
+    too_big = np.frombuffer(bytes([0x80 | (P_MOD >> 376)]) + (P_MOD & ((1 << 376) - 1)).to_bytes(47, "big"), dtype=np.uint8)
+    cases += [bad_inf, no_flag, too_big]; want_ok += [False, False, False]
+    n_off_curve = n_off_group = 0
+    for x in range(1, 30):
+        enc = np.frombuffer(bytes([0x80]) + x.to_bytes(48, "big")[1:], dtype=np.uint8)
+        on_curve = pow((x ** 3 + 4) % P_MOD, (P_MOD - 1) // 2, P_MOD) == 1
+        cases.append(enc); want_ok.append(False)                         # small x: never in the subgroup
+        n_off_curve += not on_curve; n_off_group += on_curve
+    assert n_off_curve >= 5 and n_off_group >= 5
+    pts, ok = kzg.g1_from_compressed_device(np.stack(cases), return_ok=True)
+    assert list(ok) == want_ok
+    assert not pts[2:].any() and not pts[1].any()
+    for enc, good in zip(cases, want_ok):                                # the host decoder and the oracle agree case by case
+        rc = kzg.lib().b200_g1_from_compressed(np.zeros(18, dtype=np.uint64).ctypes.data, np.ascontiguousarray(enc).ctypes.data)
+        assert (rc == 0) == good
+    with pytest.raises(kzg.KZGError):
+        kzg.g1_from_compressed_device(np.stack(cases))
+
+
+def test_trusted_setup_loader_and_text_formats(trusted_setup_bytes):
+    """eth/globals.go:33-49 on a trusted_setup.json-shaped document (built from the reference's own fixture bytes):
+    hex UnmarshalText (bls/bls_all.go:25-39) -> device FromCompressedG1, Lagrange half in reverse bit order (:48);
+    MarshalText round trip; the loaded halves satisfy the file's relation IFFT_G1(setup_G1) == setup_G1_lagrange."""
+    import json
+    s1, lag = trusted_setup_bytes
+    doc = json.dumps({"setup_G1": [bytes(r).hex() for r in s1], "setup_G2": ["c0" + "00" * 95],
+                      "setup_G1_lagrange": [bytes(r).hex() for r in lag]})
+    ts = kzg.load_trusted_setup(doc)
+    assert ts["setup_G2"].shape == (1, 96)
+    assert np.array_equal(kzg.g1_to_compressed(ts["setup_G1"]), s1)
+    brp = kzg.bit_reversal_permutation(np.arange(4096))
+    assert np.array_equal(kzg.g1_to_compressed(ts["setup_G1_lagrange"]), lag[brp])
+    assert kzg.g1_marshal_text(ts["setup_G1"][:5]) == [bytes(r).hex() for r in s1[:5]]
+    fs = kzg.FFTSettings(12)
+    nat = fs.fft_g1(ts["setup_G1"], True)
+    assert np.array_equal(kzg.g1_to_compressed(nat[brp]), kzg.g1_to_compressed(ts["setup_G1_lagrange"]))
+    with pytest.raises(kzg.KZGError):
+        kzg.g1_unmarshal_text(["zz" * 48])
+    with pytest.raises(kzg.KZGError):
+        kzg.g1_unmarshal_text(["00" * 48])                               # compression flag missing
+    with pytest.raises(kzg.KZGError):
+        kzg.g1_unmarshal_text(["c0" + "00" * 46])                        # 47 bytes
+
+
+@pytest.mark.parametrize("n,rev", [(4, False), (16, True), (4096, True), (4096, False), (512, False)])
+def test_evaluate_poly_in_evaluation_form(n, rev):
+    """bls/globals.go:106-153 stand-alone: y == p(x) for the interpolating polynomial (oracle inverse FFT + Horner,
+    independent of the barycentric formula), natural and reverse-bit-order domains, sub-size domains (scale > 0),
+    and x inside the domain (the reference's formula then yields 0)."""
+    bits = n.bit_length() - 1
+    scale = max(bits, 4) + (1 if n == 512 else 0)                        # n = 512 on a 1024-domain: roots stride 2
+    fs, ofs = kzg.FFTSettings(scale), cref.FFTSettings(bits)
+    batch = 3
+    polys = np.zeros((batch, n, 4), dtype=np.uint64)
+    xs, want = [], []
+    w = pyref.scale2_root_of_unity(bits)
+    perm = [pyref.reverse_bits_limited(n, i) for i in range(n)] if rev else list(range(n))
+    for b in range(batch):
+        v = random_fr_ints(n, 0xEF000000 + 16 * n + b)
+        coeffs = cref.limbs_to_fr(ofs.fft(cref.fr_to_limbs(v), True))
+        x = random_fr_ints(1, 0xEE000000 + b)[0] if b != 1 else pow(w, 3 % n, R)
+        xs.append(x)
+        want.append(pyref.eval_poly(coeffs, x) if b != 1 else 0)
+        polys[b] = kzg.fr_from_ints([v[perm[i]] for i in range(n)])
+    y = fs.evaluate_poly_in_evaluation_form(polys, kzg.fr_from_ints(xs), rev)
+    assert kzg.fr_to_ints(y) == want
+
+
+def test_check_proof_single_and_multi_g1_side(goldens):
+    """kzg_single_proofs.go:57-75 and kzg_multi_proofs.go:47-88 without the pairing: the G1 operands the reference
+    hands to PairingsVerify.  With the secret known, e(A, [1]) == e(proof, [t]) is A == t * proof in G1; the proofs
+    come from the closed forms the reference's tests check (kzg_single_proofs_test.go / kzg_multi_proofs_test.go:
+    quotient by X - x resp. X^n - x^n evaluated at s)."""
+    secret = int(goldens["fk20_single_test"]["secret"])
+    scale, width = 6, 64
+    fs = kzg.FFTSettings(scale)
+    setup = cref.generate_setup_g1(secret, width + 1)
+    ks = kzg.KZGSettings(fs, setup)
+    rng = random.Random(99)
+    poly = [rng.randrange(R) for _ in range(32)]
+    commit = ks.commit_to_poly(kzg.fr_from_ints(poly))
+    ps = pyref.eval_poly(poly, secret)
+    L = kzg.lib()
+    # --- single: x arbitrary, y = p(x), proof = (p(s) - y) / (s - x) G
+    xs = [rng.randrange(R) for _ in range(5)]
+    ys = [pyref.eval_poly(poly, x) for x in xs]
+    a = kzg.check_proof_single_g1(np.stack([commit] * 5), kzg.fr_from_ints(ys))
+    cmp_g1(a, cref.g1_mul_gen([(ps - y) % R for y in ys]))
+    proofs = cref.g1_mul_gen([(ps - y) * pow((secret - x) % R, -1, R) % R for x, y in zip(xs, ys)])
+    for i in range(5):                                                    # the pairing equation, in G1
+        t = kzg.fr_from_ints([(secret - xs[i]) % R])
+        lhs = np.zeros(18, dtype=np.uint64)
+        L.b200_g1_mul(lhs.ctypes.data, proofs[i].ctypes.data, t.ctypes.data)
+        assert L.b200_g1_equal(lhs.ctypes.data, np.ascontiguousarray(a[i]).ctypes.data) == 1
+    wrong = kzg.check_proof_single_g1(commit.reshape(1, 18), kzg.fr_from_ints([(ys[0] + 1) % R]))
+    assert L.b200_g1_equal(np.ascontiguousarray(wrong[0]).ctypes.data, np.ascontiguousarray(a[0]).ctypes.data) == 0
+    # --- multi: coset x <w_n>, n = 8: ys[i] = p(x w^i)
+    n = 8
+    wn = pyref.scale2_root_of_unity(3)
+    ofs = pyref.FFTSettings(3)
+    batch = 4
+    xs = [rng.randrange(1, R) for _ in range(batch)]
+    xs[1] = 0                                                             # InvModFr(0) = 0: only the constant coefficient survives
+    ys_all, want_is, want_xn = [], [], []
+    for x in xs:
+        ysb = [pyref.eval_poly(poly, x * pow(wn, i, R) % R) for i in range(n)]
+        ys_all.append(kzg.fr_from_ints(ysb))
+        interp = ofs.fft(ysb, True)
+        xinv = pow(x, -1, R) if x else 0
+        interp = [c * pow(xinv, i, R) % R for i, c in enumerate(interp)]
+        want_is.append(pyref.eval_poly(interp, secret))
+        want_xn.append(pow(x, n, R))
+    got, xn = ks.check_proof_multi_g1(np.stack([commit] * batch), kzg.fr_from_ints(xs), np.stack(ys_all))
+    assert kzg.fr_to_ints(xn) == want_xn
+    cmp_g1(got, cref.g1_mul_gen([(ps - v) % R for v in want_is]))
+    for b in (0, 2, 3):                                                   # p - I == q (X^n - x^n): A == (s^n - x^n) * [q(s)]
+        q_at_s = (ps - want_is[b]) * pow((pow(secret, n, R) - want_xn[b]) % R, -1, R) % R
+        proof = cref.g1_mul_gen([q_at_s])[0]
+        t = kzg.fr_from_ints([(pow(secret, n, R) - want_xn[b]) % R])
+        lhs = np.zeros(18, dtype=np.uint64)
+        L.b200_g1_mul(lhs.ctypes.data, proof.ctypes.data, t.ctypes.data)
+        assert L.b200_g1_equal(lhs.ctypes.data, np.ascontiguousarray(got[b]).ctypes.data) == 1
+    # a large batch takes the fixed-base table route (batch * n >= 4096): same values
+    big = 600
+    xs2 = [rng.randrange(1, R) for _ in range(big)]
+    ys2 = np.stack([kzg.fr_from_ints([pyref.eval_poly(poly[:4], x * pow(wn, i, R) % R) for i in range(n)]) for x in xs2])
+    commit4 = ks.commit_to_poly(kzg.fr_from_ints(poly[:4]))
+    got2, _ = ks.check_proof_multi_g1(np.stack([commit4] * big), kzg.fr_from_ints(xs2), ys2)
+    cmp_g1(got2, np.zeros((big, 18), dtype=np.uint64))                    # deg p < n: the interpolation IS p, difference = infinity
+    with pytest.raises(kzg.KZGPanic):
+        ks.check_proof_multi_g1(commit.reshape(1, 18), kzg.fr_from_ints([5]), np.zeros((1, 128, 4), dtype=np.uint64))
+
+
+def test_toeplitz_part2_part3_standalone(goldens):
+    """fk20_single.go:59-87 as stand-alone methods == the oracle's FK20Single internals: Part3(Part2(coeffs, xExtFFT))
+    is h, and FFTG1(h) the proofs (fk20_single.go:122-134)."""
+    t = goldens["fk20_single_test"]
+    secret, poly, scale, n2 = int(t["secret"]), t["poly"], t["fft_scale"], t["n2"]
+    n = len(poly)
+    setup = cref.generate_setup_g1(secret, n2 + 1)
+    fs = kzg.FFTSettings(scale)
+    fk = kzg.FK20SingleSettings(kzg.KZGSettings(fs, setup), n2)
+    coeffs = kzg.fr_from_ints(pyref.toeplitz_coeffs_step(poly))
+    h_ext = fs.toeplitz_part2(coeffs, fk.x_ext_fft())
+    ofs = pyref.FFTSettings(scale)
+    x = [pow(secret, j, R) for j in range(n - 2, -1, -1)] + [0] * (n + 1)
+    want_ext = [a * b % R for a, b in zip(ofs.fft(pyref.toeplitz_coeffs_step(poly)), ofs.fft(x))]
+    cmp_g1(h_ext, cref.g1_mul_gen(want_ext))
+    h = fs.toeplitz_part3(h_ext)
+    assert h.shape == (n, 18)
+    cmp_g1(h, cref.g1_mul_gen(ofs.fft(want_ext, True)[:n]))
+    cmp_g1(fs.fft_g1(h), fk.fk20_single(kzg.fr_from_ints(poly)))
+    with pytest.raises(kzg.KZGPanic):                                     # fk20_single.go:60-62
+        fs.toeplitz_part2(coeffs[:16], fk.x_ext_fft())
