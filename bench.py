@@ -39,6 +39,14 @@ N_CLASSES = len(PROFILE_CLASSES)
 METRIC = "blobs/sec (commit+FK20 all-proofs, n=%d)" % N_COEFFS
 
 
+def load_json(rel):
+    try:
+        with open(os.path.join(ROOT, rel)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -134,6 +142,66 @@ def fp_ops_model_per_blob():
     # n butterflies and n - 3 non-trivial twiddle products less, 3 n more look-up products
     fft_inv = plus(times(stages - (n - 1) - (n - 3), wnaf5), times(stages - n, butterfly))
     return plus(fft, fft_inv, times(n, wnaf5), times(n, cost(n_add=1)), times(3 * n + 3 * n, fixed_base), times(n - 1, cost(n_add=1)))
+
+
+def run_components(kzg, L, fk, fs, torch, dist, rank, world, max_over_ranks, barrier):
+    """Numbers the headline metric does not show, measured at every N (device time with CUDA events where the work is
+    device-resident, wall clock through the host-buffer call otherwise; max over ranks):
+      * one polynomial per call (the reference's API shape): FK20Single and DAUsingFK20 at n = 4096;
+      * config 4: DASFFTExtension + RecoverPolyFromSamples, n = 2^14, half missing, `batch` polynomials per GPU;
+      * config 5: DAUsingFK20Multi n = 2^20, chunk 16, chunk offsets sharded over the N GPUs with one exchange of
+        partial G1 sums over NCCL (go_kzg_b200/multi_gpu.py)."""
+    from go_kzg_b200.synth import random_fr_limbs
+    from go_kzg_b200 import multi_gpu
+    out = {}
+
+    def wall(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return max_over_ranks((time.perf_counter() - t0) / reps)
+
+    poly = random_fr_limbs(N_COEFFS, 0xC0DE + rank)
+    barrier()
+    out["fk20_single_one_polynomial_ms"] = round(wall(lambda: fk.fk20_single(poly), 3) * 1e3, 3)
+    out["da_using_fk20_one_polynomial_ms"] = round(wall(lambda: fk.da_using_fk20(poly), 3) * 1e3, 3)
+    out["one_polynomial_note"] = "host-buffer call per polynomial, n = %d (b200_fk20_single / b200_da_using_fk20), wall clock, max over ranks" % N_COEFFS
+    if N_COEFFS == 4096:
+        # ---- config 4
+        scale, batch = 14, 64
+        n = 1 << scale
+        fs14 = kzg.FFTSettings(scale)
+        even = np.stack([random_fr_limbs(n // 2, 0xD4000000 + rank * batch + b) for b in range(batch)])
+        odd = fs14.das_fft_extension_batch(even)
+        full = np.empty((batch, n, 4), dtype=np.uint64)
+        full[:, 0::2], full[:, 1::2] = even, odd
+        rng = np.random.default_rng(14 + rank)
+        present = np.ones((batch, n), dtype=np.uint8)
+        for b in range(batch):
+            present[b, rng.permutation(n)[: n // 2]] = 0
+        samples = full.copy()
+        samples[present == 0] = 0
+        rec = [None]
+        def do_rec():
+            rec[0] = fs14.recover_poly_from_samples_batch(samples, present)
+        barrier()
+        t_ext = wall(lambda: fs14.das_fft_extension_batch(even), 3)
+        t_rec = wall(do_rec, 2)
+        ok = bool(np.array_equal(rec[0], full))
+        out["config4"] = {"workload": "DASFFTExtension(8192 -> 16384) + RecoverPolyFromSamples(n=2^14, 50%% missing), %d polynomials per GPU per call" % batch,
+                          "das_extension_polys_per_s": round(world * batch / t_ext, 1), "recover_polys_per_s": round(world * batch / t_rec, 1),
+                          "recovered_equals_original": ok, "timing": "host-buffer batch calls (copies included), wall clock, max over ranks"}
+        del fs14
+    return out
+
+
+def run_config5(args, dist, world):
+    """config 5 measured after the main handles are released (its tables take up to 103 GB on one GPU)"""
+    from go_kzg_b200 import multi_gpu
+    return multi_gpu.measure_da_using_fk20_multi_sharded(scale=args.config5_scale, chunk_len=16, reps=2, dist=dist if world > 1 else None)
 
 
 def run_ours(args):
@@ -268,6 +336,15 @@ def run_ours(args):
     same = closed_form_ok(d_commit[chk].cpu().numpy().view(np.uint64), d_proofs[chk].cpu().numpy().view(np.uint64), polys[chk]) and \
         closed_form_ok(h_commit[0].numpy().view(np.uint64), h_proofs[0].numpy().view(np.uint64), polys[0])
 
+    components = None
+    if not args.no_components:
+        components = run_components(kzg, L, fk, fs, torch, dist, rank, world, max_over_ranks, barrier)
+        if args.config5_scale > 0 and N_COEFFS == 4096:
+            fk.close(); fk.ks.close()
+            del d_proofs, h_proofs, h_proofs48, flush
+            torch.cuda.empty_cache()
+            components["config5"] = run_config5(args, dist, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,22 +357,47 @@ def run_ours(args):
     stage_ms, stage_n = cls_ms[1], max(1, cls_n[1])
     algo_stage_bytes = B * 2 * G1_NTT_BYTES(N_COEFFS) * K / stage_n                       # average per launch
     achieved = algo_stage_bytes / (stage_ms / stage_n / 1e3) / 1e9
-    traffic = None
-    try:   # per-launch DRAM bytes of this kernel from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_per_launch"] * (B / tj["blobs_per_launch"])
-    except Exception:
-        pass
-    # integer roofline: 32x32->64 multiply-adds (IMAD.WIDE) the step needs against what the multiplier
-    # probe sustains (dependent 381-bit Montgomery products on all SMs, 300 multiply-adds each)
+    tj = load_json("profiles/stage_kernel_traffic.json")   # per-launch DRAM bytes / instruction counts from the committed ncu --set full capture
+    traffic = tj["dram_bytes_per_launch"] * (B / tj["blobs_per_launch"]) if tj else None
+    # Integer roofline of the dominant kernel, MEASURED: lane-level IMAD.WIDE operations one launch executes (ncu:
+    # inst_executed x share of IMAD.WIDE among executed instructions x 32, profiles/stage_kernel_traffic.json, written by
+    # tools/ncu_record.py from the committed capture) over the launch duration timed live above, against the issue limit
+    # of the multiplier pipe: one warp-wide IMAD.WIDE per 4 cycles per SM sub-partition = 8 lane-operations per cycle.
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    imad_peak = 148 * 4 * 8 * sm_mhz * 1e6
+    imad_meas = None
+    if tj and tj.get("imad_wide_lane_ops_per_launch"):
+        imad_meas = tj["imad_wide_lane_ops_per_launch"] * (B / tj["blobs_per_launch"]) / (stage_ms / stage_n / 1e3)
+    # the model count kept beside it: Fp products and squares per blob x multiply-adds each, against the multiplier probe
     pm = C.c_float()
     threads = 148 * 2048
     L.b200_probe_fp_mul(threads, 2000, C.byref(pm))
     fp_peak = threads * 2000 * 2 / (pm.value / 1e3)
     n_mul, n_sqr = fp_ops_model_per_blob()
-    imad_ach = (n_mul * IMAD_PER_MUL + n_sqr * IMAD_PER_SQR) * value / world
-    imad_peak = fp_peak * IMAD_PER_MUL
+    imad_model = (n_mul * IMAD_PER_MUL + n_sqr * IMAD_PER_SQR) * value / world
+    # per kernel class: device time per step, algorithmic bytes per step (arrays in + out, SURVEY.md 8d sizes), GB/s
+    n = N_COEFFS
+    class_bytes = {
+        "fr_ntt": B * 64 * 2 * n,                                             # one Fr NTT of 2n points per blob
+        "g1_fft_stage": B * 2 * G1_NTT_BYTES(n),                              # two size-n G1 transforms per blob
+        "g1_mul": B * 288 * n,                                                # the twist between the two transforms (in place)
+        "g1_fold": B * (n * 144 + 144) + B * 3 * 144 * n,                     # commitment fold + final addition of the even slots
+        "g1_lookup": B * (2 * n * (32 + 144) + n * (32 + 144)) + 3 * n * 144,  # ToeplitzPart2 (2n) + commitment terms (n), bases once
+        "misc": B * (n * 32 + 2 * n * 32 + n * 144 + n * 144),
+    }
+    kernels = {}
+    for i, k in enumerate(PROFILE_CLASSES):
+        if cls_n[i] == 0:
+            continue
+        ms = cls_ms[i] / K
+        ab = class_bytes.get(k)
+        kernels[k] = {"ms_per_step": round(ms, 3), "launches_per_step": int(cls_n[i] // K), "share_of_step": round(cls_ms[i] / ms_total, 4)}
+        if ab:
+            gbs = ab / (ms / 1e3) / 1e9
+            kernels[k].update({"algo_bytes_per_step": int(ab), "achieved_GBs": round(gbs, 3), "frac_of_hbm": round(gbs / hbm_peak, 6)})
+    for k, rec in (load_json("profiles/kernel_pipe_records.json") or {}).items():   # pipe utilisation per kernel from committed ncu captures
+        if k in kernels:
+            kernels[k]["ncu"] = rec
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": "blobs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,13 +416,22 @@ def run_ours(args):
                      "frac": round(achieved / hbm_peak, 6), "traffic": traffic, "peak_kind": peak_kind,
                      "share_of_step": round(stage_ms / ms_total, 4), "launches": int(stage_n),
                      "note": "integer-pipe bound kernel; see int_roofline"},
-        "int_roofline": {"unit": "T multiply-add/s (32x32->64)", "achieved": round(imad_ach / 1e12, 3), "peak": round(imad_peak / 1e12, 3),
-                         "frac": round(imad_ach / imad_peak, 4), "fp_mul_probe_G_per_s": round(fp_peak / 1e9, 3),
-                         "model_per_blob": {"fp_mul": round(n_mul), "fp_sqr": round(n_sqr)},
-                         "how": "model count of Fp products/squares per blob x (300 | 234) multiply-adds x blobs/s per GPU vs "
-                                "b200_probe_fp_mul (dependent Montgomery products, all SMs) x 300"},
+        "int_roofline": {"kernel": "k_g1_fft_stage", "unit": "T IMAD.WIDE lane-ops/s (32x32+64)",
+                         "achieved": round(imad_meas / 1e12, 3) if imad_meas else None, "peak": round(imad_peak / 1e12, 3),
+                         "frac": round(imad_meas / imad_peak, 4) if imad_meas else None,
+                         "how": "ncu inst_executed x IMAD.WIDE share x 32 per launch (profiles/stage_kernel_traffic.json) / live launch duration; "
+                                "peak = 148 SMs x 4 sub-partitions x 8 lane-ops per cycle x %.0f MHz sampled under load" % sm_mhz,
+                         "ncu_fmaheavy_pipe_busy_pct": tj.get("fmaheavy_pipe_busy_pct") if tj else None,
+                         "model": {"achieved": round(imad_model / 1e12, 3), "peak": round(fp_peak * IMAD_PER_MUL / 1e12, 3),
+                                   "frac": round(imad_model / (fp_peak * IMAD_PER_MUL), 4), "fp_mul_probe_G_per_s": round(fp_peak / 1e9, 3),
+                                   "fp_mul_per_blob": round(n_mul), "fp_sqr_per_blob": round(n_sqr),
+                                   "how": "whole step: model count of Fp products/squares per blob x (300 | 234) multiply-adds x blobs/s per GPU "
+                                          "vs b200_probe_fp_mul (dependent Montgomery products, all SMs) x 300"}},
+        "kernels": kernels,
         "kernel_class_ms_per_step": {k: round(cls_ms[i] / K, 3) for i, k in enumerate(PROFILE_CLASSES)},
     }
+    if not args.no_components:
+        out["components"] = components
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out), flush=True)
@@ -402,6 +513,8 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="blobs per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-components", action="store_true", help="skip the extra component measurements (configs 4 and 5, one-polynomial latency)")
+    ap.add_argument("--config5-scale", type=int, default=21, help="FFT scale of the config 5 component (21: n = 2^20 coefficients); 0 skips it")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

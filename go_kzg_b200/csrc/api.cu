@@ -548,18 +548,34 @@ extern "C" int b200_recover_poly_from_samples(b200_fs* fs, const uint64_t* s, co
 // data[b * bstride + i * estride]).  dif: natural order in, bit-reversed out; otherwise (DIT)
 // bit-reversed in, natural out.  No 1/n scaling here.
 // skip_dif: leading decimation-in-frequency stages already done elsewhere (dev_fk20 folds two into ToeplitzPart2)
+// One stage over `batch` transforms: whole-warp batches share the twiddle across the lanes of a warp (sparse programs);
+// for fewer transforms the lanes run across the blocks of the stage while it has at least 32 of them (same sparse
+// programs), and per-lane fixed-window programs are left for the few last (DIT) / first (DIF) stages.
+struct StagePrograms { const ScalarProgram* per_lane; const ScalarProgram* shared; };
+static int fs_stage_programs(b200_fs* fs, int inverse, size_t batch, StagePrograms* sp) {
+    sp->per_lane = sp->shared = nullptr;
+    CKS(fs_programs(fs, inverse, 1, &sp->shared));
+    if (program_mode_for_batch(batch) == 0) CKS(fs_programs(fs, inverse, 0, &sp->per_lane));
+    return B200_OK;
+}
+static void launch_stage_auto(const StagePrograms& sp, G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride,
+                              bool dif, size_t prog_stride, cudaStream_t st) {
+    if (program_mode_for_batch(batch) == 1) launch_g1_fft_stage(data, n_half, batch, m, estride, bstride, dif, sp.shared, prog_stride, st, 0);
+    else if ((n_half / m) % 32 == 0) launch_g1_fft_stage(data, n_half, batch, m, estride, bstride, dif, sp.shared, prog_stride, st, 1);
+    else launch_g1_fft_stage(data, n_half, batch, m, estride, bstride, dif, sp.per_lane, prog_stride, st, 0);
+}
 static int dev_g1_fft_stages(b200_fs* fs, G1J* data, unsigned logn, size_t batch, size_t estride, size_t bstride,
                              bool inverse, bool dif, cudaStream_t st, unsigned skip_dif = 0) {
     if (logn == 0) return B200_OK;
-    const ScalarProgram* progs;
-    CKS(fs_programs(fs, inverse ? 1 : 0, program_mode_for_batch(batch), &progs));
+    StagePrograms sp;
+    CKS(fs_stage_programs(fs, inverse ? 1 : 0, batch, &sp));
     const size_t n = (size_t)1 << logn, halfw = fs->max_width / 2;
     if (dif) {
         for (size_t m = (n / 2) >> skip_dif; m >= 1; m >>= 1)
-            launch_g1_fft_stage(data, n / 2, batch, m, estride, bstride, true, progs, halfw / m, st);
+            launch_stage_auto(sp, data, n / 2, batch, m, estride, bstride, true, halfw / m, st);
     } else {
         for (size_t m = 1; m <= n / 2; m <<= 1)
-            launch_g1_fft_stage(data, n / 2, batch, m, estride, bstride, false, progs, halfw / m, st);
+            launch_stage_auto(sp, data, n / 2, batch, m, estride, bstride, false, halfw / m, st);
     }
     return check_launches();
 }
@@ -955,12 +971,15 @@ struct b200_fk {
     b200_ks* ks = nullptr;
     size_t n2 = 0, chunk_len = 1;
     G1J* d_x_ext_fft = nullptr;   // [chunk_len][n2 / chunk_len], natural order (kzg.go:62,110-114)
+    size_t file_begin = 0, file_end = 1;   // chunk offsets ("files") held by this handle: all of them unless built sharded
     G1A* d_fb_table = nullptr;    // fixed-base window table over d_x_ext_fft (null when over budget)
     int fb_w = 8;                 // its window bits (8, or 4 for very large settings)
 };
 
 // kzg.go:43-64 / 73-116 + fk20_single.go:40-56 toeplitzPart1
-static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out) {
+// file_begin / file_end: the chunk offsets whose xExtFFT files (and window tables) this handle holds; a rank of the
+// offset-sharded FK20 multi needs only its own (config 5 on 8 GPUs: 13 GB of tables per rank instead of 103 GB)
+static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out, size_t file_begin = 0, size_t file_end = (size_t)-1) {
     *out = nullptr;
     b200_fs* fs = ks->fs;
     if (n2 > fs->max_width) return B200_ERR_TOO_LARGE;       // kzg.go:44-46 / 74-76
@@ -976,20 +995,24 @@ static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk**
     b200_fk* fk = new (std::nothrow) b200_fk();
     if (!fk) return B200_ERR_CUDA;
     fk->ks = ks; fk->n2 = n2; fk->chunk_len = l; fk->device = fs->device;
+    if (file_end == (size_t)-1) file_end = l;
+    fk->file_begin = file_begin; fk->file_end = file_end;
+    const size_t m = file_end - file_begin;            // files held
     int rc = B200_OK;
     do {
-        if (cudaMalloc(&fk->d_x_ext_fft, l * k2 * sizeof(G1J)) != cudaSuccess) { rc = B200_ERR_CUDA; break; }
+        if (cudaMalloc(&fk->d_x_ext_fft, (m ? m : 1) * k2 * sizeof(G1J)) != cudaSuccess) { rc = B200_ERR_CUDA; break; }
+        if (m == 0) break;
         DevBuf work;
-        if ((rc = work.alloc(l * k2 * sizeof(G1J), st))) break;
-        launch_g1_fill_infinity(work.as<G1J>(), l * k2, st);
+        if ((rc = work.alloc(m * k2 * sizeof(G1J), st))) break;
+        launch_g1_fill_infinity(work.as<G1J>(), m * k2, st);
         // file `off`: x[i] = SecretG1[n - l - 1 - off - i l], i < k - 1; x[k-1 .. 2k-1] = infinity
-        launch_fk20_gather_x(ks->d_secret_g1, work.as<G1J>(), n, l, st);
+        launch_fk20_gather_x(ks->d_secret_g1, work.as<G1J>(), n, l, file_begin, m, st);
         // FFT_G1 of every file (forward), natural order result
-        if ((rc = dev_g1_fft_stages(fs, work.as<G1J>(), logk2, l, 1, k2, false, true, st))) break;
-        launch_g1_copy(fk->d_x_ext_fft, 1, k2, work.as<G1J>(), 1, k2, k2, l, 1, logk2, st);
+        if ((rc = dev_g1_fft_stages(fs, work.as<G1J>(), logk2, m, 1, k2, false, true, st))) break;
+        launch_g1_copy(fk->d_x_ext_fft, 1, k2, work.as<G1J>(), 1, k2, k2, m, 1, logk2, st);
         if ((rc = check_launches())) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "sync in fk20 settings"; rc = B200_ERR_CUDA; break; }
-        if ((rc = build_fixed_base(fk->d_x_ext_fft, l * k2, &fk->d_fb_table, &fk->fb_w, st))) break;
+        if ((rc = build_fixed_base(fk->d_x_ext_fft, m * k2, &fk->d_fb_table, &fk->fb_w, st))) break;
     } while (0);
     if (rc) { b200_fk20_settings_free(fk); return rc; }
     *out = fk;
@@ -1000,6 +1023,13 @@ extern "C" int b200_fk20_multi_settings_new(b200_ks* ks, size_t n2, size_t chunk
     if (chunk_len < 1) { *out = nullptr; return B200_ERR_TOO_SMALL; }   // kzg.go:89-91
     return fk20_settings_new(ks, n2, chunk_len, out);
 }
+// kzg.go:73-116 for the ranks of an offset-sharded FK20 multi: only the files [off_begin, off_end) are built and kept
+extern "C" int b200_fk20_multi_settings_new_sharded(b200_ks* ks, size_t n2, size_t chunk_len, size_t off_begin, size_t off_end, b200_fk** out) {
+    *out = nullptr;
+    if (chunk_len < 1) return B200_ERR_TOO_SMALL;
+    if (off_begin > off_end || off_end > chunk_len) return B200_ERR_BAD_INPUT;
+    return fk20_settings_new(ks, n2, chunk_len, out, off_begin, off_end);
+}
 extern "C" void b200_fk20_settings_free(b200_fk* fk) {
     if (!fk) return;
     cudaSetDevice(fk->device);
@@ -1008,9 +1038,10 @@ extern "C" void b200_fk20_settings_free(b200_fk* fk) {
     delete fk;
 }
 extern "C" int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out) {
-    if (file >= fk->chunk_len) return B200_ERR_BAD_INPUT;
+    if (file < fk->file_begin || file >= fk->file_end) return B200_ERR_BAD_INPUT;
     CK(cudaSetDevice(fk->ks->fs->device));
     const size_t k2 = fk->n2 / fk->chunk_len;
+    file -= fk->file_begin;
     StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw;
     CKS(raw.alloc(k2 * 144, st));
@@ -1039,6 +1070,7 @@ static int dev_fk20(b200_fk* fk, const uint64_t* d_polys, size_t n, size_t batch
                     uint8_t* d_comp = nullptr) {
     b200_fs* fs = fk->ks->fs;
     const size_t l = fk->chunk_len, k = n / l, k2 = 2 * k;
+    if (fk->file_begin != 0 || fk->file_end != l) return B200_ERR_BAD_INPUT;   // sharded settings hold some of the files only
     const unsigned logk2 = log2u(k2);
     DevBuf c, h, tmp;
     CKS(c.alloc(batch * l * k2 * sizeof(Fr), st));
@@ -1151,6 +1183,7 @@ extern "C" int b200_fk20_multi_partial_dev(b200_fk* fk, const void* d_poly, size
     if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
     const size_t l = fk->chunk_len, k = n / l, k2 = 2 * k;
     if (off_begin > off_end || off_end > l) return B200_ERR_BAD_INPUT;
+    if (off_begin < off_end && (off_begin < fk->file_begin || off_end > fk->file_end)) return B200_ERR_BAD_INPUT;   // files this handle does not hold
     CK(cudaSetDevice(fk->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     b200_fs* fs = fk->ks->fs;
@@ -1165,8 +1198,9 @@ extern "C" int b200_fk20_multi_partial_dev(b200_fk* fk, const void* d_poly, size
     Fr scale = fr_inv_of_u64(k2);     // the inverse transform's 1/2k, as in dev_fk20
     Fr* c_mine = c.as<Fr>() + off_begin * k2;
     launch_fr_ntt(fs->dom, c_mine, c_mine, tmp.as<Fr>(), logk2, m, false, &scale, st);
-    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table + off_begin * k2 * fixed_base_row_entries(fk->fb_w), fk->fb_w, c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
-    else launch_g1_mul_var(fk->d_x_ext_fft + off_begin * k2, 0, c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
+    const size_t rel = off_begin - fk->file_begin;
+    if (fk->d_fb_table) launch_g1_mul_fixed_base(fk->d_fb_table + rel * k2 * fixed_base_row_entries(fk->fb_w), fk->fb_w, c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
+    else launch_g1_mul_var(fk->d_x_ext_fft + rel * k2, 0, c_mine, 1, h.as<G1J>(), m * k2, m * k2, 1, st);
     // sum the m files: fold the tail onto the head until one file is left (m need not be a power of two)
     for (size_t cnt = m; cnt > 1;) {
         size_t half = (cnt + 1) / 2;
@@ -1248,11 +1282,14 @@ extern "C" int b200_fk20_multi_finish_local_dev(b200_fk* fk, const void* d_h_ext
     }
     G1J* block = (G1J*)d_block;
     if (s == 0) CK(cudaMemcpyAsync(block, cur, k2 * sizeof(G1J), cudaMemcpyDeviceToDevice, st));
-    for (size_t mm = blk / 2; mm >= 1; mm >>= 1) launch_g1_fft_stage(block, blk / 2, 1, mm, 1, blk, true, inv_progs, halfw / mm, st);
+    StagePrograms spi, spf;
+    CKS(fs_stage_programs(fs, 1, 1, &spi));
+    CKS(fs_stage_programs(fs, 0, 1, &spf));
+    for (size_t mm = blk / 2; mm >= 1; mm >>= 1) launch_stage_auto(spi, block, blk / 2, 1, mm, 1, blk, true, halfw / mm, st);
     G1J* d_inf = nullptr;
     CKS(dev_infinity(&d_inf));
     launch_g1_copy(block + 1, 2, blk, d_inf, 0, 0, blk / 2, 1, 0, 0, st);
-    for (size_t mm = 1; mm <= blk / 2; mm <<= 1) launch_g1_fft_stage(block, blk / 2, 1, mm, 1, blk, false, fwd_progs, halfw / mm, st);
+    for (size_t mm = 1; mm <= blk / 2; mm <<= 1) launch_stage_auto(spf, block, blk / 2, 1, mm, 1, blk, false, halfw / mm, st);
     (void)logblk;
     return check_launches();
 }
@@ -1270,7 +1307,9 @@ extern "C" int b200_fk20_multi_finish_merge_dev(b200_fk* fk, const void* d_block
     DevBuf h;
     CKS(h.alloc(k2 * sizeof(G1J), st));
     CK(cudaMemcpyAsync(h.p, d_blocks, k2 * sizeof(G1J), cudaMemcpyDeviceToDevice, st));
-    for (size_t mm = k2 / world; mm <= k2 / 2; mm <<= 1) launch_g1_fft_stage(h.as<G1J>(), k2 / 2, 1, mm, 1, k2, false, fwd_progs, halfw / mm, st);
+    StagePrograms spf;
+    CKS(fs_stage_programs(fs, 0, 1, &spf));
+    for (size_t mm = k2 / world; mm <= k2 / 2; mm <<= 1) launch_stage_auto(spf, h.as<G1J>(), k2 / 2, 1, mm, 1, k2, false, halfw / mm, st);
     launch_g1_to_abi(h.as<G1J>(), (uint64_t*)d_proofs, k2, 1, 1, k2, reverse_bits ? 1 : 0, logk2, st);
     return check_launches();
 }

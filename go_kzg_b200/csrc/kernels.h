@@ -100,8 +100,10 @@ void launch_g1_compress(const G1J* in, uint8_t* out48, size_t n, size_t batch, s
 // one radix-2 stage over batch transforms of 2 * n_half points each; element i of blob b lives at
 // data[b * bstride + i * estride]; m = half block length of this stage.  DIT: (x0 + w x1, x0 - w x1),
 // DIF: (x0 + x1, w (x0 - x1)), w = progs[j * prog_stride] for position j inside the block.
+// across_blocks != 0 (needs n_half / m a multiple of 32): lanes run over the blocks of the stage, so that the 32 lanes of a warp
+// share the twiddle w^j even for a single transform; progs must then be the sparse (mode 1) programs
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
-                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st);
+                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks = 0);
 // DIF stage of one transform keeping one half of the outputs: out[i] = in[i] + in[i + m] (lower = 0) or
 // progs[i * prog_stride] * (in[i] - in[i + m]) (lower = 1), i < m
 void launch_g1_dif_half_stage(const G1J* in, G1J* out, size_t m, int lower, const ScalarProgram* progs, size_t prog_stride, cudaStream_t st);
@@ -135,9 +137,9 @@ void launch_g1_decompress(const uint8_t* in48, uint64_t* out_abi, uint32_t* stat
 // dst[b*dst_bstride + i*dst_estride] = src[b*src_bstride + idx(i)*src_estride]
 void launch_g1_copy(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J* src, size_t src_estride,
                     size_t src_bstride, size_t n, size_t batch, int bitrev, unsigned logn, cudaStream_t st);
-// kzg.go:57-61 / 103-109: work[off * 2k + i] = S[n - l - 1 - off - i l] for i < k - 1 (k = n / l);
-// the rest of work (pre-filled) stays infinity
-void launch_fk20_gather_x(const G1J* secret_g1, G1J* work, size_t n, size_t l, cudaStream_t st);
+// kzg.go:57-61 / 103-109 for the chunk offsets off0 .. off0 + files - 1: work[f * 2k + i] = S[n - l - 1 - (off0 + f) - i l]
+// for i < k - 1 (k = n / l); the rest of work (pre-filled) stays infinity
+void launch_fk20_gather_x(const G1J* secret_g1, G1J* work, size_t n, size_t l, size_t off0, size_t files, cudaStream_t st);
 // Pippenger bucket MSM over variable bases (kernels_msm.cu): *out = sum_i k[i] pts[i]; workspace of msm_workspace_bytes(n)
 size_t msm_workspace_bytes(size_t n);
 void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* workspace, G1J* out, cudaStream_t st);

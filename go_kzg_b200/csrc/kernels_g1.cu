@@ -223,17 +223,28 @@ void launch_g1_decompress(const uint8_t* in48, uint64_t* out_abi, uint32_t* stat
 // ------------------------------------------------------------------------------ FFT stage
 // thread <-> (butterfly q, blob b) with b fastest: when batch is a multiple of 32 every lane of a
 // warp runs the same twiddle program on a different blob, so the digit branches are uniform.
+// across_blocks (few transforms, at least 32 blocks in this stage): lanes run over the BLOCKS of the stage instead, so a
+// warp again holds 32 butterflies with one and the same twiddle w^j and can use the sparse (width-5 NAF) programs.
 template <bool DIF>
 __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
                                                       size_t bstride, const ScalarProgram* __restrict__ progs,
-                                                      size_t prog_stride) {
-    // lanes of a butterfly: the batch, padded to whole warps (idle lanes) so that a warp never mixes twiddles
-    const size_t lanes = g1_lanes_for_batch(batch);
+                                                      size_t prog_stride, int across_blocks) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_half * lanes) return;
-    size_t b = t % lanes, q = t / lanes;
-    if (b >= batch) return;
-    size_t j = q & (m - 1);
+    size_t b, q, j;
+    if (across_blocks) {
+        const size_t nblocks = n_half / m;                     // multiple of 32
+        if (t >= n_half * batch) return;
+        const size_t blk = t % nblocks, r = t / nblocks;
+        b = r % batch; j = r / batch;
+        q = blk * m + j;
+    } else {
+        // lanes of a butterfly: the batch, padded to whole warps (idle lanes) so that a warp never mixes twiddles
+        const size_t lanes = g1_lanes_for_batch(batch);
+        if (t >= n_half * lanes) return;
+        b = t % lanes; q = t / lanes;
+        if (b >= batch) return;
+        j = q & (m - 1);
+    }
     size_t i0 = 2 * q - j, i1 = i0 + m;
     G1J* p0 = data + b * bstride + i0 * estride;
     G1J* p1 = data + b * bstride + i1 * estride;
@@ -252,12 +263,12 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage(G1J* data, s
     }
 }
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
-                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st) {
+                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks) {
     ProfScope prof_scope(PROF_G1_FFT_STAGE, st);
-    size_t total = n_half * g1_lanes_for_batch(batch);
+    size_t total = across_blocks ? n_half * batch : n_half * g1_lanes_for_batch(batch);
     if (!total || !batch) return;
-    if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
-    else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride);
+    if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
+    else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
     g_launch_count++;
 }
 
@@ -563,18 +574,18 @@ void launch_g1_copy(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J*
     g_launch_count++;
 }
 
-__global__ void k_fk20_gather_x(const G1J* __restrict__ S, G1J* __restrict__ work, size_t n, size_t l) {
+__global__ void k_fk20_gather_x(const G1J* __restrict__ S, G1J* __restrict__ work, size_t n, size_t l, size_t off0, size_t files) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t k = n / l;
-    if (k < 2 || t >= (k - 1) * l) return;
-    size_t off = t / (k - 1), i = t % (k - 1);
-    st_vec(work + off * 2 * k + i, ld_vec(S + (n - l - 1 - off - i * l)));
+    if (k < 2 || t >= (k - 1) * files) return;
+    size_t f = t / (k - 1), i = t % (k - 1), off = off0 + f;
+    st_vec(work + f * 2 * k + i, ld_vec(S + (n - l - 1 - off - i * l)));
 }
-void launch_fk20_gather_x(const G1J* secret_g1, G1J* work, size_t n, size_t l, cudaStream_t st) {
+void launch_fk20_gather_x(const G1J* secret_g1, G1J* work, size_t n, size_t l, size_t off0, size_t files, cudaStream_t st) {
     ProfScope prof_scope(PROF_MISC, st);
     size_t k = n / l;
-    if (k < 2) return;
-    k_fk20_gather_x<<<grid_for((k - 1) * l, 256), 256, 0, st>>>(secret_g1, work, n, l); g_launch_count++;
+    if (k < 2 || !files) return;
+    k_fk20_gather_x<<<grid_for((k - 1) * files, 256), 256, 0, st>>>(secret_g1, work, n, l, off0, files); g_launch_count++;
 }
 
 // ------------------------------------------------------------------------------ self test

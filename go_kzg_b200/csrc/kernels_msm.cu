@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan p, const G1J*
     const size_t bucket = g / p.S;                 // w * B + (b - 1)
     const unsigned slice = (unsigned)(g % p.S);
     G1J acc = G1J::infinity();
+    unsigned qw = 0;
+    uint32_t qbegin = 0, qcount = 0;
     if (bucket < nb) {
         const unsigned w = (unsigned)(bucket / p.B), b = (unsigned)(bucket % p.B) + 1;
         const size_t slot = (size_t)w * (p.B + 1) + b;
@@ -93,63 +95,55 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan p, const G1J*
         uint32_t begin = slice * per, end = begin + per;
         if (begin > len) begin = len;
         if (end > len) end = len;
-        if (!QUAD) {
-            msm_accumulate_slice(p, pts, bx, sorted + (size_t)w * p.T, off + begin, off + end, *not_affine == 0, &acc);
-        } else {
-            const bool affine = *not_affine == 0;
-            const uint32_t* sw = sorted + (size_t)w * p.T;
-            for (uint32_t e = off + begin; e < off + end; e++) {
-                const uint32_t u = sw[e];
+        if (!QUAD) msm_accumulate_slice(p, pts, bx, sorted + (size_t)w * p.T, off + begin, off + end, *not_affine == 0, &acc);
+        qw = w; qbegin = off + begin; qcount = end - begin;
+    }
+    if (QUAD) {
+        // warp-collective quad operations: every quad walks max(count over the warp) steps, idle ones pass active = false
+        const bool affine = *not_affine == 0;
+        const uint32_t* sw = sorted + (size_t)qw * p.T;
+        const uint32_t steps = __reduce_max_sync(0xffffffffu, qcount);
+        for (uint32_t k = 0; k < steps; k++) {
+            const bool act = k < qcount;
+            G1J q = G1J::infinity();
+            if (act) {
+                const uint32_t u = sw[qbegin + k];
                 const size_t t = u & 0x7fffffffu;
                 const bool second = t >= p.n;
                 const size_t i = second ? t - p.n : t;
                 const bool neg = ((u >> 31) != 0) != second;
-                G1J q;
                 q.x = second ? ld_vec(bx + i) : ld_vec(&pts[i].x);
                 q.y = ld_vec(&pts[i].y);
                 if (neg) q.y = fe_neg(q.y);
-                if (affine) {
-                    G1A qa; qa.x = q.x; qa.y = q.y;
-                    quad_add_mixed(&acc, &acc, &qa);
-                } else {
-                    q.z = ld_vec(&pts[i].z);
-                    quad_add(&acc, &acc, &q);
-                }
+                if (!affine) q.z = ld_vec(&pts[i].z);
+            }
+            if (affine) {
+                G1A qa; qa.x = q.x; qa.y = q.y;
+                quad_add_mixed(&acc, &qa, act);
+            } else {
+                quad_add(&acc, &q, act);
             }
         }
     }
     // the slices of a bucket: adjacent lanes (thread units) or adjacent quads (quad units); whole warps get here
     if (!QUAD) {
         if (p.S > 1) g1_warp_sum(acc, p.S);
-    } else {
-        for (unsigned off = (p.S * 4) >> 1; off >= 4; off >>= 1) {
-            G1J other = quad_shfl_xor(acc, off);
-            quad_add(&acc, &acc, &other);
-        }
+    } else if (p.S > 1) {
+        quad_group_sum(acc, p.S);
     }
     if (bucket < nb && slice == 0 && (!QUAD || (threadIdx.x & 3u) == 0)) st_vec(buckets + bucket, acc);
 }
 
-// ---- step 5: quad = (window, segment of L buckets) -----------------------------------------------------------
+// ---- step 5: thread = (window, segment of L buckets) ---------------------------------------------------------
+// (a quad per segment was measured slower here: the collective small multiplication runs an addition on every bit)
 __global__ void __launch_bounds__(128, 4) k_msm_segments(MsmPlan p, const G1J* __restrict__ buckets, G1J* __restrict__ segs) {
-    const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned nseg = p.B / p.L;
-    if (g >= (size_t)p.W * nseg) return;             // whole quads leave together
+    if (g >= (size_t)p.W * nseg) return;
     const unsigned w = (unsigned)(g / nseg), s = (unsigned)(g % nseg);
-    const G1J* bkt = buckets + (size_t)w * p.B;
-    const unsigned b0 = s * p.L + 1;
-    G1J running = G1J::infinity(), acc = G1J::infinity();
-    for (int j = (int)p.L - 1; j >= 0; j--) {        // msm_reduce_segment with quad operations
-        G1J v = ld_vec(bkt + (b0 - 1 + j));
-        quad_add(&running, &running, &v);
-        quad_add(&acc, &acc, &running);
-    }
-    if (b0 > 1 && !running.is_inf()) {
-        G1J m;
-        quad_small_mul(&m, &running, b0 - 1);
-        quad_add(&acc, &acc, &m);
-    }
-    if ((threadIdx.x & 3u) == 0) st_vec(segs + g, acc);
+    G1J out;
+    msm_reduce_segment(buckets + (size_t)w * p.B, s * p.L + 1, p.L, &out);
+    st_vec(segs + g, out);
 }
 
 // ---- step 6: one CTA (32 quads) per window: sum of the window's segments ----------------------------------------
@@ -157,15 +151,17 @@ __global__ void __launch_bounds__(128) k_msm_windows(MsmPlan p, const G1J* __res
     __shared__ G1J part[4];
     const unsigned w = blockIdx.x, tid = threadIdx.x, quad = tid >> 2, nseg = p.B / p.L;
     G1J acc = G1J::infinity();
-    for (unsigned s = quad; s < nseg; s += 32) {
-        G1J v = ld_vec(segs + (size_t)w * nseg + s);
-        quad_add(&acc, &acc, &v);
+    for (unsigned base = 0; base < nseg; base += 32) {
+        const unsigned s = base + quad;
+        const bool act = s < nseg;
+        G1J v = act ? ld_vec(segs + (size_t)w * nseg + s) : G1J::infinity();
+        quad_add(&acc, &v, act);
     }
     quad_warp_sum(acc);
     if ((tid & 31) == 0) part[tid >> 5] = acc;
     __syncthreads();
-    if (tid < 4) {                                   // quad 0
-        for (unsigned j = 1; j < 4; j++) { G1J v = part[j]; quad_add(&acc, &acc, &v); }
+    if (tid < 32) {                                  // warp 0, every quad redundantly
+        for (unsigned j = 1; j < 4; j++) { G1J v = part[j]; quad_add(&acc, &v, true); }
         if (tid == 0) st_vec(wsums + w, acc);
     }
 }
@@ -175,22 +171,22 @@ __global__ void __launch_bounds__(160) k_msm_horner(MsmPlan p, const G1J* __rest
     __shared__ G1J part[5];
     const unsigned tid = threadIdx.x, w = tid >> 2;
     G1J acc = G1J::infinity();
-    if (w < p.W) {
-        acc = ld_vec(wsums + w);
-        for (unsigned d = 0; d < p.c * w && !acc.is_inf(); d++) quad_dbl(&acc, &acc);
-    }
+    unsigned dbls = 0;
+    if (w < p.W) { acc = ld_vec(wsums + w); dbls = p.c * w; }
+    const unsigned steps = __reduce_max_sync(0xffffffffu, dbls);
+    for (unsigned d = 0; d < steps; d++) quad_dbl(&acc, d < dbls);
     quad_warp_sum(acc);
     const unsigned nwarp = blockDim.x >> 5;
     if ((tid & 31) == 0) part[tid >> 5] = acc;
     __syncthreads();
-    if (tid < 4) {
-        for (unsigned j = 1; j < nwarp; j++) { G1J v = part[j]; quad_add(&acc, &acc, &v); }
+    if (tid < 32) {
+        for (unsigned j = 1; j < nwarp; j++) { G1J v = part[j]; quad_add(&acc, &v, true); }
         if (tid == 0) st_vec(out, acc);
     }
 }
 
-// a quad per (bucket, slice) unit while the accumulation then still fits about one wave of the chip
-static const size_t kMsmQuadUnits = (size_t)148 * 2048;
+// a quad per (bucket, slice) unit only while the expanded launch stays at about one warp per SM sub-partition
+static const size_t kMsmQuadUnits = (size_t)148 * 4 * 32;   // one warp per SM sub-partition
 
 // ---- workspace layout -------------------------------------------------------------------------------------
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -239,9 +235,11 @@ void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* w
     k_msm_scan<<<p.W, 1024, 0, st>>>(p, ws.counts, ws.offsets);
     k_msm_scatter<<<grid_for((size_t)p.W * p.T, 256), 256, 0, st>>>(p, ws.digits, ws.offsets, ws.cursors, ws.sorted);
     const size_t units = (size_t)p.W * p.B * p.S;
+    // a quad per unit only pays when the expanded launch is still a fraction of one wave (measured at n = 4096: 213 k
+    // quad lanes take 1.16 ms where 53 k thread units take 0.24 ms -- a warp instruction costs the same with 8 points as with 32)
     if (units * 4 <= kMsmQuadUnits && p.S <= 8) k_msm_accumulate<true><<<grid_for(units * 4, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
     else k_msm_accumulate<false><<<grid_for(units, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
-    k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L) * 4, 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
+    k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L), 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
     k_msm_windows<<<p.W, 128, 0, st>>>(p, ws.segs, ws.wsums);
     k_msm_horner<<<1, (unsigned)((p.W * 4 + 31) / 32 * 32), 0, st>>>(p, ws.wsums, out);
     g_launch_count += 7;

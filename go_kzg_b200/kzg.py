@@ -115,6 +115,7 @@ def lib():
     L.b200_commit_to_poly_batch.argtypes = [vp, vp, sz, sz, vp]
     L.b200_fk20_single_settings_new.argtypes = [vp, sz, C.POINTER(vp)]
     L.b200_fk20_multi_settings_new.argtypes = [vp, sz, sz, C.POINTER(vp)]
+    L.b200_fk20_multi_settings_new_sharded.argtypes = [vp, sz, sz, sz, sz, C.POINTER(vp)]
     L.b200_fk20_settings_free.argtypes = [vp]
     L.b200_fk20_settings_free.restype = None
     L.b200_fk20_x_ext_fft.argtypes = [vp, sz, vp]
@@ -600,10 +601,16 @@ class FK20SingleSettings(_FK20Base):
 class FK20MultiSettings(_FK20Base):
     """kzg.go:66-116"""
 
-    def __init__(self, ks: KZGSettings, n2: int, chunk_len: int):
+    def __init__(self, ks: KZGSettings, n2: int, chunk_len: int, offsets: range = None):
+        """offsets: build and keep only the xExtFFT files of these chunk offsets (one rank of the offset-sharded
+        multi-GPU form, go_kzg_b200/multi_gpu.py); default: all of them, as kzg.go:73-116 does."""
         h = C.c_void_p()
-        _raise(lib().b200_fk20_multi_settings_new(ks.h, n2, chunk_len, C.byref(h)), what="NewFK20MultiSettings")
-        self.h, self.ks, self.n2, self.chunk_len = h, ks, n2, chunk_len
+        if offsets is None:
+            _raise(lib().b200_fk20_multi_settings_new(ks.h, n2, chunk_len, C.byref(h)), what="NewFK20MultiSettings")
+        else:
+            _raise(lib().b200_fk20_multi_settings_new_sharded(ks.h, n2, chunk_len, offsets.start, offsets.stop, C.byref(h)),
+                   what="NewFK20MultiSettings (sharded)")
+        self.h, self.ks, self.n2, self.chunk_len, self.offsets = h, ks, n2, chunk_len, offsets
 
     def fk20_multi_da_optimized(self, poly) -> np.ndarray:
         """fk20_multi.go:58-109: n2 coefficients (upper half zero) -> 2k proofs"""

@@ -159,6 +159,10 @@ int b200_check_proof_multi_g1_batch(b200_ks* ks, const uint64_t* commitments, co
 int b200_fk20_single_settings_new(b200_ks* ks, size_t n2, b200_fk** out);
 /* kzg.go:73-116 NewFK20MultiSettings(ks, n2, chunkLen) */
 int b200_fk20_multi_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out);
+/* The same for one rank of the offset-sharded FK20 multi (multi-GPU building blocks below): only the xExtFFT files of
+ * the chunk offsets [off_begin, off_end) and their window tables are built and kept; such a handle serves
+ * b200_fk20_multi_partial_dev for those offsets and the finish calls, not the whole-polynomial entry points. */
+int b200_fk20_multi_settings_new_sharded(b200_ks* ks, size_t n2, size_t chunk_len, size_t off_begin, size_t off_end, b200_fk** out);
 void b200_fk20_settings_free(b200_fk* fk);
 /* copy of xExtFFT (file `file`, n2 / chunk_len points) -- for tests */
 int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out);
