@@ -367,3 +367,54 @@ def test_toeplitz_part2_part3_standalone(goldens):
     cmp_g1(fs.fft_g1(h), fk.fk20_single(kzg.fr_from_ints(poly)))
     with pytest.raises(kzg.KZGPanic):                                     # fk20_single.go:60-62
         fs.toeplitz_part2(coeffs[:16], fk.x_ext_fft())
+
+
+def test_fk20_multi_settings_sharded_by_offset():
+    """Per-rank FK20 multi settings (only the files of the rank's chunk offsets): partial hExtFFT per rank -> G1 sum
+    -> finish == DAUsingFK20Multi of full settings; whole-polynomial entry points refuse a partial handle."""
+    import torch
+    from go_kzg_b200 import multi_gpu
+    secret, l, cc = 1927409816240961209460912649124, 16, 32
+    n = l * cc
+    scale = (2 * n).bit_length() - 1
+    fs = kzg.FFTSettings(scale)
+    ks = kzg.KZGSettings(fs, kzg.generate_testing_setup_g1(secret, 2 * n))
+    full = kzg.FK20MultiSettings(ks, 2 * n, l)
+    poly = kzg.fr_from_ints(random_fr_ints(n, 31))
+    want = full.da_using_fk20_multi(poly)
+    L, k2, world = kzg.lib(), 2 * cc, 3
+    d_poly = torch.from_numpy(poly.view(np.int64)).cuda()
+    parts = torch.zeros((world, k2, 18), dtype=torch.int64, device="cuda")
+    last = None
+    for r in range(world):
+        mine = multi_gpu.offset_range(r, world, l)
+        fk_r = kzg.FK20MultiSettings(ks, 2 * n, l, offsets=mine)
+        cmp_g1(fk_r.x_ext_fft(mine.start), full.x_ext_fft(mine.start))
+        assert L.b200_fk20_multi_partial_dev(fk_r.h, d_poly.data_ptr(), n, mine.start, mine.stop, parts[r].data_ptr(), None) == 0
+        other = (mine.stop % l)
+        if other not in mine:
+            assert L.b200_fk20_multi_partial_dev(fk_r.h, d_poly.data_ptr(), n, other, other + 1, parts[r].data_ptr(), None) != 0
+        last = fk_r
+    d_sum = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+    assert L.b200_g1_sum_dev(parts.data_ptr(), world, k2, d_sum.data_ptr(), None) == 0
+    d_out = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+    assert L.b200_fk20_multi_finish_dev(last.h, d_sum.data_ptr(), 1, d_out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    cmp_g1(d_out.cpu().numpy().view(np.uint64), want)
+    with pytest.raises(kzg.KZGPanic):
+        last.da_using_fk20_multi(poly)
+
+
+def test_single_transform_lane_mappings_agree():
+    """One transform uses three lane mappings over its stages (across blocks with sparse programs while a stage has
+    at least 32 blocks, per-lane fixed windows for the rest); batches of 16+ use whole-warp lanes.  Same input through
+    batch 1, 3 (below the whole-warp switch) and 16 must give identical bytes, at a size with many across-block stages."""
+    n, scale = 2048, 11
+    ks, pts = _random_points(n, 2048, False)
+    fs, fo = kzg.FFTSettings(scale), cref.FFTSettings(scale)
+    for inv in (False, True):
+        want = cref.g1_compress(cref.g1_mul_gen(cref.limbs_to_fr(fo.fft(cref.fr_to_limbs(ks), inv))))
+        assert np.array_equal(kzg.g1_to_compressed(fs.fft_g1(pts, inv)), want)
+        for batch in (3, 16):
+            out = fs.fft_g1_batch(np.stack([pts] * batch), inv)
+            assert np.array_equal(kzg.g1_to_compressed(out[batch - 1]), want)
