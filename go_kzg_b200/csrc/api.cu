@@ -617,6 +617,51 @@ extern "C" int b200_fft_g1_batch(b200_fs* fs, const uint64_t* vals, size_t n, si
 extern "C" int b200_fft_g1(b200_fs* fs, const uint64_t* vals, size_t n, int inverse, uint64_t* out) {
     return host_fft_g1(fs, vals, n, 1, inverse, out, n);
 }
+// das_extension.go:7-84 over G1 -- the "G1 version of the DAS extension FFT" of the TODO at fk20_multi.go:96: given the
+// even-index evaluations of a polynomial of degree < n over G1, the odd-index ones.  Same butterfly network as the Fr form
+// (kernels_fr.cu: descent = inverse DIF stages down to pairs, a middle butterfly with the root Exp[n / 2], ascent = DIT
+// stages with the odd roots Exp[(1 + 2 i) n / L], finally 1 / n), run with the G1 stage kernel; roots are indexed on
+// the full domain with stride 1 whatever n is, like the reference.  In place, n a power of two >= 2, 2 n <= MaxWidth.
+// (The FK20 pipelines do not use it: they hold the COEFFICIENTS h, for which the zero-padded transform costs one twist
+// plus two half-size transforms -- fewer multiplications than a transform plus this extension.  DESIGN.md section 3.)
+extern "C" int b200_das_fft_extension_g1(b200_fs* fs, uint64_t* vals, size_t n) {
+    if (n * 2 > fs->max_width) return B200_ERR_TOO_SMALL;   // das_extension.go:72-74
+    if (n < 2 || !is_pow2(n)) return B200_ERR_BAD_INPUT;    // das_extension.go:22-24 "bad usage"
+    CK(cudaSetDevice(fs->device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    const unsigned logn = log2u(n);
+    DevBuf raw, buf, prog;
+    CKS(raw.alloc(n * 144, st)); CKS(buf.alloc(n * sizeof(G1J), st));
+    CK(cudaMemcpyAsync(raw.p, vals, n * 144, cudaMemcpyHostToDevice, st));
+    launch_g1_from_abi(raw.as<uint64_t>(), buf.as<G1J>(), n, st);
+    StagePrograms spi, spf;
+    CKS(fs_stage_programs(fs, 1, 1, &spi));
+    CKS(fs_stage_programs(fs, 0, 1, &spf));
+    G1J* d = buf.as<G1J>();
+    for (size_t m = n / 2; m >= 2; m >>= 1)                  // descent: (a0 + a1, (a0 - a1) Rev[i n / m]), i < m
+        launch_stage_auto(spi, d, n / 2, 1, m, 1, n, true, n / m, st);
+    {                                                        // pairs: x = a0 + a1, t = (a0 - a1) Exp[n / 2]; (x + t, x - t)
+        StagePrograms mid = {spf.per_lane + n / 2, spf.shared + n / 2};
+        launch_stage_auto(mid, d, n / 2, 1, 1, 1, n, true, 0, st);
+        launch_stage_auto(spf, d, n / 2, 1, 1, 1, n, false, 0, st);
+    }
+    for (size_t m = 2; m <= n / 2; m <<= 1) {                // ascent: (a0 + a1 Exp[(1 + 2 i) n / (2 m)], a0 - ..), i < m
+        StagePrograms odd = {spf.per_lane + n / (2 * m), spf.shared + n / (2 * m)};
+        launch_stage_auto(odd, d, n / 2, 1, m, 1, n, false, n / m, st);
+    }
+    ScalarProgram sp;
+    make_scalar_program(&sp, fe_from_mont(fr_inv_of_u64(n)), 1);
+    CKS(prog.alloc(sizeof(ScalarProgram), st));
+    CK(cudaMemcpyAsync(prog.p, &sp, sizeof sp, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                           // sp lives on this stack frame
+    launch_g1_mul_programs(d, n, 1, 1, n, prog.as<ScalarProgram>(), 0, 0, logn, st);
+    launch_g1_to_abi(d, raw.as<uint64_t>(), n, 1, 1, n, 0, 0, st);
+    CKS(check_launches());
+    CK(cudaMemcpyAsync(vals, raw.p, n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
 // fk20_single.go:80-87 ToeplitzPart3: inverse FFTG1, first half of the result (n2 / 2 points)
 extern "C" int b200_toeplitz_part3(b200_fs* fs, const uint64_t* h_ext_fft, size_t n2, uint64_t* out) {
     return host_fft_g1(fs, h_ext_fft, n2, 1, 1, out, n2 / 2);
@@ -979,7 +1024,9 @@ struct b200_fk {
 // kzg.go:43-64 / 73-116 + fk20_single.go:40-56 toeplitzPart1
 // file_begin / file_end: the chunk offsets whose xExtFFT files (and window tables) this handle holds; a rank of the
 // offset-sharded FK20 multi needs only its own (config 5 on 8 GPUs: 13 GB of tables per rank instead of 103 GB)
-static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out, size_t file_begin = 0, size_t file_end = (size_t)-1) {
+// x_ext_fft_host: previously exported files (b200_fk20_x_ext_fft) to adopt instead of recomputing them (setup cache)
+static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk** out, size_t file_begin = 0, size_t file_end = (size_t)-1,
+                             const uint64_t* x_ext_fft_host = nullptr) {
     *out = nullptr;
     b200_fs* fs = ks->fs;
     if (n2 > fs->max_width) return B200_ERR_TOO_LARGE;       // kzg.go:44-46 / 74-76
@@ -1004,6 +1051,14 @@ static int fk20_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_fk**
         if (m == 0) break;
         DevBuf work;
         if ((rc = work.alloc(m * k2 * sizeof(G1J), st))) break;
+        if (x_ext_fft_host) {
+            if (cudaMemcpyAsync(work.p, x_ext_fft_host, m * k2 * 144, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = B200_ERR_CUDA; break; }
+            launch_g1_from_abi(work.as<uint64_t>(), fk->d_x_ext_fft, m * k2, st);
+            if ((rc = check_launches())) break;
+            if (cudaStreamSynchronize(st) != cudaSuccess) { g_cuda_err = "sync in fk20 settings"; rc = B200_ERR_CUDA; break; }
+            if ((rc = build_fixed_base(fk->d_x_ext_fft, m * k2, &fk->d_fb_table, &fk->fb_w, st))) break;
+            break;
+        }
         launch_g1_fill_infinity(work.as<G1J>(), m * k2, st);
         // file `off`: x[i] = SecretG1[n - l - 1 - off - i l], i < k - 1; x[k-1 .. 2k-1] = infinity
         launch_fk20_gather_x(ks->d_secret_g1, work.as<G1J>(), n, l, file_begin, m, st);
@@ -1029,6 +1084,16 @@ extern "C" int b200_fk20_multi_settings_new_sharded(b200_ks* ks, size_t n2, size
     if (chunk_len < 1) return B200_ERR_TOO_SMALL;
     if (off_begin > off_end || off_end > chunk_len) return B200_ERR_BAD_INPUT;
     return fk20_settings_new(ks, n2, chunk_len, out, off_begin, off_end);
+}
+// Settings from cached xExtFFT files (the output of b200_fk20_x_ext_fft for the offsets [off_begin, off_end), concatenated):
+// skips the G1 transforms of kzg.go:57-62 / 101-114; the window tables are rebuilt (seconds of device time, faster than reading them).
+// The caller vouches that the files belong to `ks` (key the cache by a digest of the setup, as go_kzg_b200/kzg.py does).
+extern "C" int b200_fk20_settings_new_from_x_ext_fft(b200_ks* ks, size_t n2, size_t chunk_len, size_t off_begin, size_t off_end,
+                                                     const uint64_t* x_ext_fft, b200_fk** out) {
+    *out = nullptr;
+    if (chunk_len < 1) return B200_ERR_TOO_SMALL;
+    if (off_begin > off_end || off_end > chunk_len || !x_ext_fft) return B200_ERR_BAD_INPUT;
+    return fk20_settings_new(ks, n2, chunk_len, out, off_begin, off_end, x_ext_fft);
 }
 extern "C" void b200_fk20_settings_free(b200_fk* fk) {
     if (!fk) return;

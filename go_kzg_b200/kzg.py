@@ -105,6 +105,7 @@ def lib():
     L.b200_fft_g1_batch.argtypes = [vp, vp, sz, sz, i32, vp]
     L.b200_das_fft_extension.argtypes = [vp, vp, sz]
     L.b200_das_fft_extension_batch.argtypes = [vp, vp, sz, sz]
+    L.b200_das_fft_extension_g1.argtypes = [vp, vp, sz]
     L.b200_zero_poly_via_multiplication.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200_recover_poly_from_samples.argtypes = [vp, vp, vp, sz, vp]
     L.b200_recover_poly_from_samples_batch.argtypes = [vp, vp, vp, sz, sz, vp]
@@ -116,6 +117,7 @@ def lib():
     L.b200_fk20_single_settings_new.argtypes = [vp, sz, C.POINTER(vp)]
     L.b200_fk20_multi_settings_new.argtypes = [vp, sz, sz, C.POINTER(vp)]
     L.b200_fk20_multi_settings_new_sharded.argtypes = [vp, sz, sz, sz, sz, C.POINTER(vp)]
+    L.b200_fk20_settings_new_from_x_ext_fft.argtypes = [vp, sz, sz, sz, sz, vp, C.POINTER(vp)]
     L.b200_fk20_settings_free.argtypes = [vp]
     L.b200_fk20_settings_free.restype = None
     L.b200_fk20_x_ext_fft.argtypes = [vp, sz, vp]
@@ -421,6 +423,12 @@ class FFTSettings:
         _raise(lib().b200_das_fft_extension(self.h, _p(v), v.shape[0]), what="DASFFTExtension")
         return v
 
+    def das_fft_extension_g1(self, vals) -> np.ndarray:
+        """das_extension.go:71-84 over G1 points (fk20_multi.go:96 TODO): odd-index evaluations from the even ones."""
+        v = _g1(vals).copy()
+        _raise(lib().b200_das_fft_extension_g1(self.h, _p(v), v.shape[0]), what="DASFFTExtension (G1)")
+        return v
+
     def das_fft_extension_batch(self, vals) -> np.ndarray:
         v = np.ascontiguousarray(vals, dtype=np.uint64).copy()
         _raise(lib().b200_das_fft_extension_batch(self.h, _p(v), v.shape[1], v.shape[0]), what="DASFFTExtension")
@@ -462,6 +470,14 @@ class KZGSettings:
         n2 = g.shape[0] if secret_g2_len is None else secret_g2_len
         _raise(lib().b200_kzg_settings_new(fs.h, _p(g), g.shape[0], n2, C.byref(h)), what="NewKZGSettings")
         self.h, self.fs = h, fs
+        self._g1_bytes = g if g.shape[0] <= (1 << 16) else None   # for setup_digest(); large setups are hashed at construction
+        self._digest = None if self._g1_bytes is not None else _digest_points(g)
+
+    def setup_digest(self) -> str:
+        """SHA-256 of SecretG1 as handed in (ABI limbs) -- the key of the on-disk settings cache."""
+        if self._digest is None:
+            self._digest = _digest_points(self._g1_bytes)
+        return self._digest
 
     def close(self):
         if getattr(self, "h", None):
@@ -528,6 +544,39 @@ class KZGSettings:
         return out
 
 
+def _digest_points(g: np.ndarray) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(g, dtype=np.uint64).tobytes()).hexdigest()
+
+
+def _fk20_cached_handle(ks, n2: int, chunk_len: int, offsets, cache_dir: str, build):
+    """On-disk cache of the xExtFFT files (kzg.go:57-62, 101-114), keyed by a digest of the setup, the FFT width, n2,
+    the chunk length and the offsets.  build() -> handle computes them on the device; a cache hit adopts the stored
+    files through b200_fk20_settings_new_from_x_ext_fft (the window tables are rebuilt either way)."""
+    import hashlib
+    lo, hi = (0, chunk_len) if offsets is None else (offsets.start, offsets.stop)
+    key = hashlib.sha256(("%s|%d|%d|%d|%d|%d" % (ks.setup_digest(), ks.fs.max_scale, n2, chunk_len, lo, hi)).encode()).hexdigest()[:32]
+    path = os.path.join(cache_dir, "fk20_xextfft_%s.npy" % key)
+    k2 = n2 // chunk_len
+    if os.path.exists(path):
+        files = np.load(path)
+        if files.shape == (hi - lo, k2, 18) and files.dtype == np.uint64:
+            h = C.c_void_p()
+            _raise(lib().b200_fk20_settings_new_from_x_ext_fft(ks.h, n2, chunk_len, lo, hi, _p(np.ascontiguousarray(files)), C.byref(h)),
+                   what="FK20 settings from cache")
+            return h, True
+    h = build()
+    os.makedirs(cache_dir, exist_ok=True)
+    files = np.zeros((hi - lo, k2, 18), dtype=np.uint64)
+    for f in range(lo, hi):
+        _raise(lib().b200_fk20_x_ext_fft(h, f, _p(files[f - lo])))
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as fh:
+        np.save(fh, files)
+    os.replace(tmp, path)
+    return h, False
+
+
 class _FK20Base:
     def close(self):
         if getattr(self, "h", None):
@@ -552,9 +601,17 @@ class _FK20Base:
 class FK20SingleSettings(_FK20Base):
     """kzg.go:38-64"""
 
-    def __init__(self, ks: KZGSettings, n2: int):
-        h = C.c_void_p()
-        _raise(lib().b200_fk20_single_settings_new(ks.h, n2, C.byref(h)), what="NewFK20SingleSettings")
+    def __init__(self, ks: KZGSettings, n2: int, cache_dir: str = None):
+        """cache_dir: keep / reuse xExtFFT on disk (keyed by a digest of the setup); default: recompute, as kzg.go:43-64"""
+        def build():
+            h = C.c_void_p()
+            _raise(lib().b200_fk20_single_settings_new(ks.h, n2, C.byref(h)), what="NewFK20SingleSettings")
+            return h
+        self.from_cache = False
+        if cache_dir is None:
+            h = build()
+        else:
+            h, self.from_cache = _fk20_cached_handle(ks, n2, 1, None, cache_dir, build)
         self.h, self.ks, self.n2, self.chunk_len = h, ks, n2, 1
 
     def fk20_single(self, poly) -> np.ndarray:
@@ -601,15 +658,23 @@ class FK20SingleSettings(_FK20Base):
 class FK20MultiSettings(_FK20Base):
     """kzg.go:66-116"""
 
-    def __init__(self, ks: KZGSettings, n2: int, chunk_len: int, offsets: range = None):
+    def __init__(self, ks: KZGSettings, n2: int, chunk_len: int, offsets: range = None, cache_dir: str = None):
         """offsets: build and keep only the xExtFFT files of these chunk offsets (one rank of the offset-sharded
-        multi-GPU form, go_kzg_b200/multi_gpu.py); default: all of them, as kzg.go:73-116 does."""
-        h = C.c_void_p()
-        if offsets is None:
-            _raise(lib().b200_fk20_multi_settings_new(ks.h, n2, chunk_len, C.byref(h)), what="NewFK20MultiSettings")
+        multi-GPU form, go_kzg_b200/multi_gpu.py); default: all of them, as kzg.go:73-116 does.
+        cache_dir: keep / reuse the files on disk (keyed by a digest of the setup)."""
+        def build():
+            h = C.c_void_p()
+            if offsets is None:
+                _raise(lib().b200_fk20_multi_settings_new(ks.h, n2, chunk_len, C.byref(h)), what="NewFK20MultiSettings")
+            else:
+                _raise(lib().b200_fk20_multi_settings_new_sharded(ks.h, n2, chunk_len, offsets.start, offsets.stop, C.byref(h)),
+                       what="NewFK20MultiSettings (sharded)")
+            return h
+        self.from_cache = False
+        if cache_dir is None or chunk_len < 1 or n2 < 2 or (n2 & (n2 - 1)):
+            h = build()
         else:
-            _raise(lib().b200_fk20_multi_settings_new_sharded(ks.h, n2, chunk_len, offsets.start, offsets.stop, C.byref(h)),
-                   what="NewFK20MultiSettings (sharded)")
+            h, self.from_cache = _fk20_cached_handle(ks, n2, chunk_len, offsets, cache_dir, build)
         self.h, self.ks, self.n2, self.chunk_len, self.offsets = h, ks, n2, chunk_len, offsets
 
     def fk20_multi_da_optimized(self, poly) -> np.ndarray:

@@ -193,7 +193,7 @@ def measure_da_using_fk20_multi_sharded(scale: int = 21, chunk_len: int = 16, re
     bits = k2.bit_length() - 1
     brp = int(format(pos, "0%db" % bits)[::-1], 2)
     rbuf = np.zeros((1, 4), dtype=np.uint64)
-    L.b200_fr_root_of_unity(bits, rbuf.ctypes.data)            # w_k2 (bls/globals.go:27-60)
+    L.b200_fr_root_of_unity(scale, rbuf.ctypes.data)           # root of the full 2n domain: x = w_2n^brp(pos) (fk20_multi_test.go:60-64)
     root = kzg.fr_to_ints(rbuf)[0]
     xl = pow(pow(root, brp, R), chunk_len, R)
     acc = 0

@@ -126,6 +126,9 @@ int b200_evaluate_poly_in_evaluation_form_batch(b200_fs* fs, const uint64_t* pol
  * reference, is only meaningful for MaxWidth == 2 n). */
 int b200_das_fft_extension(b200_fs* fs, uint64_t* vals, size_t n);
 int b200_das_fft_extension_batch(b200_fs* fs, uint64_t* vals, size_t n, size_t batch);
+/* das_extension.go:71-84 over G1Points -- the "G1 version of the DAS extension FFT" the reference leaves as a TODO at
+ * fk20_multi.go:96: odd-index evaluations from the n even-index ones, in place; same checks as the Fr form. */
+int b200_das_fft_extension_g1(b200_fs* fs, uint64_t* vals, size_t n);
 /* zero_poly.go:116-217 ZeroPolyViaMultiplication -> (zeroEval[length], zeroPoly[length]) */
 int b200_zero_poly_via_multiplication(b200_fs* fs, const uint64_t* missing_indices, size_t n_missing, size_t length,
                                       uint64_t* zero_eval, uint64_t* zero_poly);
@@ -163,6 +166,11 @@ int b200_fk20_multi_settings_new(b200_ks* ks, size_t n2, size_t chunk_len, b200_
  * the chunk offsets [off_begin, off_end) and their window tables are built and kept; such a handle serves
  * b200_fk20_multi_partial_dev for those offsets and the finish calls, not the whole-polynomial entry points. */
 int b200_fk20_multi_settings_new_sharded(b200_ks* ks, size_t n2, size_t chunk_len, size_t off_begin, size_t off_end, b200_fk** out);
+/* Setup-time precompute as a cacheable artefact (kzg.go:101-114 costs 16 G1 transforms of 2^17 points
+ * per process at config 5): settings from xExtFFT files exported earlier with b200_fk20_x_ext_fft (offsets
+ * [off_begin, off_end), (off_end - off_begin) x n2 / chunk_len points, concatenated).  chunk_len = 1 gives single settings. */
+int b200_fk20_settings_new_from_x_ext_fft(b200_ks* ks, size_t n2, size_t chunk_len, size_t off_begin, size_t off_end,
+                                          const uint64_t* x_ext_fft, b200_fk** out);
 void b200_fk20_settings_free(b200_fk* fk);
 /* copy of xExtFFT (file `file`, n2 / chunk_len points) -- for tests */
 int b200_fk20_x_ext_fft(b200_fk* fk, size_t file, uint64_t* out);

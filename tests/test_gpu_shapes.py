@@ -418,3 +418,52 @@ def test_single_transform_lane_mappings_agree():
         for batch in (3, 16):
             out = fs.fft_g1_batch(np.stack([pts] * batch), inv)
             assert np.array_equal(kzg.g1_to_compressed(out[batch - 1]), want)
+
+
+@pytest.mark.parametrize("scale", [2, 5, 8, 12])
+def test_das_fft_extension_over_g1(scale):
+    """The G1 form of DASFFTExtension (das_extension.go:7-84; the TODO at fk20_multi.go:96), in the exponent:
+    ext([k_i G]) == [ext(k)_i G] with the oracle's Fr extension; interleaved, the 2n points are the FFTG1 of a
+    coefficient vector whose upper half is infinity (das_extension_test.go:42-86 over G1)."""
+    n = 1 << (scale - 1)
+    ks, pts = _random_points(n, 77 + scale, scale % 2 == 0)
+    fs, fo = kzg.FFTSettings(scale), cref.FFTSettings(scale)
+    odd = fs.das_fft_extension_g1(pts)
+    want = cref.limbs_to_fr(fo.das_fft_extension(cref.fr_to_limbs(ks)))
+    cmp_g1(odd, cref.g1_mul_gen(want))
+    if scale <= 8:
+        inter = np.empty((2 * n, 18), dtype=np.uint64)
+        inter[0::2], inter[1::2] = pts, odd
+        coeffs = fs.fft_g1(inter, True)
+        assert (kzg.g1_to_compressed(coeffs[n:])[:, 0] == 0xC0).all()
+    with pytest.raises(kzg.KZGPanic):
+        kzg.FFTSettings(3).das_fft_extension_g1(np.zeros((8, 18), dtype=np.uint64))
+
+
+def test_fk20_settings_disk_cache(tmp_path, goldens):
+    """xExtFFT as a cached artefact.  The second construction adopts the stored files
+    (b200_fk20_settings_new_from_x_ext_fft) and proves identically; another setup gets another key."""
+    t = goldens["fk20_multi_test"]
+    secret, l, cc = int(t["secret"]), t["chunk_len"], t["chunk_count"]
+    n = l * cc
+    scale = (2 * n).bit_length() - 1
+    fs = kzg.FFTSettings(scale)
+    ks = kzg.KZGSettings(fs, cref.generate_setup_g1(secret, 2 * n))
+    poly = kzg.fr_from_ints(random_fr_ints(n, 41))
+    a = kzg.FK20MultiSettings(ks, 2 * n, l, cache_dir=str(tmp_path))
+    b = kzg.FK20MultiSettings(ks, 2 * n, l, cache_dir=str(tmp_path))
+    assert not a.from_cache and b.from_cache
+    want = a.da_using_fk20_multi(poly)
+    assert np.array_equal(kzg.g1_to_compressed(b.da_using_fk20_multi(poly)), kzg.g1_to_compressed(want))
+    cmp_g1(b.x_ext_fft(5), a.x_ext_fft(5))
+    s1 = kzg.FK20SingleSettings(ks, 2 * n, cache_dir=str(tmp_path))
+    s2 = kzg.FK20SingleSettings(ks, 2 * n, cache_dir=str(tmp_path))
+    assert not s1.from_cache and s2.from_cache
+    cmp_g1(s2.fk20_single(poly), cref.g1_mul_gen(pyref.fk20_single_exponents(kzg.fr_to_ints(poly), secret)))
+    ks2 = kzg.KZGSettings(fs, cref.generate_setup_g1(secret + 1, 2 * n))
+    c = kzg.FK20MultiSettings(ks2, 2 * n, l, cache_dir=str(tmp_path))
+    assert not c.from_cache
+    r = kzg.FK20MultiSettings(ks, 2 * n, l, offsets=range(4, 9), cache_dir=str(tmp_path))
+    r2 = kzg.FK20MultiSettings(ks, 2 * n, l, offsets=range(4, 9), cache_dir=str(tmp_path))
+    assert not r.from_cache and r2.from_cache
+    cmp_g1(r2.x_ext_fft(8), a.x_ext_fft(8))
