@@ -43,9 +43,9 @@ def _spill_bytes(line: str) -> int:
     return int(m.group(1)) if m else 0
 
 
-def _compile(unit: str, verbose: bool) -> str:
-    obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
-    cmd = [NVCC, *FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, unit), "-o", obj]
+def _compile(unit: str, verbose: bool, defines=(), tag: str = "") -> str:
+    obj = os.path.join(OBJ, unit.replace(".cu", tag + ".o"))
+    cmd = [NVCC, *FLAGS, *["-D" + d for d in defines], "-Xptxas", "-v", "-c", os.path.join(CSRC, unit), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
@@ -66,5 +66,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines) -> str:
+    """Experiment builds (tools/sessions): the same library with extra -D flags as lib/libb200kzg_<tag>.so, selected at
+    run time with the environment variable B200_KZG_LIB.  Not part of the product build."""
+    out = os.path.join(HERE, "lib", "libb200kzg_%s.so" % tag)
+    os.makedirs(OBJ, exist_ok=True)
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(lambda u: _compile(u, False, defines, "_" + tag), UNITS))
+    subprocess.check_call([NVCC, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -111,11 +111,18 @@ static __host__ __device__ __noinline__ bool g1_add_mixed_h(G1J* r, Fp* h_out, c
 //     rescaled by (Z_7 / Z_i)^(2,3), which makes all entries affine on the curve scaled by
 //     Zg = Z_7 * Z_S.  The endomorphism (x, y) -> (beta x, -y) commutes with the scaling.
 //   * the accumulator lives on that curve; one product by Zg brings the result home.
+// ext (optional): storage for the 16 coordinates of the table outside the thread's stack -- shared memory in the
+// B200_STAGE_SMEM_TABLE build of the stage kernel; coordinate c of entry i lives at ext[(c * 8 + i) * estride].
 static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* p, const int8_t* d1, const int8_t* d2, int top,
-                                                            int mode) {
+                                                            int mode, Fp* ext = nullptr, unsigned estride = 1) {
     if (top < 0 || p->is_inf()) { *out = G1J::infinity(); return; }
-    G1J tab[8];       // x, y: table entry; z: the ratio H_i while the table is being built
+    Fp xy_local[16];  // table entries x[0..8), y[0..8) (untouched when ext is given)
+    Fp hz[8];         // the ratio H_i while the table is being built
     Fp bx[8];
+    Fp* const T = ext ? ext : xy_local;
+    const unsigned ts = ext ? estride : 1u;
+#define TAB_X(i) T[(unsigned)(i) * ts]
+#define TAB_Y(i) T[(8u + (unsigned)(i)) * ts]
     G1J cur, nxt;
     G1A step;
     Fp zs;            // Z_S: scaling of the curve the chain runs on
@@ -124,9 +131,9 @@ static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* 
         zs = p->z;
         step.x = p->x; step.y = p->y;
         cur.x = p->x; cur.y = p->y; cur.z = Fp::one();
-        tab[0] = cur;
+        TAB_X(0) = cur.x; TAB_Y(0) = cur.y; hz[0] = cur.z;
         g1_dbl_ni(&nxt, &cur);
-        tab[1] = nxt;                      // z = Z_1 / Z_0 with Z_0 = 1
+        TAB_X(1) = nxt.x; TAB_Y(1) = nxt.y; hz[1] = nxt.z;   // z = Z_1 / Z_0 with Z_0 = 1
         cur = nxt;
         first = 2;
     } else {          // {1,3,..,15} P: S = 2P, chain starts at P
@@ -135,29 +142,29 @@ static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* 
         step.x = nxt.x; step.y = nxt.y;
         Fp c2 = fp_sqr(zs);
         cur.x = fp_mul(p->x, c2); cur.y = fp_mul(p->y, fp_mul(c2, zs)); cur.z = p->z;
-        tab[0] = cur;
+        TAB_X(0) = cur.x; TAB_Y(0) = cur.y; hz[0] = cur.z;
         first = 1;
     }
     bool ok = !zs.is_zero();
     for (int i = first; i < 8 && ok; i++) {
         Fp h;
         ok = g1_add_mixed_h(&nxt, &h, &cur, &step);
-        tab[i].x = nxt.x; tab[i].y = nxt.y; tab[i].z = h;
+        TAB_X(i) = nxt.x; TAB_Y(i) = nxt.y; hz[i] = h;
         cur = nxt;
     }
     if (!ok) { g1_mul_digits_jac(out, p, d1, d2, top, mode); return; }
     const Fp zg = fp_mul(cur.z, zs);
     {
-        Fp s = tab[7].z;                   // Z_7 / Z_6
+        Fp s = hz[7];                      // Z_7 / Z_6
         for (int i = 6; i >= 0; i--) {
             Fp s2 = fp_sqr(s);
-            tab[i].x = fp_mul(tab[i].x, s2);
-            tab[i].y = fp_mul(tab[i].y, fp_mul(s2, s));
-            if (i) s = fp_mul(s, tab[i].z);
+            TAB_X(i) = fp_mul(TAB_X(i), s2);
+            TAB_Y(i) = fp_mul(TAB_Y(i), fp_mul(s2, s));
+            if (i) s = fp_mul(s, hz[i]);
         }
     }
     const Fp beta = fp_const_beta();
-    for (int i = 0; i < 8; i++) bx[i] = fp_mul(tab[i].x, beta);
+    for (int i = 0; i < 8; i++) bx[i] = fp_mul(TAB_X(i), beta);
     G1J acc = G1J::infinity();
     G1A t;
     for (int i = top; i >= 0; i--) {
@@ -166,7 +173,7 @@ static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* 
         if (a) {
             int m = a < 0 ? -a : a;
             int idx = mode == 0 ? m - 1 : m >> 1;
-            t.x = tab[idx].x; t.y = tab[idx].y;
+            t.x = TAB_X(idx); t.y = TAB_Y(idx);
             if (a < 0) t.y = fe_neg(t.y);
             g1_add_mixed_ni(&acc, &acc, &t);
         }
@@ -174,19 +181,21 @@ static __host__ __device__ __noinline__ void g1_mul_digits(G1J* out, const G1J* 
         if (b) {
             int m = b < 0 ? -b : b;
             int idx = mode == 0 ? m - 1 : m >> 1;
-            t.x = bx[idx]; t.y = tab[idx].y;
+            t.x = bx[idx]; t.y = TAB_Y(idx);
             if (b > 0) t.y = fe_neg(t.y);
             g1_add_mixed_ni(&acc, &acc, &t);
         }
     }
     acc.z = fp_mul(acc.z, zg);
     *out = acc;
+#undef TAB_X
+#undef TAB_Y
 }
 
-__host__ __device__ __forceinline__ void g1_mul_program(G1J* out, const G1J* p, const ScalarProgram* prog) {
+__host__ __device__ __forceinline__ void g1_mul_program(G1J* out, const G1J* p, const ScalarProgram* prog, Fp* ext = nullptr, unsigned estride = 1) {
     int top = prog->top;
     if (prog->is_one) { *out = *p; return; }
-    g1_mul_digits(out, p, prog->d1, prog->d2, top, prog->mode);
+    g1_mul_digits(out, p, prog->d1, prog->d2, top, prog->mode, ext, estride);
 }
 
 // ---- on-device recoding of a variable scalar (canonical 8 x u32, < r) ---------------------

@@ -225,10 +225,24 @@ void launch_g1_decompress(const uint8_t* in48, uint64_t* out_abi, uint32_t* stat
 // warp runs the same twiddle program on a different blob, so the digit branches are uniform.
 // across_blocks (few transforms, at least 32 blocks in this stage): lanes run over the BLOCKS of the stage instead, so a
 // warp again holds 32 butterflies with one and the same twiddle w^j and can use the sparse (width-5 NAF) programs.
+// B200_STAGE_SMEM_TABLE (experiment, off by default): the 8-entry table of the twiddle product lives in shared memory
+// (16 coordinates x 48 B per thread = 96 KiB per CTA, hence 2 CTAs per SM) instead of the thread's stack.
+#ifdef B200_STAGE_SMEM_TABLE
+#define STAGE_MINB 2
+#define STAGE_SMEM_BYTES (16u * 48u * G1_BLOCK)
+#define STAGE_EXT reinterpret_cast<Fp*>(stage_smem) + threadIdx.x, G1_BLOCK
+#else
+#define STAGE_MINB G1_MINB
+#define STAGE_SMEM_BYTES 0u
+#define STAGE_EXT nullptr, 1u
+#endif
 template <bool DIF>
-__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
+__global__ void __launch_bounds__(G1_BLOCK, STAGE_MINB) k_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
                                                       size_t bstride, const ScalarProgram* __restrict__ progs,
                                                       size_t prog_stride, int across_blocks) {
+#ifdef B200_STAGE_SMEM_TABLE
+    extern __shared__ uint4 stage_smem[];
+#endif
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t b, q, j;
     if (across_blocks) {
@@ -252,23 +266,34 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage(G1J* data, s
     G1J x0 = ld_vec(p0), x1 = ld_vec(p1), s, d;
     if (DIF) {
         g1_add_sub_ni(&s, &d, &x0, &x1);
-        g1_mul_program(&x1, &d, prog);
+        g1_mul_program(&x1, &d, prog, STAGE_EXT);
         st_vec(p0, s);
         st_vec(p1, x1);
     } else {
-        g1_mul_program(&d, &x1, prog);
+        g1_mul_program(&d, &x1, prog, STAGE_EXT);
         g1_add_sub_ni(&s, &x1, &x0, &d);
         st_vec(p0, s);
         st_vec(p1, x1);
     }
+}
+static void stage_smem_opt_in() {
+#ifdef B200_STAGE_SMEM_TABLE
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaFuncSetAttribute(k_g1_fft_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM_BYTES);
+    cudaFuncSetAttribute(k_g1_fft_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM_BYTES);
+    done[dev] = true;
+#endif
 }
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
                          const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks) {
     ProfScope prof_scope(PROF_G1_FFT_STAGE, st);
     size_t total = across_blocks ? n_half * batch : n_half * g1_lanes_for_batch(batch);
     if (!total || !batch) return;
-    if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
-    else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
+    stage_smem_opt_in();
+    if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
+    else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
     g_launch_count++;
 }
 

@@ -247,3 +247,22 @@ def test_from_compressed_rejects_points_outside_the_subgroup(L):
     if L.b200_g1_from_compressed(_p(np.zeros(18, dtype=np.uint64)), _p(off)) != 0:
         with pytest.raises(kzg.KZGError):
             kzg.g1_from_compressed(off[None, :])
+
+
+def test_bucket_msm_pipeline_replayed_on_the_host(tmp_path):
+    """The per-thread bodies of the Pippenger pipeline (msm.cuh: GLV split, signed window digits, counting sort,
+    bucket accumulation, segment reduction) are __host__ __device__: tools/msm_host_check.cu replays the kernels one
+    thread at a time on the CPU against double-and-add -- affine and Jacobian inputs, zero / one / r - 1 scalars, a
+    point at infinity, the same term twice (doubling inside a bucket) and P with -P (cancellation)."""
+    import shutil
+    import subprocess
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not (os.path.exists(nvcc) or shutil.which("nvcc")):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "msm_host_check")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "go_kzg_b200", "csrc"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tools", "msm_host_check.cu")],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
+    assert "plan n=4096: c=10 W=13 B=512" in out.stdout
