@@ -110,6 +110,18 @@ def main():
     r_var = row("g1_mul_many n=65536 (k_g1_mul_var: per-term windowed GLV multiplication)", 1, big_n * 320, t, ["g1_mul"])
     r_var["terms_per_s"] = round(big_n / (r_var["device_ms"] / 1e3), 1)
     out.append(r_var)
+    # where the fixed tail of the bucket method (bucket reduction + 120 doublings, ~1.1 ms) stops mattering
+    for lg in (18, 20):
+        nn = 1 << lg
+        pp = np.concatenate([pts] * (nn // 4096))
+        ss = random_fr_limbs(nn, 20 + lg)
+        t = timed(lambda: kzg.lincomb_g1(pp, ss), reps=2)
+        r = row("lincomb_g1 n=2^%d generic (bucket MSM), single" % lg, 1, nn * 176 + 144, t, ["g1_msm"])
+        r["terms_per_s"] = round(nn / (r["device_ms"] / 1e3), 1)
+        r["per_term_rate_vs_k_g1_mul_var"] = round(r["terms_per_s"] / r_var["terms_per_s"], 2)
+        out.append(r)
+        del pp, ss
+    r_msm["per_term_rate_vs_k_g1_mul_var"] = round(r_msm["terms_per_s"] / r_var["terms_per_s"], 2)
     # one polynomial per call (the reference API): FK20Single / DAUsingFK20 latency at n = 4096
     import time
     first = pts
