@@ -168,6 +168,12 @@ def run_components(kzg, L, fk, fs, torch, dist, rank, world, max_over_ranks, bar
     barrier()
     out["fk20_single_one_polynomial_ms"] = round(wall(lambda: fk.fk20_single(poly), 3) * 1e3, 3)
     out["da_using_fk20_one_polynomial_ms"] = round(wall(lambda: fk.da_using_fk20(poly), 3) * 1e3, 3)
+    if N_COEFFS == 4096:
+        dab = 32
+        dpolys = np.stack([random_fr_limbs(N_COEFFS, 0xDA00 + rank * dab + b) for b in range(dab)])
+        t_da = wall(lambda: fk.da_using_fk20_batch(dpolys), 2)
+        out["da_using_fk20_batch"] = {"blobs_per_s": round(world * dab / t_da, 2), "batch_per_gpu": dab,
+                                      "note": "b200_da_using_fk20_batch, n = 4096 -> 8192 proofs per blob, host buffers (copies included), wall clock"}
     out["one_polynomial_note"] = "host-buffer call per polynomial, n = %d (b200_fk20_single / b200_da_using_fk20), wall clock, max over ranks" % N_COEFFS
     if N_COEFFS == 4096:
         # ---- config 4

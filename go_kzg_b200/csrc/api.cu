@@ -1229,6 +1229,32 @@ extern "C" int b200_da_using_fk20(b200_fk* fk, const uint64_t* poly, size_t n, u
     if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
     return host_fk20(fk, poly, n, 2, proofs);
 }
+// DAUsingFK20 for `batch` polynomials (fk20_single.go:176-196 per polynomial): lanes of a warp = polynomials, like the
+// headline batch call.  Device-buffer form on the caller's stream, and the host-buffer form around it.
+extern "C" int b200_da_using_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_proofs, void* cuda_stream) {
+    if (fk->chunk_len != 1) return B200_ERR_BAD_INPUT;
+    if (n > fk->ks->fs->max_width / 2) return B200_ERR_TOO_LARGE;   // fk20_single.go:178-180
+    if (!is_pow2(n)) return B200_ERR_NOT_POW2;                      // fk20_single.go:181-183
+    if (2 * n != fk->n2) return B200_ERR_LEN_MISMATCH;
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fk->device));
+    unsigned long long before = g_launch_count;
+    CKS(dev_fk20(fk, (const uint64_t*)d_polys, n, batch, 2, (uint64_t*)d_proofs, (cudaStream_t)cuda_stream));
+    t_last_launches = g_launch_count - before;
+    return B200_OK;
+}
+extern "C" int b200_da_using_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint64_t* proofs) {
+    if (batch == 0) return B200_OK;
+    CK(cudaSetDevice(fk->device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    DevBuf dp, dout;
+    CKS(dp.alloc(batch * n * 32, st)); CKS(dout.alloc(batch * 2 * n * 144, st));
+    CK(cudaMemcpyAsync(dp.p, polys, batch * n * 32, cudaMemcpyHostToDevice, st));
+    CKS(b200_da_using_fk20_batch_dev(fk, dp.p, n, batch, dout.p, st));
+    CK(cudaMemcpyAsync(proofs, dout.p, batch * 2 * n * 144, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
 extern "C" int b200_fk20_multi_da_optimized(b200_fk* fk, const uint64_t* poly, size_t n2, uint64_t* proofs) {
     if (n2 > fk->ks->fs->max_width) return B200_ERR_TOO_LARGE;   // fk20_multi.go:60-63
     if (!upper_half_zero(poly, n2)) return B200_ERR_BAD_INPUT;   // fk20_multi.go:65-69

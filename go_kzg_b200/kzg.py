@@ -124,6 +124,8 @@ def lib():
     L.b200_fk20_single.argtypes = [vp, vp, sz, vp]
     L.b200_fk20_single_da_optimized.argtypes = [vp, vp, sz, vp]
     L.b200_da_using_fk20.argtypes = [vp, vp, sz, vp]
+    L.b200_da_using_fk20_batch.argtypes = [vp, vp, sz, sz, vp]
+    L.b200_da_using_fk20_batch_dev.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200_fk20_multi_da_optimized.argtypes = [vp, vp, sz, vp]
     L.b200_da_using_fk20_multi.argtypes = [vp, vp, sz, vp]
     L.b200_commit_fk20_batch.argtypes = [vp, vp, sz, sz, vp, vp]
@@ -633,6 +635,14 @@ class FK20SingleSettings(_FK20Base):
         p = _fr(poly)
         out = np.zeros((2 * p.shape[0], 18), dtype=np.uint64)
         _raise(lib().b200_da_using_fk20(self.h, _p(p), p.shape[0], _p(out)), what="DAUsingFK20")
+        return out
+
+    def da_using_fk20_batch(self, polys) -> np.ndarray:
+        """DAUsingFK20 (fk20_single.go:176-196) for every polynomial of the batch: (batch, 2n, 18)"""
+        p = np.ascontiguousarray(polys, dtype=np.uint64)
+        batch, n = p.shape[0], p.shape[1]
+        out = np.zeros((batch, 2 * n, 18), dtype=np.uint64)
+        _raise(lib().b200_da_using_fk20_batch(self.h, _p(p), n, batch, _p(out)), what="DAUsingFK20 (batch)")
         return out
 
     def commit_fk20_batch(self, polys):

@@ -180,6 +180,9 @@ int b200_fk20_single(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proo
 int b200_fk20_single_da_optimized(b200_fk* fk, const uint64_t* poly, size_t n2, uint64_t* proofs);
 /* fk20_single.go:176-196 DAUsingFK20: n coefficients -> 2n proofs in reverse bit order */
 int b200_da_using_fk20(b200_fk* fk, const uint64_t* poly, size_t n, uint64_t* proofs);
+/* DAUsingFK20 for `batch` polynomials of n coefficients (2n proofs each, reverse bit order), host buffers / device buffers. */
+int b200_da_using_fk20_batch(b200_fk* fk, const uint64_t* polys, size_t n, size_t batch, uint64_t* proofs);
+int b200_da_using_fk20_batch_dev(b200_fk* fk, const void* d_polys, size_t n, size_t batch, void* d_proofs, void* cuda_stream);
 /* fk20_multi.go:58-109 FK20MultiDAOptimized: n2 coefficients (upper half zero) -> 2k proofs */
 int b200_fk20_multi_da_optimized(b200_fk* fk, const uint64_t* poly, size_t n2, uint64_t* proofs);
 /* fk20_multi.go:113-133 DAUsingFK20Multi: n coefficients -> 2k proofs in reverse bit order */

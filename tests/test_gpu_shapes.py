@@ -91,6 +91,26 @@ def test_da_using_fk20_n4096(fk4096):
     cmp_g1(fk4096.fk20_single(poly), cref.g1_mul_gen(nat[0::2]))
 
 
+def test_da_using_fk20_batch_n4096(fk4096):
+    """DAUsingFK20 batched (lanes = polynomials) at n = 4096: 32 polynomials, two checked in full against the closed form,
+    one position of every polynomial; a ragged batch of 3 takes the per-lane program path."""
+    batch = 32
+    polys = blob_polys(batch, 4096, first_blob=7000)
+    got = fk4096.da_using_fk20_batch(polys)
+    assert got.shape == (batch, 8192, 18)
+    ints = [kzg.fr_to_ints(polys[b]) for b in range(batch)]
+    for b in (0, 31):
+        rev = single_proof_exponents(ints[b], SECRET, 13)
+        pyref.reverse_bit_order(rev)
+        cmp_g1(got[b], cref.g1_mul_gen(rev))
+    pos = 5000
+    x = pow(pyref.scale2_root_of_unity(13), pyref.reverse_bits_limited(8192, pos), R)
+    want = [(pyref.eval_poly(p, SECRET) - pyref.eval_poly(p, x)) * pow((SECRET - x) % R, -1, R) % R for p in ints]
+    cmp_g1(got[:, pos], cref.g1_mul_gen(want))
+    small = fk4096.da_using_fk20_batch(polys[:3])
+    assert np.array_equal(kzg.g1_to_compressed(small[2]), kzg.g1_to_compressed(got[2]))
+
+
 def _random_points(n, seed, affine):
     rng = random.Random(seed)
     ks = [rng.randrange(R) for _ in range(n)]
