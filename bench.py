@@ -174,6 +174,30 @@ def run_components(kzg, L, fk, fs, torch, dist, rank, world, max_over_ranks, bar
         t_da = wall(lambda: fk.da_using_fk20_batch(dpolys), 2)
         out["da_using_fk20_batch"] = {"blobs_per_s": round(world * dab / t_da, 2), "batch_per_gpu": dab,
                                       "note": "b200_da_using_fk20_batch, n = 4096 -> 8192 proofs per blob, host buffers (copies included), wall clock"}
+    # the same one-polynomial call from many host threads at once (goroutines in the Go binding): every call runs on its own
+    # pooled stream, so independent callers fill the SMs that a single 64-warp stage leaves idle
+    import threading
+    def concurrent(nthreads, reps):
+        polys_t = [random_fr_limbs(N_COEFFS, 0xCC00 + rank * 64 + t) for t in range(nthreads)]
+        errs = []
+        def worker(t):
+            try:
+                for _ in range(reps):
+                    fk.fk20_single(polys_t[t])
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        dt = time.perf_counter() - t0
+        if errs:
+            raise errs[0]
+        return nthreads * reps / dt
+    concurrent(4, 1)
+    out["fk20_single_concurrent_callers"] = {("%d_threads_polys_per_s" % t): round(world * max_over_ranks(-concurrent(t, 2)) * -1, 2) for t in (1, 8, 32)}
     out["one_polynomial_note"] = "host-buffer call per polynomial, n = %d (b200_fk20_single / b200_da_using_fk20), wall clock, max over ranks" % N_COEFFS
     if N_COEFFS == 4096:
         # ---- config 4

@@ -1405,6 +1405,42 @@ extern "C" int b200_fk20_multi_finish_merge_dev(b200_fk* fk, const void* d_block
     return check_launches();
 }
 
+// The merge, sharded as well: after the all-gather of the blocks every rank holds the whole array, and the last s forward
+// stages only ever combine the `world` elements i, i + blk, i + 2 blk, .. of one position i inside the blocks.  Rank r takes
+// the positions [r sub, (r + 1) sub), sub = blk / world, of every block: `sub` independent size-`world` transforms with
+// element stride blk whose twiddles depend on the position (index (c_low blk + i) of the stage's table) -- 1 / world of the
+// butterflies per rank instead of all of them.  d_blocks is overwritten; d_part receives [world][sub] internal points.
+// A second all-gather of the parts (rank-major) and b200_fk20_multi_finish_assemble_dev give every rank the full result.
+extern "C" int b200_fk20_multi_finish_merge_part_dev(b200_fk* fk, void* d_blocks, size_t rank, size_t world, void* d_part, void* cuda_stream) {
+    CK(cudaSetDevice(fk->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    b200_fs* fs = fk->ks->fs;
+    const size_t k2 = fk->n2 / fk->chunk_len;
+    if (!is_pow2(world) || rank >= world || world * world > k2) return B200_ERR_BAD_INPUT;
+    const size_t blk = k2 / world, sub = blk / world, halfw = fs->max_width / 2;
+    const ScalarProgram* fwd_progs;
+    CKS(fs_programs(fs, 0, 0, &fwd_progs));                    // lanes hold different positions: per-lane fixed-window programs
+    G1J* mine = (G1J*)d_blocks + rank * sub;
+    for (size_t t = 1; t < world; t <<= 1)                     // stage with half length mm = blk t pairs block c with block c + t
+        launch_g1_fft_stage(mine, world / 2, sub, t, blk, 1, false, fwd_progs, halfw / (blk * t), st, 0, blk, 1, rank * sub);
+    launch_g1_copy((G1J*)d_part, 1, sub, mine, 1, blk, sub, world, 0, 0, st);   // part[c][i] = blocks[c blk + r sub + i]
+    return check_launches();
+}
+extern "C" int b200_fk20_multi_finish_assemble_dev(b200_fk* fk, const void* d_parts, size_t world, int reverse_bits, void* d_proofs,
+                                                   void* cuda_stream) {
+    CK(cudaSetDevice(fk->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t k2 = fk->n2 / fk->chunk_len;
+    if (!is_pow2(world) || world * world > k2) return B200_ERR_BAD_INPUT;
+    const size_t sub = k2 / world / world;
+    DevBuf h;
+    CKS(h.alloc(k2 * sizeof(G1J), st));
+    // gathered parts are [r][c][i]; natural position is (c, r, i)
+    launch_g1_swap_digits(h.as<G1J>(), (const G1J*)d_parts, world, world, sub, st);
+    launch_g1_to_abi(h.as<G1J>(), (uint64_t*)d_proofs, k2, 1, 1, k2, reverse_bits ? 1 : 0, log2u(k2), st);
+    return check_launches();
+}
+
 extern "C" int b200_commit_partial_dev(b200_ks* ks, const void* d_coeffs, size_t begin, size_t end, void* d_out, void* cuda_stream) {
     if (begin > end || end > ks->n_g1) return B200_ERR_BAD_INPUT;
     CK(cudaSetDevice(ks->device));

@@ -103,7 +103,10 @@ void launch_g1_compress(const G1J* in, uint8_t* out48, size_t n, size_t batch, s
 // across_blocks != 0 (needs n_half / m a multiple of 32): lanes run over the blocks of the stage, so that the 32 lanes of a warp
 // share the twiddle w^j even for a single transform; progs must then be the sparse (mode 1) programs
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
-                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks = 0);
+                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks = 0, size_t jmul = 1, size_t bmul = 0,
+                         size_t joff = 0);   // twiddle index (j jmul + b bmul + joff) prog_stride, b = index in the batch
+// dst[(a B + b) C + k] = src[(b A + a) C + k]
+void launch_g1_swap_digits(G1J* dst, const G1J* src, size_t A, size_t B, size_t C, cudaStream_t st);
 // DIF stage of one transform keeping one half of the outputs: out[i] = in[i] + in[i + m] (lower = 0) or
 // progs[i * prog_stride] * (in[i] - in[i + m]) (lower = 1), i < m
 void launch_g1_dif_half_stage(const G1J* in, G1J* out, size_t m, int lower, const ScalarProgram* progs, size_t prog_stride, cudaStream_t st);

@@ -239,7 +239,7 @@ void launch_g1_decompress(const uint8_t* in48, uint64_t* out_abi, uint32_t* stat
 template <bool DIF>
 __global__ void __launch_bounds__(G1_BLOCK, STAGE_MINB) k_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
                                                       size_t bstride, const ScalarProgram* __restrict__ progs,
-                                                      size_t prog_stride, int across_blocks) {
+                                                      size_t prog_stride, int across_blocks, size_t jmul, size_t bmul, size_t joff) {
 #ifdef B200_STAGE_SMEM_TABLE
     extern __shared__ uint4 stage_smem[];
 #endif
@@ -262,7 +262,9 @@ __global__ void __launch_bounds__(G1_BLOCK, STAGE_MINB) k_g1_fft_stage(G1J* data
     size_t i0 = 2 * q - j, i1 = i0 + m;
     G1J* p0 = data + b * bstride + i0 * estride;
     G1J* p1 = data + b * bstride + i1 * estride;
-    const ScalarProgram* prog = progs + j * prog_stride;
+    // twiddle of the butterfly: position j inside the block; the strided sub-transforms of a sharded merge (api.cu) add the
+    // element's position in its sub-range (b) and the sub-range's offset: index (j jmul + b bmul + joff)
+    const ScalarProgram* prog = progs + (j * jmul + b * bmul + joff) * prog_stride;
     G1J x0 = ld_vec(p0), x1 = ld_vec(p1), s, d;
     if (DIF) {
         g1_add_sub_ni(&s, &d, &x0, &x1);
@@ -287,13 +289,13 @@ static void stage_smem_opt_in() {
 #endif
 }
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
-                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks) {
+                         const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks, size_t jmul, size_t bmul, size_t joff) {
     ProfScope prof_scope(PROF_G1_FFT_STAGE, st);
     size_t total = across_blocks ? n_half * batch : n_half * g1_lanes_for_batch(batch);
     if (!total || !batch) return;
     stage_smem_opt_in();
-    if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
-    else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks);
+    if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks, jmul, bmul, joff);
+    else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks, jmul, bmul, joff);
     g_launch_count++;
 }
 
@@ -597,6 +599,20 @@ void launch_g1_copy(G1J* dst, size_t dst_estride, size_t dst_bstride, const G1J*
     if (!n || !batch) return;
     k_g1_copy<<<grid_for(n * batch, 256), 256, 0, st>>>(dst, dst_estride, dst_bstride, src, src_estride, src_bstride, n, batch, bitrev, logn);
     g_launch_count++;
+}
+
+// dst[(a B + b) C + k] = src[(b A + a) C + k]: swaps the two leading digits of a three-digit index (parts gathered
+// rank-major -> natural position order in the sharded merge of FK20 multi)
+__global__ void k_g1_swap_digits(G1J* __restrict__ dst, const G1J* __restrict__ src, size_t A, size_t B, size_t C) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A * B * C) return;
+    size_t k = t % C, ab = t / C, b = ab % B, a = ab / B;
+    st_vec(dst + t, ld_vec(src + (b * A + a) * C + k));
+}
+void launch_g1_swap_digits(G1J* dst, const G1J* src, size_t A, size_t B, size_t C, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!(A * B * C)) return;
+    k_g1_swap_digits<<<grid_for(A * B * C, 256), 256, 0, st>>>(dst, src, A, B, C); g_launch_count++;
 }
 
 __global__ void k_fk20_gather_x(const G1J* __restrict__ S, G1J* __restrict__ work, size_t n, size_t l, size_t off0, size_t files) {

@@ -141,6 +141,8 @@ def lib():
     L.b200_fk20_multi_finish_dev.argtypes = [vp, vp, i32, vp, vp]
     L.b200_fk20_multi_finish_local_dev.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200_fk20_multi_finish_merge_dev.argtypes = [vp, vp, sz, i32, vp, vp]
+    L.b200_fk20_multi_finish_merge_part_dev.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.b200_fk20_multi_finish_assemble_dev.argtypes = [vp, vp, sz, i32, vp, vp]
     L.b200_commit_partial_dev.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200_generate_testing_setup_g1.argtypes = [vp, sz, vp]
     L.b200_fk20_last_launch_count.argtypes = [vp]

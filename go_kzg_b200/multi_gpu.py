@@ -38,6 +38,12 @@ def block_sharded_transforms(world: int, k2: int) -> bool:
     return world > 1 and world & (world - 1) == 0 and 2 * world <= k2
 
 
+def merge_sharded(world: int, k2: int) -> bool:
+    """Whether the last log2(world) forward stages are sharded too (b200_fk20_multi_finish_merge_part_dev): every rank needs
+    at least one position per block."""
+    return block_sharded_transforms(world, k2) and world * world <= k2
+
+
 def _stream_ptr(torch):
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -75,7 +81,14 @@ def da_using_fk20_multi_sharded(fk: "kzg.FK20MultiSettings", poly: np.ndarray, d
         _check(L.b200_fk20_multi_finish_local_dev(fk.h, d_sum.data_ptr(), rank, world, d_block.data_ptr(), sp), "FK20 multi finish (local)")
         blocks = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(blocks, d_block)
-        _check(L.b200_fk20_multi_finish_merge_dev(fk.h, blocks.data_ptr(), world, 1, d_out.data_ptr(), sp), "FK20 multi finish (merge)")
+        if merge_sharded(world, k2):
+            d_mine = torch.zeros((k2 // world, 18), dtype=torch.int64, device="cuda")
+            _check(L.b200_fk20_multi_finish_merge_part_dev(fk.h, blocks.data_ptr(), rank, world, d_mine.data_ptr(), sp), "FK20 multi finish (merge part)")
+            parts2 = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(parts2, d_mine)
+            _check(L.b200_fk20_multi_finish_assemble_dev(fk.h, parts2.data_ptr(), world, 1, d_out.data_ptr(), sp), "FK20 multi finish (assemble)")
+        else:
+            _check(L.b200_fk20_multi_finish_merge_dev(fk.h, blocks.data_ptr(), world, 1, d_out.data_ptr(), sp), "FK20 multi finish (merge)")
     else:
         _check(L.b200_fk20_multi_finish_dev(fk.h, d_sum.data_ptr(), 1, d_out.data_ptr(), sp), "FK20 multi finish")
     torch.cuda.synchronize()
@@ -138,6 +151,9 @@ def measure_da_using_fk20_multi_sharded(scale: int = 21, chunk_len: int = 16, re
     d_block = torch.zeros((max(1, k2 // world), 18), dtype=torch.int64, device="cuda")
     blocks = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
     sharded_transforms = block_sharded_transforms(world, k2)
+    sharded_merge = merge_sharded(world, k2)
+    d_mine = torch.zeros((max(1, k2 // world), 18), dtype=torch.int64, device="cuda")
+    parts2 = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
 
     def step(ev):
         ev[0].record()
@@ -153,7 +169,12 @@ def measure_da_using_fk20_multi_sharded(scale: int = 21, chunk_len: int = 16, re
         if sharded_transforms:
             _check(L.b200_fk20_multi_finish_local_dev(fk.h, src.data_ptr(), rank, world, d_block.data_ptr(), sp), "finish (local)")
             dist.all_gather_into_tensor(blocks, d_block)
-            _check(L.b200_fk20_multi_finish_merge_dev(fk.h, blocks.data_ptr(), world, 1, d_out.data_ptr(), sp), "finish (merge)")
+            if sharded_merge:
+                _check(L.b200_fk20_multi_finish_merge_part_dev(fk.h, blocks.data_ptr(), rank, world, d_mine.data_ptr(), sp), "finish (merge part)")
+                dist.all_gather_into_tensor(parts2, d_mine)
+                _check(L.b200_fk20_multi_finish_assemble_dev(fk.h, parts2.data_ptr(), world, 1, d_out.data_ptr(), sp), "finish (assemble)")
+            else:
+                _check(L.b200_fk20_multi_finish_merge_dev(fk.h, blocks.data_ptr(), world, 1, d_out.data_ptr(), sp), "finish (merge)")
         else:
             _check(L.b200_fk20_multi_finish_dev(fk.h, src.data_ptr(), 1, d_out.data_ptr(), sp), "finish")
         ev[3].record()
@@ -215,6 +236,6 @@ def measure_da_using_fk20_multi_sharded(scale: int = 21, chunk_len: int = 16, re
     return {"workload": "DAUsingFK20Multi n=2^%d chunk=%d -> %d coset proofs, chunk offsets sharded over %d GPU(s)" % (scale - 1, chunk_len, k2, world),
             "n_gpus": world, "ms_total": round(best[3], 2), "ms_partial_hext_fft": round(best[0], 2),
             "ms_exchange_allgather_plus_g1_sum": round(best[1], 2), "ms_g1_transforms": round(best[2], 2),
-            "transforms_block_sharded": bool(sharded_transforms), "polys_per_s": round(1e3 / best[3], 4),
+            "transforms_block_sharded": bool(sharded_transforms), "merge_stages_sharded": bool(sharded_merge), "polys_per_s": round(1e3 / best[3], 4),
             "exchange_bytes_per_rank": int(k2 * 144) if world > 1 else 0, "ranks_agree": same, "closed_form_position_ok": bool(closed),
             "files_per_rank": len(mine), "settings_build_s": round(setup_s, 1)}

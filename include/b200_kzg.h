@@ -239,6 +239,11 @@ int b200_fk20_multi_finish_dev(b200_fk* fk, const void* d_h_ext_fft, int reverse
  * forward stages; the blocks are all-gathered in rank order; _merge runs the last s forward stages and converts. */
 int b200_fk20_multi_finish_local_dev(b200_fk* fk, const void* d_h_ext_fft, size_t rank, size_t world, void* d_block, void* cuda_stream);
 int b200_fk20_multi_finish_merge_dev(b200_fk* fk, const void* d_blocks, size_t world, int reverse_bits, void* d_proofs, void* cuda_stream);
+/* The merge sharded as well (world^2 <= k2): after the all-gather of the blocks, rank r runs the last s forward stages only for
+ * the positions [r sub, (r+1) sub), sub = k2 / world^2, of every block (d_blocks is overwritten) and leaves them in d_part
+ * (k2 / world internal points); the parts are all-gathered in rank order and _assemble converts them to the proof array. */
+int b200_fk20_multi_finish_merge_part_dev(b200_fk* fk, void* d_blocks, size_t rank, size_t world, void* d_part, void* cuda_stream);
+int b200_fk20_multi_finish_assemble_dev(b200_fk* fk, const void* d_parts, size_t world, int reverse_bits, void* d_proofs, void* cuda_stream);
 /* Partial LinCombG1 over points/scalars [begin, end) of the settings' SecretG1 (MSM sharded by
  * point range); partial sums are exchanged and added with b200_g1_sum_dev. */
 int b200_commit_partial_dev(b200_ks* ks, const void* d_coeffs, size_t begin, size_t end, void* d_out, void* cuda_stream);

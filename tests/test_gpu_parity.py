@@ -592,6 +592,16 @@ def test_sharded_fk20_multi_blocks_on_one_gpu():
         assert L.b200_fk20_multi_finish_merge_dev(fk.h, blocks.data_ptr(), w2, 1, d_out2.data_ptr(), None) == 0
         torch.cuda.synchronize()
         cmp_g1(d_out2.cpu().numpy().view(np.uint64), want)
+        # the merge sharded as well: every rank finishes its positions of every block, parts gathered in rank order
+        if multi_gpu.merge_sharded(w2, k2) or w2 == 1:
+            parts2 = torch.zeros((w2, k2 // w2, 18), dtype=torch.int64, device="cuda")
+            for r in range(w2):
+                mine = blocks.clone()                                     # the rank's own copy of the all-gathered blocks
+                assert L.b200_fk20_multi_finish_merge_part_dev(fk.h, mine.data_ptr(), r, w2, parts2[r].data_ptr(), None) == 0
+            d_out3 = torch.zeros((k2, 18), dtype=torch.int64, device="cuda")
+            assert L.b200_fk20_multi_finish_assemble_dev(fk.h, parts2.data_ptr(), w2, 1, d_out3.data_ptr(), None) == 0
+            torch.cuda.synchronize()
+            cmp_g1(d_out3.cpu().numpy().view(np.uint64), want)
     assert L.b200_fk20_multi_finish_local_dev(fk.h, d_sum.data_ptr(), 0, 3, blocks.data_ptr(), None) != 0      # not a power of two
     # the single-process entry of the sharded driver, and the point-range sharded commitment
     cmp_g1(multi_gpu.da_using_fk20_multi_sharded(fk, poly), want)

@@ -81,3 +81,14 @@ def test_block_sharded_transform_rule():
     from go_kzg_b200 import multi_gpu
     assert [w for w in range(1, 20) if multi_gpu.block_sharded_transforms(w, 1 << 17)] == [2, 4, 8, 16]
     assert not multi_gpu.block_sharded_transforms(8, 8) and multi_gpu.block_sharded_transforms(4, 8)
+
+
+def test_transform_sharding_rules():
+    """which parts of the FK20-multi finish are spread over the ranks (multi_gpu.block_sharded_transforms / merge_sharded)"""
+    from go_kzg_b200 import multi_gpu
+    k2 = 1 << 17
+    assert not multi_gpu.block_sharded_transforms(1, k2)
+    assert all(multi_gpu.block_sharded_transforms(w, k2) and multi_gpu.merge_sharded(w, k2) for w in (2, 4, 8))
+    assert not multi_gpu.block_sharded_transforms(3, k2) and not multi_gpu.merge_sharded(3, k2)     # not a power of two
+    assert multi_gpu.block_sharded_transforms(8, 16) and not multi_gpu.merge_sharded(8, 16)          # 16 points: 2 per block, 0 per (block, rank)
+    assert multi_gpu.merge_sharded(8, 64)
