@@ -560,8 +560,9 @@ static int fs_stage_programs(b200_fs* fs, int inverse, size_t batch, StageProgra
 }
 static void launch_stage_auto(const StagePrograms& sp, G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride,
                               bool dif, size_t prog_stride, cudaStream_t st) {
+    const size_t share = g1_stage_uses_quads(n_half, batch) ? 8 : 32;      // units of a warp that must hold the same twiddle
     if (program_mode_for_batch(batch) == 1) launch_g1_fft_stage(data, n_half, batch, m, estride, bstride, dif, sp.shared, prog_stride, st, 0);
-    else if ((n_half / m) % 32 == 0) launch_g1_fft_stage(data, n_half, batch, m, estride, bstride, dif, sp.shared, prog_stride, st, 1);
+    else if ((n_half / m) % share == 0) launch_g1_fft_stage(data, n_half, batch, m, estride, bstride, dif, sp.shared, prog_stride, st, 1);
     else launch_g1_fft_stage(data, n_half, batch, m, estride, bstride, dif, sp.per_lane, prog_stride, st, 0);
 }
 static int dev_g1_fft_stages(b200_fs* fs, G1J* data, unsigned logn, size_t batch, size_t estride, size_t bstride,

@@ -105,6 +105,9 @@ void launch_g1_compress(const G1J* in, uint8_t* out48, size_t n, size_t batch, s
 void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride, size_t bstride, bool dif,
                          const ScalarProgram* progs, size_t prog_stride, cudaStream_t st, int across_blocks = 0, size_t jmul = 1, size_t bmul = 0,
                          size_t joff = 0);   // twiddle index (j jmul + b bmul + joff) prog_stride, b = index in the batch
+// whether launch_g1_fft_stage runs one butterfly per quad of lanes for this shape (then across_blocks needs n_half / m to be a
+// multiple of 8 only, instead of 32)
+bool g1_stage_uses_quads(size_t n_half, size_t batch);
 // dst[(a B + b) C + k] = src[(b A + a) C + k]
 void launch_g1_swap_digits(G1J* dst, const G1J* src, size_t A, size_t B, size_t C, cudaStream_t st);
 // DIF stage of one transform keeping one half of the outputs: out[i] = in[i] + in[i + m] (lower = 0) or

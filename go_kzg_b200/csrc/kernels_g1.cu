@@ -9,6 +9,7 @@
 // (out-of-line point operations, tables in local memory).
 #include "g1_dev.cuh"
 #include "kernels.h"
+#include "quad.cuh"
 
 namespace b200 {
 
@@ -278,6 +279,47 @@ __global__ void __launch_bounds__(G1_BLOCK, STAGE_MINB) k_g1_fft_stage(G1J* data
         st_vec(p1, x1);
     }
 }
+// The same stage with one butterfly per QUAD of lanes (quad.cuh), for launches too small to occupy the chip (one or a few
+// transforms): the butterfly's chain of ~1450 dependent products becomes ~650-750 dependent levels.  Lane mapping as above on
+// the quad index; with across_blocks the 8 quads of a warp share the twiddle (sparse program), otherwise fixed windows.
+template <bool DIF>
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage_quad(G1J* data, size_t n_half, size_t batch, size_t m, size_t estride,
+                                                                         size_t bstride, const ScalarProgram* __restrict__ progs,
+                                                                         size_t prog_stride, int across_blocks, size_t jmul, size_t bmul, size_t joff) {
+    const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool valid = t < n_half * batch;             // quads past the end idle through the collective operations
+    const size_t tc = valid ? t : 0;
+    size_t b, q, j;
+    if (across_blocks) {
+        const size_t nblocks = n_half / m;             // multiple of 8: the quads of a warp share (b, j)
+        const size_t blk = tc % nblocks, r = tc / nblocks;
+        b = r % batch; j = r / batch;
+        q = blk * m + j;
+    } else {
+        b = tc % batch; q = tc / batch;
+        j = q & (m - 1);
+    }
+    const size_t i0 = 2 * q - j, i1 = i0 + m;
+    G1J* p0 = data + b * bstride + i0 * estride;
+    G1J* p1 = data + b * bstride + i1 * estride;
+    const ScalarProgram* prog = progs + (j * jmul + b * bmul + joff) * prog_stride;
+    G1J x0 = G1J::infinity(), x1 = G1J::infinity(), s, d;
+    if (valid) { x0 = ld_vec(p0); x1 = ld_vec(p1); }
+    if (DIF) {
+        quad_add_sub(&s, &d, &x0, &x1);
+        quad_mul_program(&x1, &d, prog);
+    } else {
+        quad_mul_program(&d, &x1, prog);
+        quad_add_sub(&s, &x1, &x0, &d);
+    }
+    if (valid && (threadIdx.x & 3u) == 0) { st_vec(p0, s); st_vec(p1, x1); }
+}
+// butterflies per launch up to which a quad per butterfly is used (4 x as many lanes: at most ~1 warp per SM sub-partition)
+#ifndef B200_QUAD_STAGE_MAX
+#define B200_QUAD_STAGE_MAX 4096
+#endif
+bool g1_stage_uses_quads(size_t n_half, size_t batch) { return batch < 16 && n_half * batch <= B200_QUAD_STAGE_MAX; }
+
 static void stage_smem_opt_in() {
 #ifdef B200_STAGE_SMEM_TABLE
     static bool done[64] = {};
@@ -293,6 +335,13 @@ void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_
     ProfScope prof_scope(PROF_G1_FFT_STAGE, st);
     size_t total = across_blocks ? n_half * batch : n_half * g1_lanes_for_batch(batch);
     if (!total || !batch) return;
+    if (g1_stage_uses_quads(n_half, batch)) {
+        const size_t lanes = (n_half * batch * 4 + 31) / 32 * 32;       // whole warps: the quad operations are warp-collective
+        if (dif) k_g1_fft_stage_quad<true><<<grid_for(lanes, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks, jmul, bmul, joff);
+        else k_g1_fft_stage_quad<false><<<grid_for(lanes, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks, jmul, bmul, joff);
+        g_launch_count++;
+        return;
+    }
     stage_smem_opt_in();
     if (dif) k_g1_fft_stage<true><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks, jmul, bmul, joff);
     else k_g1_fft_stage<false><<<grid_for(total, G1_BLOCK), G1_BLOCK, STAGE_SMEM_BYTES, st>>>(data, n_half, batch, m, estride, bstride, progs, prog_stride, across_blocks, jmul, bmul, joff);

@@ -80,38 +80,39 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan p, const G1J*
                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ not_affine,
                                                            G1J* __restrict__ buckets) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t g = QUAD ? tid >> 2 : tid;
-    const size_t nb = (size_t)p.W * p.B;
-    const size_t bucket = g / p.S;                 // w * B + (b - 1)
-    const unsigned slice = (unsigned)(g % p.S);
+    const size_t u = QUAD ? tid >> 2 : tid;        // unit index; the units of a window start at a multiple of 32
+    unsigned w = 0;
+    while (w + 1 < p.W && u >= p.unit_off[w + 1]) w++;
+    const unsigned S = p.Sw[w];
+    const size_t local = u - p.unit_off[w];
+    const unsigned b = (unsigned)(local / S) + 1, slice = (unsigned)(local % S);
+    const bool valid = u < p.unit_off[p.W] && b <= p.Bw[w];
     G1J acc = G1J::infinity();
-    unsigned qw = 0;
     uint32_t qbegin = 0, qcount = 0;
-    if (bucket < nb) {
-        const unsigned w = (unsigned)(bucket / p.B), b = (unsigned)(bucket % p.B) + 1;
+    if (valid) {
         const size_t slot = (size_t)w * (p.B + 1) + b;
         const uint32_t len = counts[slot], off = offsets[slot];
-        const uint32_t per = (len + p.S - 1) / p.S;
+        const uint32_t per = (len + S - 1) / S;
         uint32_t begin = slice * per, end = begin + per;
         if (begin > len) begin = len;
         if (end > len) end = len;
         if (!QUAD) msm_accumulate_slice(p, pts, bx, sorted + (size_t)w * p.T, off + begin, off + end, *not_affine == 0, &acc);
-        qw = w; qbegin = off + begin; qcount = end - begin;
+        qbegin = off + begin; qcount = end - begin;
     }
     if (QUAD) {
         // warp-collective quad operations: every quad walks max(count over the warp) steps, idle ones pass active = false
         const bool affine = *not_affine == 0;
-        const uint32_t* sw = sorted + (size_t)qw * p.T;
+        const uint32_t* sw = sorted + (size_t)w * p.T;
         const uint32_t steps = __reduce_max_sync(0xffffffffu, qcount);
         for (uint32_t k = 0; k < steps; k++) {
             const bool act = k < qcount;
             G1J q = G1J::infinity();
             if (act) {
-                const uint32_t u = sw[qbegin + k];
-                const size_t t = u & 0x7fffffffu;
+                const uint32_t v = sw[qbegin + k];
+                const size_t t = v & 0x7fffffffu;
                 const bool second = t >= p.n;
                 const size_t i = second ? t - p.n : t;
-                const bool neg = ((u >> 31) != 0) != second;
+                const bool neg = ((v >> 31) != 0) != second;
                 q.x = second ? ld_vec(bx + i) : ld_vec(&pts[i].x);
                 q.y = ld_vec(&pts[i].y);
                 if (neg) q.y = fe_neg(q.y);
@@ -125,13 +126,14 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan p, const G1J*
             }
         }
     }
-    // the slices of a bucket: adjacent lanes (thread units) or adjacent quads (quad units); whole warps get here
+    // the slices of a bucket: adjacent lanes (thread units) or adjacent quads (quad units); whole warps get here, and a
+    // warp lies inside one window, so S is uniform over it
     if (!QUAD) {
-        if (p.S > 1) g1_warp_sum(acc, p.S);
-    } else if (p.S > 1) {
-        quad_group_sum(acc, p.S);
+        if (S > 1) g1_warp_sum(acc, S);
+    } else if (S > 1) {
+        quad_group_sum(acc, S);
     }
-    if (bucket < nb && slice == 0 && (!QUAD || (threadIdx.x & 3u) == 0)) st_vec(buckets + bucket, acc);
+    if (valid && slice == 0 && (!QUAD || (threadIdx.x & 3u) == 0)) st_vec(buckets + (size_t)w * p.B + (b - 1), acc);
 }
 
 // ---- step 5: thread = (window, segment of L buckets) ---------------------------------------------------------
@@ -234,11 +236,15 @@ void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* w
     k_msm_recode<<<grid_for(n, 128), 128, 0, st>>>(p, pts, k, k_is_mont, ws.digits, ws.counts, ws.bx, ws.flag);
     k_msm_scan<<<p.W, 1024, 0, st>>>(p, ws.counts, ws.offsets);
     k_msm_scatter<<<grid_for((size_t)p.W * p.T, 256), 256, 0, st>>>(p, ws.digits, ws.offsets, ws.cursors, ws.sorted);
-    const size_t units = (size_t)p.W * p.B * p.S;
+    const size_t units = p.unit_off[p.W];
+    cudaMemsetAsync(ws.buckets, 0, (size_t)p.W * p.B * sizeof(G1J), st);   // buckets no unit owns (beyond Bw[w]) are infinity
     // a quad per unit only pays when the expanded launch is still a fraction of one wave (measured at n = 4096: 213 k
     // quad lanes take 1.16 ms where 53 k thread units take 0.24 ms -- a warp instruction costs the same with 8 points as with 32)
-    if (units * 4 <= kMsmQuadUnits && p.S <= 8) k_msm_accumulate<true><<<grid_for(units * 4, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
-    else k_msm_accumulate<false><<<grid_for(units, 128), 128, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
+    bool quad_ok = units * 4 <= kMsmQuadUnits;
+    for (unsigned w = 0; w < p.W; w++) quad_ok = quad_ok && p.Sw[w] <= 8;
+    // 64-thread CTAs: a launch below one wave then spreads evenly over the SMs (CTAs of 128 leave some SMs with 3 and others with 2)
+    if (quad_ok) k_msm_accumulate<true><<<grid_for(units * 4, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
+    else k_msm_accumulate<false><<<grid_for(units, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
     k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L), 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
     k_msm_windows<<<p.W, 128, 0, st>>>(p, ws.segs, ws.wsums);
     k_msm_horner<<<1, (unsigned)((p.W * 4 + 31) / 32 * 32), 0, st>>>(p, ws.wsums, out);

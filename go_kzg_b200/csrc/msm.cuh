@@ -23,18 +23,30 @@
 
 namespace b200 {
 
+#define MSM_MAX_WINDOWS 34
 struct MsmPlan {
     size_t n = 0;       // points
     size_t T = 0;       // terms = 2 n
     unsigned c = 0;     // window bits
     unsigned W = 0;     // windows
     unsigned B = 0;     // buckets per window = 2^(c-1), bucket index 1..B
-    unsigned S = 1;     // slices per bucket in the accumulation (power of two <= 32)
+    unsigned S = 1;     // base number of slices per bucket in the accumulation (power of two <= 32)
     unsigned L = 1;     // buckets per segment in the reduction (power of two)
+    // Accumulation units.  The windows are not equally loaded: the top window holds only the 128 - c (W - 1) leading bits of
+    // a half scalar, so its digits are non-negative and below 2^bits -- fewer buckets, each proportionally longer -- and a
+    // last window may hold nothing but the carry.  Window w gets Bw[w] buckets x Sw[w] slices with Bw Sw (about) constant,
+    // so that every (bucket, slice) unit adds the same number of terms; units of one window are padded to whole warps.
+    unsigned Bw[MSM_MAX_WINDOWS] = {};
+    unsigned Sw[MSM_MAX_WINDOWS] = {};
+    unsigned unit_off[MSM_MAX_WINDOWS + 1] = {};
 };
 
+// thread slots of one full wave of the accumulation kernel (148 SMs x 4 CTAs x 128 threads at 124 registers)
+static const size_t kMsmWaveSlots = (size_t)148 * 4 * 128;
+
 // Window width minimising (additions into buckets) + (additions of the bucket reduction); slices so that the
-// accumulation has enough threads to fill the chip while each slice keeps a few terms.
+// accumulation has as many units as fit ONE wave of the chip (a second, nearly empty wave would double its time)
+// while each slice keeps a few terms.
 inline MsmPlan msm_plan(size_t n) {
     MsmPlan p;
     p.n = n; p.T = 2 * n;
@@ -48,9 +60,22 @@ inline MsmPlan msm_plan(size_t n) {
     p.B = 1u << (p.c - 1);
     const double avg = (double)p.T / p.B;                       // terms per bucket (upper bound: zero digits drop out)
     p.S = 1;
-    while (p.S < 32 && (size_t)p.W * p.B * p.S < 65536 && avg / (2 * p.S) >= 2.0) p.S *= 2;
+    while (p.S < 32 && (size_t)p.W * p.B * p.S * 2 <= kMsmWaveSlots && avg / (2 * p.S) >= 2.0) p.S *= 2;
     p.L = p.B >= 2048 ? 8 : 4;
     if (p.L > p.B) p.L = p.B;
+    unsigned off = 0;
+    for (unsigned w = 0; w < p.W; w++) {
+        const int bits = 128 - (int)(p.c * w);                  // bits of a 128-bit half scalar that reach this window
+        unsigned bw = p.B;
+        if (bits < (int)p.c) bw = bits <= 0 ? 1u : (1u << bits);   // digit = bits + carry <= 2^bits: never negative there
+        if (bw > p.B) bw = p.B;
+        unsigned sw = p.S * (p.B / bw);
+        if (sw > 32) sw = 32;
+        p.Bw[w] = bw; p.Sw[w] = sw;
+        p.unit_off[w] = off;
+        off += (bw * sw + 31u) / 32u * 32u;
+    }
+    p.unit_off[p.W] = off;
     return p;
 }
 

@@ -61,7 +61,7 @@ __device__ __forceinline__ void quad_sqr(const Fp& a0, const Fp& a1, const Fp& a
 }
 
 // *p = 2 * *p where active, in 3 levels (formulas of g1_dbl: 2M + 5S; they map infinity to infinity by themselves)
-__device__ __noinline__ void quad_dbl(G1J* p_io, bool active) {
+static __device__ __noinline__ void quad_dbl(G1J* p_io, bool active) {
     const G1J p = *p_io;
     Fp a, b, yz, u0, c, t, f;
     quad_mul(p.x, p.x, p.y, p.y, p.y, p.z, p.x, p.x, a, b, yz, u0);
@@ -81,7 +81,7 @@ __device__ __noinline__ void quad_dbl(G1J* p_io, bool active) {
 // *p = *p + *q where active; both Jacobian; 5 levels.  Cases of g1_add by selection: an infinite operand returns the
 // other one; P == -Q falls out of the formulas (H = 0 gives Z3 = 0); P == Q needs a doubling, run by the whole warp
 // when any active quad hits it.
-__device__ __noinline__ void quad_add(G1J* p_io, const G1J* q_in, bool active) {
+static __device__ __noinline__ void quad_add(G1J* p_io, const G1J* q_in, bool active) {
     const G1J p = *p_io, q = *q_in;
     Fp z1z1, z2z2, a, b, u1, u2, s1, s2;
     quad_mul(p.z, p.z, q.z, q.z, p.y, q.z, q.y, p.z, z1z1, z2z2, a, b);
@@ -109,7 +109,7 @@ __device__ __noinline__ void quad_add(G1J* p_io, const G1J* q_in, bool active) {
 }
 
 // *p = *p + *q where active, Q affine (finite, or (0, 0) for infinity); 5 levels
-__device__ __noinline__ void quad_add_mixed(G1J* p_io, const G1A* q_in, bool active) {
+static __device__ __noinline__ void quad_add_mixed(G1J* p_io, const G1A* q_in, bool active) {
     const G1J p = *p_io;
     const G1A q = *q_in;
     Fp z1z1, t, u2, s2, t0, t1;
@@ -147,6 +147,98 @@ __device__ __forceinline__ void quad_small_mul(G1J* out, const G1J* p, unsigned 
         quad_add(&acc, p, active && ((m >> bit) & 1u));
     }
     if (active) *out = acc;
+}
+
+// (x + t, x - t) in 5 levels, sharing the common subexpressions of the two additions (the radix-2 butterfly of
+// fft_g1.go:52-54; g1_add_sub).  t == +-x is rare: the whole warp then runs two plain additions.
+static __device__ __noinline__ void quad_add_sub(G1J* sum, G1J* diff, const G1J* x_in, const G1J* t_in) {
+    const G1J x = *x_in, t = *t_in;
+    Fp z1z1, z2z2, a, b, u1, u2, s1, s2;
+    quad_mul(x.z, x.z, t.z, t.z, x.y, t.z, t.y, x.z, z1z1, z2z2, a, b);
+    quad_mul(x.x, z2z2, t.x, z1z1, a, z2z2, b, z1z1, u1, u2, s1, s2);
+    const Fp h = fe_sub(u2, u1), rp = fe_sub(s2, s1), rm = fe_sub(fe_neg(s2), s1);
+    Fp hh, zz, rp2, rm2, hhh, v, z3, t0;
+    quad_mul(h, h, x.z, t.z, rp, rp, rm, rm, hh, zz, rp2, rm2);
+    quad_mul(h, hh, u1, hh, zz, h, h, hh, hhh, v, z3, t0);
+    const Fp v2 = fe_dbl(v);
+    G1J sp, dm;
+    sp.x = fe_sub(fe_sub(rp2, hhh), v2);
+    dm.x = fe_sub(fe_sub(rm2, hhh), v2);
+    Fp yp, ym, sh;
+    quad_mul(rp, fe_sub(v, sp.x), rm, fe_sub(v, dm.x), s1, hhh, s1, hhh, yp, ym, sh, t0);
+    sp.y = fe_sub(yp, sh); dm.y = fe_sub(ym, sh);
+    sp.z = z3; dm.z = z3;
+    const bool xinf = x.is_inf(), tinf = t.is_inf();
+    const bool same = !xinf && !tinf && h.is_zero();
+    if (__any_sync(QUAD_FULL, same)) {
+        G1J s2p = x, d2p = x, nt = t;
+        nt.y = fe_neg(t.y);
+        quad_add(&s2p, &t, true);
+        quad_add(&d2p, &nt, true);
+        sp = g1_select(same, s2p, sp);
+        dm = g1_select(same, d2p, dm);
+    }
+    G1J nt = t;
+    nt.y = fe_neg(t.y);
+    sp = g1_select(xinf, t, sp); dm = g1_select(xinf, nt, dm);        // 0 + t, 0 - t
+    sp = g1_select(tinf, x, sp); dm = g1_select(tinf, x, dm);         // x +- 0
+    *sum = sp; *diff = dm;
+}
+
+// k * P for the digit strings of a ScalarProgram (g1_dev.cuh), one quad per product.  Jacobian table: with quads a general
+// addition costs the same 5 levels as a mixed one, so the effective-affine construction of g1_mul_digits buys nothing here.
+// mode 1 (sparse digits) requires every quad of the warp to hold the SAME program (across-block lane mapping); mode 0 adds at
+// the fixed window positions for whichever quads have a non-zero digit there.
+static __device__ __noinline__ void quad_mul_digits(G1J* out, const G1J* p_in, const int8_t* d1, const int8_t* d2, int top, int mode) {
+    G1J tab[8];
+    Fp bx[8];
+    tab[0] = *p_in;
+    if (mode == 0) {                      // {1..8} P
+        tab[1] = tab[0]; quad_dbl(&tab[1], true);
+        tab[2] = tab[1]; quad_add(&tab[2], &tab[0], true);
+        tab[3] = tab[1]; quad_dbl(&tab[3], true);
+        tab[4] = tab[3]; quad_add(&tab[4], &tab[0], true);
+        tab[5] = tab[2]; quad_dbl(&tab[5], true);
+        tab[6] = tab[5]; quad_add(&tab[6], &tab[0], true);
+        tab[7] = tab[3]; quad_dbl(&tab[7], true);
+    } else {                              // {1, 3, .., 15} P
+        G1J p2 = tab[0];
+        quad_dbl(&p2, true);
+        for (int i = 1; i < 8; i++) { tab[i] = tab[i - 1]; quad_add(&tab[i], &p2, true); }
+    }
+    const Fp beta = fp_const_beta();
+    quad_mul(tab[0].x, beta, tab[1].x, beta, tab[2].x, beta, tab[3].x, beta, bx[0], bx[1], bx[2], bx[3]);
+    quad_mul(tab[4].x, beta, tab[5].x, beta, tab[6].x, beta, tab[7].x, beta, bx[4], bx[5], bx[6], bx[7]);
+    G1J acc = G1J::infinity();
+    const int wtop = __reduce_max_sync(QUAD_FULL, top);
+    for (int i = wtop; i >= 0; i--) {
+        quad_dbl(&acc, true);             // the doubling formulas keep infinity at infinity
+        const int a = d1[i];
+        if (__any_sync(QUAD_FULL, a != 0)) {
+            const int mg = a < 0 ? -a : a;
+            const int idx = a ? (mode == 0 ? mg - 1 : mg >> 1) : 0;
+            G1J t = tab[idx];
+            if (a < 0) t.y = fe_neg(t.y);
+            quad_add(&acc, &t, a != 0);
+        }
+        const int b = d2[i];
+        if (__any_sync(QUAD_FULL, b != 0)) {
+            const int mg = b < 0 ? -b : b;
+            const int idx = b ? (mode == 0 ? mg - 1 : mg >> 1) : 0;
+            G1J t = tab[idx];
+            t.x = bx[idx];
+            if (b > 0) t.y = fe_neg(t.y);     // z^2 (x, y) = (beta x, -y)
+            quad_add(&acc, &t, b != 0);
+        }
+    }
+    *out = acc;
+}
+// warp-collective g1_mul_program: a product by 1 is skipped only when the whole warp has it
+__device__ __forceinline__ void quad_mul_program(G1J* out, const G1J* p, const ScalarProgram* prog) {
+    if (__all_sync(QUAD_FULL, prog->is_one != 0)) { *out = *p; return; }
+    G1J r;
+    quad_mul_digits(&r, p, prog->d1, prog->d2, prog->top, prog->mode);
+    *out = r;
 }
 
 // sum over the quads of a warp: every quad ends with the total of all eight

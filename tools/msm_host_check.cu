@@ -25,21 +25,25 @@ static G1J msm_replay(const std::vector<G1J>& pts, const std::vector<Fr>& ks) {
     }
     for (unsigned w = 0; w < p.W; w++)
         for (size_t t = 0; t < p.T; t++) msm_scatter_term(p, w, t, digits.data(), offsets.data(), cursors.data(), sorted.data());
-    std::vector<G1J> buckets((size_t)p.W * p.B);
-    for (size_t bucket = 0; bucket < buckets.size(); bucket++) {
-        const unsigned w = (unsigned)(bucket / p.B), b = (unsigned)(bucket % p.B) + 1;
-        const size_t slot = (size_t)w * (p.B + 1) + b;
-        const uint32_t len = counts[slot], off = offsets[slot], per = (len + p.S - 1) / p.S;
-        G1J sum = G1J::infinity();
-        for (unsigned s = 0; s < p.S; s++) {
-            uint32_t begin = s * per, end = begin + per;
-            if (begin > len) begin = len;
-            if (end > len) end = len;
-            G1J part;
-            msm_accumulate_slice(p, pts.data(), bx.data(), sorted.data() + (size_t)w * p.T, off + begin, off + end, not_affine == 0, &part);
-            sum = g1_add(sum, part);
+    std::vector<G1J> buckets((size_t)p.W * p.B, G1J::infinity());
+    // units exactly as k_msm_accumulate maps them: window w has Bw[w] buckets x Sw[w] slices
+    for (unsigned w = 0; w < p.W; w++) {
+        for (unsigned b = 1; b <= p.B; b++) {
+            const size_t slot = (size_t)w * (p.B + 1) + b;
+            if (b > p.Bw[w]) { if (counts[slot]) { printf("digit beyond Bw in window %u\n", w); exit(2); } continue; }
+            const unsigned S = p.Sw[w];
+            const uint32_t len = counts[slot], off = offsets[slot], per = (len + S - 1) / S;
+            G1J sum = G1J::infinity();
+            for (unsigned sl = 0; sl < S; sl++) {
+                uint32_t begin = sl * per, end = begin + per;
+                if (begin > len) begin = len;
+                if (end > len) end = len;
+                G1J part;
+                msm_accumulate_slice(p, pts.data(), bx.data(), sorted.data() + (size_t)w * p.T, off + begin, off + end, not_affine == 0, &part);
+                sum = g1_add(sum, part);
+            }
+            buckets[(size_t)w * p.B + (b - 1)] = sum;
         }
-        buckets[bucket] = sum;
     }
     G1J total = G1J::infinity();
     const unsigned nseg = p.B / p.L;
@@ -88,12 +92,13 @@ int main(int argc, char** argv) {
             G1J got = msm_replay(pts, ks);
             if (!g1_equal(got, want)) { bad++; printf("mismatch n=%zu variant=%d\n", n, variant); }
             MsmPlan p = msm_plan(n);
-            printf("n=%zu variant=%d c=%u W=%u B=%u S=%u L=%u\n", n, variant, p.c, p.W, p.B, p.S, p.L);
+            printf("n=%zu variant=%d c=%u W=%u B=%u S=%u L=%u top: Bw=%u Sw=%u units=%u\n", n, variant, p.c, p.W, p.B, p.S, p.L, p.Bw[p.W - 1], p.Sw[p.W - 1], p.unit_off[p.W]);
         }
     }
     for (size_t n : {(size_t)4096, (size_t)65536, (size_t)1 << 20}) {
         MsmPlan p = msm_plan(n);
         printf("plan n=%zu: c=%u W=%u B=%u S=%u L=%u\n", n, p.c, p.W, p.B, p.S, p.L);
+        for (unsigned w = 0; w < p.W; w++) printf("   window %u: Bw=%u Sw=%u units at %u\n", w, p.Bw[w], p.Sw[w], p.unit_off[w]);
     }
     printf("bad=%d\n", bad);
     return bad != 0;
