@@ -59,8 +59,17 @@ inline MsmPlan msm_plan(size_t n) {
     p.W = (129 + p.c - 1) / p.c;
     p.B = 1u << (p.c - 1);
     const double avg = (double)p.T / p.B;                       // terms per bucket (upper bound: zero digits drop out)
+    // Slices per bucket.  Measured (profiles/r02_msm_accumulate_2p20.txt): a warp of this kernel advances at its own
+    // latency-bound pace (~60 k cycles per mixed addition) whether 1 or 4 warps share a sub-partition, so the time is
+    // (rounds of resident warps) x (chain of one unit): minimise ceil(units / slots) x (avg / S additions + log2 S tree levels).
     p.S = 1;
-    while (p.S < 32 && (size_t)p.W * p.B * p.S * 2 <= kMsmWaveSlots && avg / (2 * p.S) >= 2.0) p.S *= 2;
+    double best_t = 0;
+    for (unsigned S = 1, lg = 0; S <= 32 && (S == 1 || avg / S >= 2.0); S *= 2, lg++) {
+        const size_t units = (size_t)p.W * p.B * S;
+        const double rounds = (double)((units + kMsmWaveSlots - 1) / kMsmWaveSlots);
+        const double t = rounds * (avg / S * 11.0 + lg * 16.0);
+        if (S == 1 || t < best_t) { best_t = t; p.S = S; }
+    }
     p.L = p.B >= 2048 ? 8 : 4;
     if (p.L > p.B) p.L = p.B;
     unsigned off = 0;
