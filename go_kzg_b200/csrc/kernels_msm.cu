@@ -148,12 +148,13 @@ __global__ void __launch_bounds__(128, 4) k_msm_segments(MsmPlan p, const G1J* _
     st_vec(segs + g, out);
 }
 
-// ---- step 6: one CTA (32 quads) per window: sum of the window's segments ----------------------------------------
-__global__ void __launch_bounds__(128) k_msm_windows(MsmPlan p, const G1J* __restrict__ segs, G1J* __restrict__ wsums) {
-    __shared__ G1J part[4];
+// ---- step 6: one CTA (64 quads) per window: sum of the window's segments ----------------------------------------
+#define MSM_WINDOWS_THREADS 256
+__global__ void __launch_bounds__(MSM_WINDOWS_THREADS) k_msm_windows(MsmPlan p, const G1J* __restrict__ segs, G1J* __restrict__ wsums) {
+    __shared__ G1J part[MSM_WINDOWS_THREADS / 32];
     const unsigned w = blockIdx.x, tid = threadIdx.x, quad = tid >> 2, nseg = p.B / p.L;
     G1J acc = G1J::infinity();
-    for (unsigned base = 0; base < nseg; base += 32) {
+    for (unsigned base = 0; base < nseg; base += MSM_WINDOWS_THREADS / 4) {
         const unsigned s = base + quad;
         const bool act = s < nseg;
         G1J v = act ? ld_vec(segs + (size_t)w * nseg + s) : G1J::infinity();
@@ -162,11 +163,13 @@ __global__ void __launch_bounds__(128) k_msm_windows(MsmPlan p, const G1J* __res
     quad_warp_sum(acc);
     if ((tid & 31) == 0) part[tid >> 5] = acc;
     __syncthreads();
-    if (tid < 32) {                                  // warp 0, every quad redundantly
-        for (unsigned j = 1; j < 4; j++) { G1J v = part[j]; quad_add(&acc, &v, true); }
-        if (tid == 0) st_vec(wsums + w, acc);
+    if (tid < 32) {                                  // warp 0: quad j takes the sum of warp j (8 warps, 8 quads), then a shuffle tree
+        G1J v = part[tid >> 2];
+        quad_warp_sum(v);
+        if (tid == 0) st_vec(wsums + w, v);
     }
 }
+static_assert(MSM_WINDOWS_THREADS == 256, "warp 0 holds one quad per warp of the CTA");
 
 // ---- step 7: one CTA, quad w doubles the sum of window w  c w  times; then the sum over the windows -------------
 __global__ void __launch_bounds__(160) k_msm_horner(MsmPlan p, const G1J* __restrict__ wsums, G1J* __restrict__ out) {
@@ -246,7 +249,7 @@ void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* w
     if (quad_ok) k_msm_accumulate<true><<<grid_for(units * 4, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
     else k_msm_accumulate<false><<<grid_for(units, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
     k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L), 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
-    k_msm_windows<<<p.W, 128, 0, st>>>(p, ws.segs, ws.wsums);
+    k_msm_windows<<<p.W, MSM_WINDOWS_THREADS, 0, st>>>(p, ws.segs, ws.wsums);
     k_msm_horner<<<1, (unsigned)((p.W * 4 + 31) / 32 * 32), 0, st>>>(p, ws.wsums, out);
     g_launch_count += 7;
 }

@@ -70,7 +70,7 @@ inline MsmPlan msm_plan(size_t n) {
         const double t = rounds * (avg / S * 11.0 + lg * 16.0);
         if (S == 1 || t < best_t) { best_t = t; p.S = S; }
     }
-    p.L = p.B >= 2048 ? 8 : 4;
+    p.L = 4;
     if (p.L > p.B) p.L = p.B;
     unsigned off = 0;
     for (unsigned w = 0; w < p.W; w++) {
