@@ -184,9 +184,10 @@ __global__ void __launch_bounds__(160) k_msm_horner(MsmPlan p, const G1J* __rest
     const unsigned nwarp = blockDim.x >> 5;
     if ((tid & 31) == 0) part[tid >> 5] = acc;
     __syncthreads();
-    if (tid < 32) {
-        for (unsigned j = 1; j < nwarp; j++) { G1J v = part[j]; quad_add(&acc, &v, true); }
-        if (tid == 0) st_vec(out, acc);
+    if (tid < 32) {                                  // quad j of warp 0 takes the sum of warp j, then a shuffle tree
+        G1J v = (tid >> 2) < nwarp ? part[tid >> 2] : G1J::infinity();
+        quad_warp_sum(v);
+        if (tid == 0) st_vec(out, v);
     }
 }
 
