@@ -487,3 +487,42 @@ def test_fk20_settings_disk_cache(tmp_path, goldens):
     r2 = kzg.FK20MultiSettings(ks, 2 * n, l, offsets=range(4, 9), cache_dir=str(tmp_path))
     assert not r.from_cache and r2.from_cache
     cmp_g1(r2.x_ext_fft(8), a.x_ext_fft(8))
+
+
+def test_concurrent_callers_share_handles(fk4096):
+    """include/b200_kzg.h: handles may be used from any thread concurrently (goroutines in the Go binding).  Eight host
+    threads hammer one FK20 settings object, one KZGSettings (lazily built commitment table) and the handle-less
+    LinCombG1 at once -- different entry points, different sizes -- and every result must equal the sequential one."""
+    import threading
+    polys = blob_polys(8, 4096, first_blob=12000)
+    ks_pts, pts = _random_points(300, 4321, True)
+    scal = kzg.fr_from_ints([random.Random(5).randrange(R) for _ in range(300)])
+    want_single = [kzg.g1_to_compressed(fk4096.fk20_single(polys[i])) for i in range(4)]
+    want_commit = kzg.g1_to_compressed(fk4096.ks.commit_to_poly_batch(polys))
+    want_lin = kzg.g1_to_compressed(kzg.lincomb_g1(pts, scal).reshape(1, 18))
+    want_fft = fk4096.ks.fs.fft(polys[0])
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(3):
+                if t < 4:
+                    got = kzg.g1_to_compressed(fk4096.fk20_single(polys[t]))
+                    assert np.array_equal(got, want_single[t]), "fk20_single thread %d" % t
+                elif t < 6:
+                    got = kzg.g1_to_compressed(fk4096.ks.commit_to_poly_batch(polys))
+                    assert np.array_equal(got, want_commit), "commit thread %d" % t
+                elif t == 6:
+                    got = kzg.g1_to_compressed(kzg.lincomb_g1(pts, scal).reshape(1, 18))
+                    assert np.array_equal(got, want_lin), "lincomb"
+                else:
+                    assert np.array_equal(fk4096.ks.fs.fft(polys[0]), want_fft), "fft"
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
