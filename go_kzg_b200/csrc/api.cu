@@ -675,7 +675,9 @@ extern "C" int b200_toeplitz_part3(b200_fs* fs, const uint64_t* h_ext_fft, size_
 static const size_t kMsmMinTerms = 32;
 static int dev_lincomb(const G1J* d_pts, size_t pts_bstride, const Fr* d_k, int k_is_mont, G1J* work, size_t n,
                        size_t batch, cudaStream_t st, const G1A* fb_table = nullptr, int fb_w = 8) {
-    if (!fb_table && n >= kMsmMinTerms) {
+    // The bucket method pays per MSM a latency-bound tail of ~1.3 ms (bucket reduction + 120 doublings), so several small MSMs
+    // in one call are cheaper as one launch of per-term products (72 ns per term at full occupancy) + fold tree.
+    if (!fb_table && n >= kMsmMinTerms && (batch == 1 || n >= 16384)) {
         DevBuf ws;
         CKS(ws.alloc(msm_workspace_bytes(n), st));
         for (size_t b = 0; b < batch; b++)
