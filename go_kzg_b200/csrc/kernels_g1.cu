@@ -314,9 +314,12 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage_quad(G1J* da
     }
     if (valid && (threadIdx.x & 3u) == 0) { st_vec(p0, s); st_vec(p1, x1); }
 }
-// butterflies per launch up to which a quad per butterfly is used (4 x as many lanes: at most ~1 warp per SM sub-partition)
+// Butterflies per launch up to which a quad per butterfly is used.  OFF by default (0): measured on one polynomial
+// (n = 4096, 2048 butterflies per stage) the quad stage is 2 % faster per call (fft_g1 20.3 -> 20.0 ms) but occupies 4 x the
+// warps, and the aggregate rate of concurrent one-polynomial callers drops by a third (32 callers: 136 -> 91 polynomials/s).
+// Build with -DB200_QUAD_STAGE_MAX=4096 to get it back.
 #ifndef B200_QUAD_STAGE_MAX
-#define B200_QUAD_STAGE_MAX 4096
+#define B200_QUAD_STAGE_MAX 0
 #endif
 bool g1_stage_uses_quads(size_t n_half, size_t batch) { return batch < 16 && n_half * batch <= B200_QUAD_STAGE_MAX; }
 
