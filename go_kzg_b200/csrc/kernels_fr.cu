@@ -226,11 +226,33 @@ void launch_fr_ntt(const FrDomain& dom, const Fr* in, Fr* out, Fr* tmp, unsigned
     P.n = n;
     P.has_scale = 0;
     if (logn <= 12) {
-        P.in = in; P.out = out; P.logm = logn; P.cols = 1;
-        P.in_estride = 1; P.in_cstride = 0; P.out_kstride = 1; P.out_cstride = 0;
+        P.logm = logn;
+        P.in_estride = 1; P.out_kstride = 1;
         P.tw = twbase + n / 2; P.big = nullptr; P.big_stride = 0; P.c_fast = 0;
         if (scale_or_null) { P.has_scale = 1; P.scale = *scale_or_null; }
-        run_pass(P, 1, batch, st);
+        // Many short transforms (the levels of the zero-polynomial product tree, interpolations of CheckProofMulti): one CTA per
+        // transform would be a handful of threads each; pack G transforms into the columns of one CTA's tile instead.
+        size_t done = 0;
+        if (logn <= 10 && batch >= 4) {
+            size_t G = 4096 / n;
+            if (G > 64) G = 64;
+            while (G > batch) G >>= 1;
+            const size_t groups = batch / G;
+            P.in = in; P.out = out; P.cols = (unsigned)G;
+            P.in_cstride = n; P.out_cstride = n;          // column c of group g = transform g G + c
+            for (size_t g0 = 0; g0 < groups; g0 += 65535) {   // grid.x carries the groups, grid.y = 1
+                const size_t ng = groups - g0 < 65535 ? groups - g0 : 65535;
+                NttPass Q = P;
+                Q.in = in + g0 * G * n; Q.out = out + g0 * G * n;
+                run_pass(Q, ng, 1, st);
+            }
+            done = groups * G;
+        }
+        if (done < batch) {
+            P.in = in + done * n; P.out = out + done * n; P.cols = 1;
+            P.in_cstride = 0; P.out_cstride = 0;
+            run_pass(P, 1, batch - done, st);
+        }
         return;
     }
     const unsigned log1 = (logn + 1) / 2, log2 = logn - log1;
@@ -546,13 +568,15 @@ void launch_fr_mul_table(Fr* v, const Fr* table, size_t n, size_t batch, cudaStr
 // a[i] = a[i] / c[i] with Montgomery's trick over DIV_CHUNK consecutive elements per lane: one
 // Fermat inversion per chunk instead of one per element (the reference inverts every element,
 // recover_from_samples.go:89-91 / bls/bignum_kilic.go:103-107; x / 0 = 0 there as here).
-#define DIV_CHUNK 16
+// CHUNK elements per lane: the Fermat inversion (~380 products) is shared by CHUNK divisions (3 products each).  16 keeps many
+// lanes busy for a single polynomial; 64 quarters the inversions for batches (recovery n = 2^14 x 64: 0.71 -> measured below).
+template <int CHUNK>
 __global__ void __launch_bounds__(128) k_fr_div(Fr* a, const Fr* __restrict__ c, size_t total) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t lo = t * DIV_CHUNK;
+    size_t lo = t * CHUNK;
     if (lo >= total) return;
-    size_t cnt = total - lo < DIV_CHUNK ? total - lo : DIV_CHUNK;
-    Fr pre[DIV_CHUNK];
+    size_t cnt = total - lo < CHUNK ? total - lo : CHUNK;
+    Fr pre[CHUNK];
     Fr acc = Fr::one();
     for (size_t i = 0; i < cnt; i++) {
         pre[i] = acc;
@@ -571,7 +595,9 @@ __global__ void __launch_bounds__(128) k_fr_div(Fr* a, const Fr* __restrict__ c,
 void launch_fr_div(Fr* a, const Fr* c, size_t total, cudaStream_t st) {
     ProfScope prof_scope(PROF_MISC, st);
     if (!total) return;
-    k_fr_div<<<grid_for((total + DIV_CHUNK - 1) / DIV_CHUNK, 128), 128, 0, st>>>(a, c, total); g_launch_count++;
+    if (total >= ((size_t)1 << 18)) k_fr_div<64><<<grid_for((total + 63) / 64, 128), 128, 0, st>>>(a, c, total);
+    else k_fr_div<16><<<grid_for((total + 15) / 16, 128), 128, 0, st>>>(a, c, total);
+    g_launch_count++;
 }
 // flags[b] |= 1 if a known sample changed (recover_from_samples.go:103-107);
 // flags[b] |= 2 if zeroEval[i] == 0 disagrees with "missing" (recover_from_samples.go:54-58)

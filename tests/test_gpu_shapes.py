@@ -526,3 +526,16 @@ def test_concurrent_callers_share_handles(fk4096):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n,batch", [(1, 9), (2, 4), (16, 5), (64, 70), (256, 33), (1024, 7), (1000, 6)])
+def test_fft_fr_batches_of_short_transforms(n, batch):
+    """Short transforms are packed several to a CTA tile (kernels_fr.cu: launch_fr_ntt): full groups plus a ragged tail,
+    both directions, against the oracle; n = 1000 pads to 1024 like fft_fr.go:60."""
+    scale = max((n - 1).bit_length(), 4)
+    fs, fo = kzg.FFTSettings(scale), cref.FFTSettings(scale)
+    v = np.stack([kzg.fr_from_ints(random_fr_ints(n, 31 * n + b)) for b in range(batch)])
+    for inv in (False, True):
+        out = fs.fft_batch(v, inv)
+        for b in (0, batch // 2, batch - 1):
+            assert np.array_equal(out[b], fo.fft(v[b], inv))
