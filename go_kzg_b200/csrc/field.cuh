@@ -14,6 +14,7 @@
 // and bls/bls_kilic.go:41-56 of the reference.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include "constants.cuh"
 
 #ifdef __CUDACC__
@@ -445,6 +446,7 @@ typedef Fe<FrParams> Fr;
 }  // namespace b200
 #include "field_fp64_impl.cuh"
 #include "field_karatsuba.cuh"
+#include "field_hybrid.cuh"
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------
@@ -487,6 +489,14 @@ static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) {
     if (fp_on_fp64_pipe()) return fe_sqr_fp64(x);
     return fe_sqr(x);
 }
+#elif defined(B200_HYBRID_MUL)
+// product half on the FP64 pipe, reduction half on the FMA-heavy pipe (field_hybrid.cuh); B200_HYBRID_MUL = 1: both, 2: product only
+static __device__ __noinline__ Fp fp_mul_out(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul_hyb(x, y); }
+#if B200_HYBRID_MUL == 1
+static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { Fp x = *a; return fe_sqr_hyb(x); }
+#else
+static __device__ __noinline__ Fp fp_sqr_out(const Fp* a) { Fp x = *a; return fe_sqr(x); }
+#endif
 #elif defined(B200_KARATSUBA)
 // Karatsuba product half + m * p-only reduction rows (field_karatsuba.cuh); the square keeps fe_sqr
 // (the Karatsuba square needs more FMA-pipe cycles than it saves once its carry adds are counted).

@@ -20,6 +20,9 @@ int main() {
         Fp a = rnd_fp(it < 36 ? it % 6 : 0), b = rnd_fp(it < 36 ? it / 6 : 0);
         Fp w = fe_mul(a, b), g = fe_mul_fp64(a, b);
         if (w != g) { bad++; if (bad < 5) printf("mul mismatch it=%d\n", it); }
+        Fp hm = fe_mul_hyb(a, b), hs = fe_sqr_hyb(a);
+        if (w != hm) { bad++; if (bad < 5) printf("hybrid mul mismatch it=%d\n", it); }
+        if (fe_sqr(a) != hs) { bad++; if (bad < 5) printf("hybrid sqr mismatch it=%d\n", it); }
         Fp ws = fe_sqr(a), gs = fe_sqr_fp64(a);
         if (ws != gs) { bad++; if (bad < 5) printf("sqr mismatch it=%d\n", it); }
     }
