@@ -30,5 +30,16 @@ from .kzg import (  # noqa: F401
     lincomb_g1,
     g1_mul_many,
     generate_testing_setup_g1,
+    generate_testing_setup_g2,
+    g2_generator,
+    g2_add,
+    g2_sub,
+    g2_neg,
+    g2_mul,
+    g2_equal,
+    g2_to_compressed,
+    g2_from_compressed,
+    pairings_verify,
+    pairing,
     R_MOD,
 )

@@ -6,11 +6,13 @@
 #include <atomic>
 #include <stdlib.h>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
 #include "../../include/b200_kzg.h"
 #include "hostutil.cuh"
+#include "pairing.h"
 #include "kernels.h"
 
 using namespace b200;
@@ -206,6 +208,61 @@ extern "C" void b200_g1_to_compressed_many(uint8_t* out, const uint64_t* pts, si
 }
 extern "C" int b200_g1_from_compressed_many(uint64_t* out, const uint8_t* in, size_t n) {
     for (size_t i = 0; i < n; i++) CKS(b200_g1_from_compressed(out + 18 * i, in + 48 * i));
+    return B200_OK;
+}
+
+// ---- G2 and the pairing (pairing.h): host code, verification side only -------------------------------------------
+extern "C" void b200_g2_generator(uint64_t* out) { g2_to_abi(out, g2_generator()); }
+extern "C" void b200_g2_add(uint64_t* dst, const uint64_t* a, const uint64_t* b) { g2_to_abi(dst, g2_add(g2_from_abi(a), g2_from_abi(b))); }
+extern "C" void b200_g2_sub(uint64_t* dst, const uint64_t* a, const uint64_t* b) { g2_to_abi(dst, g2_sub(g2_from_abi(a), g2_from_abi(b))); }
+extern "C" void b200_g2_neg(uint64_t* dst) { g2_to_abi(dst, g2_neg(g2_from_abi(dst))); }
+extern "C" void b200_g2_mul(uint64_t* dst, const uint64_t* a, const uint64_t* k) { g2_to_abi(dst, g2_mul(g2_from_abi(a), fr_load_canon(k))); }
+extern "C" int b200_g2_equal(const uint64_t* a, const uint64_t* b) { return g2_equal(g2_from_abi(a), g2_from_abi(b)) ? 1 : 0; }
+extern "C" void b200_g2_to_compressed(uint8_t* out, const uint64_t* p) { g2_compress(out, g2_from_abi(p)); }
+extern "C" int b200_g2_from_compressed(uint64_t* out, const uint8_t* in) {
+    G2J p;
+    if (g2_decompress(p, in)) return B200_ERR_BAD_INPUT;
+    g2_to_abi(out, p);
+    return B200_OK;
+}
+// setup.go:9-26 GenerateTestingSetup, G2 half: out[i] = secret^i * GenG2 (host: ~n scalar multiplications)
+extern "C" int b200_generate_testing_setup_g2(const uint64_t* secret, size_t n, uint64_t* out) {
+    const Fr s = fr_from_abi_mont(secret);
+    Fr pw = Fr::one();
+    const G2J g = g2_generator();
+    for (size_t i = 0; i < n; i++) {
+        g2_to_abi(out + 36 * i, g2_mul(g, fe_from_mont(pw)));
+        pw = fe_mul(pw, s);
+    }
+    return B200_OK;
+}
+static bool abi_coords_canonical(const uint64_t* p, int coords) {
+    for (int i = 0; i < coords; i++) if (!fp_abi_canonical(p + 6 * i)) return false;
+    return true;
+}
+// bls/bls_kilic.go:152-158 PairingsVerify: e(a1, a2) == e(b1, b2).  Points off their curve -> B200_ERR_BAD_INPUT
+// (kilic's engine assumes valid points; an answer for invalid ones would be meaningless).
+extern "C" int b200_pairings_verify(const uint64_t* a1, const uint64_t* a2, const uint64_t* b1, const uint64_t* b2, int* ok) {
+    *ok = 0;
+    if (!abi_coords_canonical(a1, 3) || !abi_coords_canonical(b1, 3) || !abi_coords_canonical(a2, 6) || !abi_coords_canonical(b2, 6))
+        return B200_ERR_BAD_INPUT;
+    const G1J p1 = g1_from_abi(a1), p2 = g1_from_abi(b1);
+    const G2J q1 = g2_from_abi(a2), q2 = g2_from_abi(b2);
+    if (!g1_on_curve(p1) || !g1_on_curve(p2) || !g2_on_curve(q1) || !g2_on_curve(q2)) return B200_ERR_BAD_INPUT;
+    *ok = pairings_verify(p1, q1, p2, q2) ? 1 : 0;
+    return B200_OK;
+}
+// e(p, q) as the 12 canonical Fp coefficients (a_0, b_0, .., a_5, b_5) of sum (a_i + b_i u) w^i, w^6 = 1 + u
+extern "C" int b200_pairing(const uint64_t* p, const uint64_t* q, uint64_t* out) {
+    if (!abi_coords_canonical(p, 3) || !abi_coords_canonical(q, 6)) return B200_ERR_BAD_INPUT;
+    const G1J pp = g1_from_abi(p);
+    const G2J qq = g2_from_abi(q);
+    if (!g1_on_curve(pp) || !g2_on_curve(qq)) return B200_ERR_BAD_INPUT;
+    const Fp12 e = pairing(pp, qq);
+    for (int i = 0; i < 6; i++) {
+        Fp a = fe_from_mont(e.c[i].c0), b = fe_from_mont(e.c[i].c1);
+        memcpy(out + 12 * i, a.l, 48); memcpy(out + 12 * i + 6, b.l, 48);
+    }
     return B200_OK;
 }
 
@@ -841,6 +898,7 @@ struct b200_ks {
     int fb_w = 8;                 // its window bits
     size_t fb_n = 0;
     std::vector<G1A*> retired;    // smaller tables superseded by d_fb_table (freed with the settings)
+    std::vector<G2J> h_secret_g2; // SecretG2 (kzg.go:16), host copy: only the verification entry points read it
 };
 
 // Fixed-base window tables.  Window bits: 8 by default (384 KiB per base: 1.5 GiB for the 4096 commitment bases,
@@ -1011,6 +1069,131 @@ extern "C" int b200_check_proof_multi_g1_batch(b200_ks* ks, const uint64_t* comm
     CK(cudaMemcpyAsync(x_pow_n, xn.p, batch * 32, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return B200_OK;
+}
+
+// KZGSettings.SecretG2 (kzg.go:14-16).  Only CheckProofSingle / CheckProofMulti read it (SecretG2[1], SecretG2[len(ys)]), on the
+// host; call once, before the handle is shared between threads.  n may be smaller than the G1 half (e.g. only the entries the
+// verifier needs); every point must be on the twist.
+extern "C" int b200_kzg_settings_set_secret_g2(b200_ks* ks, const uint64_t* secret_g2, size_t n) {
+    std::vector<G2J> pts(n);
+    for (size_t i = 0; i < n; i++) {
+        if (!abi_coords_canonical(secret_g2 + 36 * i, 6)) return B200_ERR_BAD_INPUT;
+        pts[i] = g2_from_abi(secret_g2 + 36 * i);
+        if (!g2_on_curve(pts[i])) return B200_ERR_BAD_INPUT;
+    }
+    std::lock_guard<std::mutex> lk(ks->mu);
+    ks->h_secret_g2.swap(pts);
+    return B200_OK;
+}
+
+// ok[i] = e(lhs[i], [1]_2) == e(proofs[i], rhs[i]) on the host cores, one pairing check per item
+static int pairing_checks(const uint64_t* lhs, const uint64_t* proofs, const std::vector<G2J>& rhs, size_t batch, uint8_t* ok) {
+    for (size_t i = 0; i < batch; i++)
+        if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
+    const G2J gen = g2_generator();
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > batch) nt = (unsigned)batch;
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (size_t i; (i = next.fetch_add(1)) < batch;)
+            ok[i] = pairings_verify(g1_from_abi(lhs + 18 * i), gen, g1_from_abi(proofs + 18 * i), rhs[i]) ? 1 : 0;
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return B200_OK;
+}
+
+// kzg_single_proofs.go:57-75 CheckProofSingle for `batch` (commitment, proof, x, y): [commitment - y G]_1 on the device
+// (b200_check_proof_single_g1_batch), [s - x]_2 = SecretG2[1] - x GenG2 (:59-62) and the pairing check (:74) on the host.
+extern "C" int b200_check_proof_single_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                             const uint64_t* ys, size_t batch, uint8_t* ok) {
+    if (ks->h_secret_g2.size() < 2) return B200_ERR_TOO_SMALL;          // SecretG2[1]
+    if (batch == 0) return B200_OK;
+    std::vector<uint64_t> lhs(batch * 18);
+    CKS(b200_check_proof_single_g1_batch(commitments, ys, batch, lhs.data()));
+    const G2J gen = g2_generator(), s2 = ks->h_secret_g2[1];
+    std::vector<G2J> rhs(batch);
+    for (size_t i = 0; i < batch; i++) {
+        if (!fr_canon_valid(xs + 4 * i)) return B200_ERR_BAD_INPUT;
+        rhs[i] = g2_sub(s2, g2_mul(gen, fr_load_canon(xs + 4 * i)));
+    }
+    return pairing_checks(lhs.data(), proofs, rhs, batch, ok);
+}
+extern "C" int b200_check_proof_single(b200_ks* ks, const uint64_t* commitment, const uint64_t* proof, const uint64_t* x, const uint64_t* y,
+                                       int* ok) {
+    uint8_t r = 0;
+    *ok = 0;
+    CKS(b200_check_proof_single_batch(ks, commitment, proof, x, y, 1, &r));
+    *ok = r;
+    return B200_OK;
+}
+// kzg_multi_proofs.go:47-88 CheckProofMulti for `batch` samples of n values: interpolation, MSM and subtraction on the device
+// (b200_check_proof_multi_g1_batch), [s^n - x^n]_2 = SecretG2[n] - x^n GenG2 (:71-76) and the pairing check (:87) on the host.
+extern "C" int b200_check_proof_multi_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                            const uint64_t* ys, size_t n, size_t batch, uint8_t* ok) {
+    if (ks->h_secret_g2.size() <= n) return B200_ERR_TOO_SMALL;         // SecretG2[len(ys)]
+    if (batch == 0) return B200_OK;
+    std::vector<uint64_t> lhs(batch * 18), xn(batch * 4);
+    CKS(b200_check_proof_multi_g1_batch(ks, commitments, xs, ys, n, batch, lhs.data(), xn.data()));
+    const G2J gen = g2_generator(), sn = ks->h_secret_g2[n];
+    std::vector<G2J> rhs(batch);
+    for (size_t i = 0; i < batch; i++) rhs[i] = g2_sub(sn, g2_mul(gen, fr_load_canon(xn.data() + 4 * i)));
+    return pairing_checks(lhs.data(), proofs, rhs, batch, ok);
+}
+extern "C" int b200_check_proof_multi(b200_ks* ks, const uint64_t* commitment, const uint64_t* proof, const uint64_t* x, const uint64_t* ys,
+                                      size_t n, int* ok) {
+    uint8_t r = 0;
+    *ok = 0;
+    CKS(b200_check_proof_multi_batch(ks, commitment, proof, x, ys, n, 1, &r));
+    *ok = r;
+    return B200_OK;
+}
+
+// Aggregated verification: `batch` proofs with ONE pairing check.  e(A_i, [1]_2) == e(proof_i, [t]_2 - c_i [1]_2) for all i
+// (single: A_i = commitment_i - y_i G, t = s, c_i = x_i; multi: A_i = commitment_i - [I_i(s)]_1, t = s^n, c_i = x_i^n)
+// is, for scalars r_i the prover cannot predict, equivalent (up to probability ~batch / r) to
+//     e(sum r_i A_i + sum (r_i c_i) proof_i, [1]_2) == e(sum r_i proof_i, [t]_2):
+// three MSMs of `batch` terms on the device (bucket MSM from 32 terms on) and one pairing on the host.  rs: batch canonical
+// scalars from the caller's CSPRNG (the Go shim uses crypto/rand); a single r_i == 0 would drop proof i from the check,
+// so zeros are rejected.
+static int aggregate_check(const uint64_t* a_pts, const uint64_t* proofs, const uint64_t* cs, const uint64_t* rs, size_t batch,
+                           const G2J& t2, int* ok) {
+    std::vector<uint64_t> rc(batch * 4);
+    for (size_t i = 0; i < batch; i++) {
+        if (!fr_canon_valid(rs + 4 * i) || !fr_canon_valid(cs + 4 * i)) return B200_ERR_BAD_INPUT;
+        const Fr r = fr_load_canon(rs + 4 * i);
+        if (r.is_zero()) return B200_ERR_BAD_INPUT;
+        fr_store_canon(rc.data() + 4 * i, fe_mul(fe_to_mont(r), fr_load_canon(cs + 4 * i)));
+        if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
+    }
+    uint64_t sa[18], sb[18], sp[18];
+    CKS(b200_g1_lincomb(a_pts, rs, batch, sa));
+    CKS(b200_g1_lincomb(proofs, rc.data(), batch, sb));
+    CKS(b200_g1_lincomb(proofs, rs, batch, sp));
+    const G1J lhs = g1_add(g1_from_abi(sa), g1_from_abi(sb));
+    *ok = pairings_verify(lhs, g2_generator(), g1_from_abi(sp), t2) ? 1 : 0;
+    return B200_OK;
+}
+extern "C" int b200_check_proof_single_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                                 const uint64_t* ys, const uint64_t* rs, size_t batch, int* ok) {
+    *ok = 0;
+    if (ks->h_secret_g2.size() < 2) return B200_ERR_TOO_SMALL;
+    if (batch == 0) { *ok = 1; return B200_OK; }
+    std::vector<uint64_t> a(batch * 18);
+    CKS(b200_check_proof_single_g1_batch(commitments, ys, batch, a.data()));
+    return aggregate_check(a.data(), proofs, xs, rs, batch, ks->h_secret_g2[1], ok);
+}
+extern "C" int b200_check_proof_multi_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                                const uint64_t* ys, size_t n, const uint64_t* rs, size_t batch, int* ok) {
+    *ok = 0;
+    if (ks->h_secret_g2.size() <= n) return B200_ERR_TOO_SMALL;
+    if (batch == 0) { *ok = 1; return B200_OK; }
+    std::vector<uint64_t> a(batch * 18), xn(batch * 4);
+    CKS(b200_check_proof_multi_g1_batch(ks, commitments, xs, ys, n, batch, a.data(), xn.data()));
+    return aggregate_check(a.data(), proofs, xn.data(), rs, batch, ks->h_secret_g2[n], ok);
 }
 
 // ------------------------------------------------------------------------------ FK20

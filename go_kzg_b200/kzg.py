@@ -90,6 +90,25 @@ def lib():
     L.b200_evaluate_poly_in_evaluation_form_batch.argtypes = [vp, vp, vp, sz, sz, i32, vp]
     L.b200_check_proof_single_g1_batch.argtypes = [vp, vp, sz, vp]
     L.b200_check_proof_multi_g1_batch.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp]
+    for name in ("b200_g2_add", "b200_g2_sub", "b200_g2_mul", "b200_g2_to_compressed"):
+        getattr(L, name).argtypes = [vp, vp, vp] if name != "b200_g2_to_compressed" else [vp, vp]
+        getattr(L, name).restype = None
+    L.b200_g2_generator.argtypes = [vp]
+    L.b200_g2_generator.restype = None
+    L.b200_g2_neg.argtypes = [vp]
+    L.b200_g2_neg.restype = None
+    L.b200_g2_equal.argtypes = [vp, vp]
+    L.b200_g2_from_compressed.argtypes = [vp, vp]
+    L.b200_generate_testing_setup_g2.argtypes = [vp, sz, vp]
+    L.b200_pairings_verify.argtypes = [vp, vp, vp, vp, C.POINTER(i32)]
+    L.b200_pairing.argtypes = [vp, vp, vp]
+    L.b200_kzg_settings_set_secret_g2.argtypes = [vp, vp, sz]
+    L.b200_check_proof_single.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i32)]
+    L.b200_check_proof_single_batch.argtypes = [vp, vp, vp, vp, vp, sz, vp]
+    L.b200_check_proof_multi.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(i32)]
+    L.b200_check_proof_multi_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
+    L.b200_check_proof_single_aggregate.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.POINTER(i32)]
+    L.b200_check_proof_multi_aggregate.argtypes = [vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(i32)]
     L.b200_g1_lincomb.argtypes = [vp, vp, sz, vp]
     L.b200_g1_mul_many.argtypes = [vp, vp, sz, vp]
     L.b200_fft_settings_new.argtypes = [C.c_uint8, C.POINTER(vp)]
@@ -166,6 +185,10 @@ def _fr(a) -> np.ndarray:
 
 def _g1(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 18)
+
+
+def _g2(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 36)
 
 
 def _raise(status: int, errors=(), what: str = ""):
@@ -270,7 +293,8 @@ def load_trusted_setup(source, device: bool = True) -> dict:
     """eth/globals.go:33-49: parses a trusted_setup.json-shaped document ({"setup_G1": [...], "setup_G2": [...],
     "setup_G1_lagrange": [...]}, hex strings without 0x).  Returns {"setup_G1": (n, 18) points,
     "setup_G1_lagrange": (n, 18) points ALREADY in reverse bit order (eth/globals.go:48 kzgSetupLagrange),
-    "setup_G2": (m, 96) raw compressed bytes -- G2 stays with the caller's pairing backend}.
+    "setup_G2": (m, 96) raw compressed bytes (g2_from_compressed decodes the entries a verifier needs; a decode includes
+    the subgroup check, ~ms per point on the host)}.
     `source` is a path, a JSON string / bytes, or an already parsed dict."""
     import json
     if isinstance(source, dict):
@@ -300,6 +324,89 @@ def check_proof_single_g1(commitments, ys) -> np.ndarray:
     out = np.zeros_like(c)
     _raise(lib().b200_check_proof_single_g1_batch(_p(c), _p(y), c.shape[0], _p(out)), what="CheckProofSingle (G1 side)")
     return out
+
+
+# ---- G2 and the pairing: host code of the library (verification side; bls/bls_kilic.go:69-104,123-130,152-158) ----
+def g2_generator() -> np.ndarray:
+    out = np.zeros(36, dtype=np.uint64)
+    lib().b200_g2_generator(_p(out))
+    return out
+
+
+def _g2_binop(name, a, b) -> np.ndarray:
+    a, b = _g2(a)[0].copy(), np.ascontiguousarray(b, dtype=np.uint64).reshape(-1)
+    out = np.zeros(36, dtype=np.uint64)
+    getattr(lib(), name)(_p(out), _p(a), _p(b))
+    return out
+
+
+def g2_add(a, b) -> np.ndarray:
+    return _g2_binop("b200_g2_add", a, b)
+
+
+def g2_sub(a, b) -> np.ndarray:
+    return _g2_binop("b200_g2_sub", a, b)
+
+
+def g2_mul(a, k: int) -> np.ndarray:
+    """bls/bls_kilic.go:80-84 MulG2 (k an integer, reduced mod r)"""
+    return _g2_binop("b200_g2_mul", a, fr_from_ints([k % R_MOD])[0])
+
+
+def g2_neg(a) -> np.ndarray:
+    out = _g2(a)[0].copy()
+    lib().b200_g2_neg(_p(out))
+    return out
+
+
+def g2_equal(a, b) -> bool:
+    a, b = _g2(a)[0].copy(), _g2(b)[0].copy()
+    return bool(lib().b200_g2_equal(_p(a), _p(b)))
+
+
+def g2_to_compressed(pts) -> np.ndarray:
+    """bls/bls_kilic.go:123-125 ToCompressedG2 per point -> (n, 96) uint8"""
+    g = _g2(pts)
+    out = np.zeros((g.shape[0], 96), dtype=np.uint8)
+    for i in range(g.shape[0]):
+        row = np.ascontiguousarray(g[i])
+        lib().b200_g2_to_compressed(_p(out[i]), _p(row))
+    return out
+
+
+def g2_from_compressed(b) -> np.ndarray:
+    """bls/bls_kilic.go:127-130 FromCompressedG2 per point; a bad encoding is an error, as in the reference"""
+    raw = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 96)
+    out = np.zeros((raw.shape[0], 36), dtype=np.uint64)
+    for i in range(raw.shape[0]):
+        row = np.ascontiguousarray(raw[i])
+        _raise(lib().b200_g2_from_compressed(_p(out[i]), _p(row)), errors=(BAD_INPUT,), what="FromCompressedG2")
+    return out
+
+
+def generate_testing_setup_g2(secret: int, n: int) -> np.ndarray:
+    """setup.go:9-26 GenerateTestingSetup (G2 half): [secret^i * GenG2] for i < n (host: one scalar multiplication each)."""
+    out = np.zeros((n, 36), dtype=np.uint64)
+    s = fr_from_ints([secret % R_MOD])
+    _raise(lib().b200_generate_testing_setup_g2(_p(s), n, _p(out)), what="GenerateTestingSetup (G2)")
+    return out
+
+
+def pairings_verify(a1, a2, b1, b2) -> bool:
+    """bls/bls_kilic.go:152-158 PairingsVerify: e(a1, a2) == e(b1, b2)"""
+    a1, b1 = _g1(a1)[0].copy(), _g1(b1)[0].copy()
+    a2, b2 = _g2(a2)[0].copy(), _g2(b2)[0].copy()
+    ok = C.c_int(0)
+    _raise(lib().b200_pairings_verify(_p(a1), _p(a2), _p(b1), _p(b2), C.byref(ok)), what="PairingsVerify")
+    return bool(ok.value)
+
+
+def pairing(p, q) -> list:
+    """e(p, q) as 12 integers a_0, b_0, .., a_5, b_5: sum (a_i + b_i u) w^i in Fp2[w] / (w^6 - (1 + u))"""
+    p, q = _g1(p)[0].copy(), _g2(q)[0].copy()
+    out = np.zeros((12, 6), dtype=np.uint64)
+    _raise(lib().b200_pairing(_p(p), _p(q), _p(out)), what="pairing")
+    return [sum(int(v) << (64 * j) for j, v in enumerate(row)) for row in out]
 
 
 def lincomb_g1(points, scalars) -> np.ndarray:
@@ -466,14 +573,19 @@ class FFTSettings:
 
 
 class KZGSettings:
-    """kzg.go:11-36.  secret_g2 stays with the caller's CPU backend; only its length is checked."""
+    """kzg.go:11-36.  secret_g2 (optional, (m, 36) uint64): the points CheckProofSingle / CheckProofMulti read; it may
+    hold fewer entries than SecretG1 (the checks need SecretG2[1] and SecretG2[len(ys)]); secret_g2_len is the length
+    NewKZGSettings compares with len(SecretG1) (kzg.go:22-24) and defaults to it."""
 
-    def __init__(self, fs: FFTSettings, secret_g1, secret_g2_len=None):
+    def __init__(self, fs: FFTSettings, secret_g1, secret_g2_len=None, secret_g2=None):
         g = _g1(secret_g1)
         h = C.c_void_p()
         n2 = g.shape[0] if secret_g2_len is None else secret_g2_len
         _raise(lib().b200_kzg_settings_new(fs.h, _p(g), g.shape[0], n2, C.byref(h)), what="NewKZGSettings")
         self.h, self.fs = h, fs
+        if secret_g2 is not None:
+            q = _g2(secret_g2)
+            _raise(lib().b200_kzg_settings_set_secret_g2(h, _p(q), q.shape[0]), what="NewKZGSettings (SecretG2)")
         self._g1_bytes = g if g.shape[0] <= (1 << 16) else None   # for setup_digest(); large setups are hashed at construction
         self._digest = None if self._g1_bytes is not None else _digest_points(g)
 
@@ -540,6 +652,68 @@ class KZGSettings:
         xn = np.zeros((batch, 4), dtype=np.uint64)
         _raise(lib().b200_check_proof_multi_g1_batch(self.h, _p(c), _p(x), _p(y), n, batch, _p(out), _p(xn)), what="CheckProofMulti (G1 side)")
         return out, xn
+
+    def check_proof_single(self, commitment, proof, x, y) -> bool:
+        """kzg_single_proofs.go:57-75 CheckProofSingle (x, y: (4,) uint64 canonical)"""
+        c, pr, xx, yy = _g1(commitment)[0].copy(), _g1(proof)[0].copy(), _fr(x)[0].copy(), _fr(y)[0].copy()
+        ok = C.c_int(0)
+        _raise(lib().b200_check_proof_single(self.h, _p(c), _p(pr), _p(xx), _p(yy), C.byref(ok)), what="CheckProofSingle")
+        return bool(ok.value)
+
+    def check_proof_single_batch(self, commitments, proofs, xs, ys) -> np.ndarray:
+        """CheckProofSingle for a batch: the G1 sides in one device call, the pairing checks spread over the host cores."""
+        c, pr, xx, yy = _g1(commitments), _g1(proofs), _fr(xs), _fr(ys)
+        batch = c.shape[0]
+        assert pr.shape[0] == batch and xx.shape[0] == batch and yy.shape[0] == batch
+        ok = np.zeros(batch, dtype=np.uint8)
+        _raise(lib().b200_check_proof_single_batch(self.h, _p(c), _p(pr), _p(xx), _p(yy), batch, _p(ok)), what="CheckProofSingle")
+        return ok.astype(bool)
+
+    def check_proof_multi(self, commitment, proof, x, ys) -> bool:
+        """kzg_multi_proofs.go:47-88 CheckProofMulti (ys: (n, 4) uint64, n a power of two)"""
+        c, pr, xx, yy = _g1(commitment)[0].copy(), _g1(proof)[0].copy(), _fr(x)[0].copy(), _fr(ys)
+        ok = C.c_int(0)
+        _raise(lib().b200_check_proof_multi(self.h, _p(c), _p(pr), _p(xx), _p(yy), yy.shape[0], C.byref(ok)), what="CheckProofMulti")
+        return bool(ok.value)
+
+    def check_proof_multi_batch(self, commitments, proofs, xs, ys) -> np.ndarray:
+        """CheckProofMulti for a batch of samples: ys (batch, n, 4)"""
+        c, pr, xx = _g1(commitments), _g1(proofs), _fr(xs)
+        y = np.ascontiguousarray(ys, dtype=np.uint64)
+        batch, n = y.shape[0], y.shape[1]
+        assert c.shape[0] == batch and pr.shape[0] == batch and xx.shape[0] == batch
+        ok = np.zeros(batch, dtype=np.uint8)
+        _raise(lib().b200_check_proof_multi_batch(self.h, _p(c), _p(pr), _p(xx), _p(y), n, batch, _p(ok)), what="CheckProofMulti")
+        return ok.astype(bool)
+
+    @staticmethod
+    def _random_scalars(batch: int) -> np.ndarray:
+        import secrets
+        return fr_from_ints([secrets.randbelow(R_MOD - 1) + 1 for _ in range(batch)])
+
+    def check_proof_single_aggregate(self, commitments, proofs, xs, ys, rs=None) -> bool:
+        """All proofs of the batch with one pairing (random linear combination; three device MSMs).  rs: non-zero
+        unpredictable scalars, drawn from `secrets` when omitted."""
+        c, pr, xx, yy = _g1(commitments), _g1(proofs), _fr(xs), _fr(ys)
+        batch = c.shape[0]
+        assert pr.shape[0] == batch and xx.shape[0] == batch and yy.shape[0] == batch
+        r = self._random_scalars(batch) if rs is None else _fr(rs)
+        ok = C.c_int(0)
+        _raise(lib().b200_check_proof_single_aggregate(self.h, _p(c), _p(pr), _p(xx), _p(yy), _p(r), batch, C.byref(ok)),
+               what="CheckProofSingle (aggregate)")
+        return bool(ok.value)
+
+    def check_proof_multi_aggregate(self, commitments, proofs, xs, ys, rs=None) -> bool:
+        """CheckProofMulti for a batch of samples (ys (batch, n, 4)) with one pairing."""
+        c, pr, xx = _g1(commitments), _g1(proofs), _fr(xs)
+        y = np.ascontiguousarray(ys, dtype=np.uint64)
+        batch, n = y.shape[0], y.shape[1]
+        assert c.shape[0] == batch and pr.shape[0] == batch and xx.shape[0] == batch
+        r = self._random_scalars(batch) if rs is None else _fr(rs)
+        ok = C.c_int(0)
+        _raise(lib().b200_check_proof_multi_aggregate(self.h, _p(c), _p(pr), _p(xx), _p(y), n, _p(r), batch, C.byref(ok)),
+               what="CheckProofMulti (aggregate)")
+        return bool(ok.value)
 
     def commit_to_poly_batch(self, coeffs) -> np.ndarray:
         c = np.ascontiguousarray(coeffs, dtype=np.uint64)

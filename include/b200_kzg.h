@@ -79,6 +79,28 @@ int b200_g1_from_compressed(uint64_t out[18], const uint8_t in[48]);            
 void b200_g1_to_compressed_many(uint8_t* out, const uint64_t* pts, size_t n);
 int b200_g1_from_compressed_many(uint64_t* out, const uint8_t* in, size_t n);
 
+/* G2 and the pairing: HOST code (go_kzg_b200/csrc/pairing.h), verification side only -- two G2 operations and one pairing
+ * check per proof.  G2 = Jacobian X, Y, Z over Fp2, each coordinate (c0, c1) of 6 x uint64 canonical limbs: 36 x uint64 =
+ * 288 bytes, infinity <=> Z == 0 (all-zero value = infinity).  Compressed: 96 bytes, ZCash form (x.c1 || x.c0). */
+void b200_g2_generator(uint64_t out[36]);                                           /* bls/bls_kilic.go:24 GenG2 */
+void b200_g2_add(uint64_t dst[36], const uint64_t a[36], const uint64_t b[36]);     /* bls/bls_kilic.go:86 AddG2 */
+void b200_g2_sub(uint64_t dst[36], const uint64_t a[36], const uint64_t b[36]);     /* bls/bls_kilic.go:90 SubG2 */
+void b200_g2_neg(uint64_t dst[36]);                                                 /* bls/bls_kilic.go:94 NegG2 (in place) */
+void b200_g2_mul(uint64_t dst[36], const uint64_t a[36], const uint64_t k[4]);      /* bls/bls_kilic.go:80 MulG2 */
+int b200_g2_equal(const uint64_t a[36], const uint64_t b[36]);                      /* bls/bls_kilic.go:110 EqualG2 */
+void b200_g2_to_compressed(uint8_t out[96], const uint64_t p[36]);                  /* bls/bls_kilic.go:123 ToCompressedG2 */
+/* bls/bls_kilic.go:127 FromCompressedG2: flags, coordinates < p, curve equation, prime-order subgroup; else B200_ERR_BAD_INPUT */
+int b200_g2_from_compressed(uint64_t out[36], const uint8_t in[96]);
+/* setup.go:9-26 GenerateTestingSetup, G2 half: out[i] = secret^i * GenG2 (host, one scalar multiplication per entry) */
+int b200_generate_testing_setup_g2(const uint64_t secret[4], size_t n, uint64_t* out);
+/* bls/bls_kilic.go:152-158 PairingsVerify: *ok = (e(a1, a2) == e(b1, b2)).  Non-canonical coordinates or points off their
+ * curve -> B200_ERR_BAD_INPUT. */
+int b200_pairings_verify(const uint64_t a1[18], const uint64_t a2[36], const uint64_t b1[18], const uint64_t b2[36], int* ok);
+/* e(p, q) itself: the 12 canonical Fp coefficients a_0, b_0, .., a_5, b_5 (6 x uint64 each) of sum (a_i + b_i u) w^i in
+ * Fp2[w] / (w^6 - (1 + u)), Fp2 = Fp[u] / (u^2 + 1); exponent (p^12 - 1) / r exactly (tests compare it with an independent
+ * restatement). */
+int b200_pairing(const uint64_t p[18], const uint64_t q[36], uint64_t out[72]);
+
 /* bls/bls_kilic.go:118-121 FromCompressedG1 over an array ON THE DEVICE (eth/globals.go:33-49 decodes 3 x 4096 points
  * at start-up; larger setups hold millions): flags, x < p, curve equation, prime-order subgroup.  ok (may be NULL)
  * gets 1 per accepted point; a rejected encoding -> B200_ERR_BAD_INPUT with that output zeroed. */
@@ -140,7 +162,7 @@ int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t* samples, c
 
 /* ------------------------------------------------------------------ KZGSettings ------------ */
 /* kzg.go:21-36 NewKZGSettings: n_g1 != n_g2 -> LEN_MISMATCH; n_g1 < MaxWidth -> TOO_SMALL.
- * The G2 half stays on the caller's CPU backend (verification only); only its length is checked. */
+ * Only the length of the G2 half is checked here; b200_kzg_settings_set_secret_g2 hands the points over (verification only). */
 int b200_kzg_settings_new(b200_fs* fs, const uint64_t* secret_g1, size_t n_g1, size_t n_g2, b200_ks** out);
 void b200_kzg_settings_free(b200_ks* ks);
 /* kzg_single_proofs.go:17-19 CommitToPoly = LinCombG1(SecretG1[:n], coeffs) */
@@ -156,6 +178,32 @@ int b200_check_proof_single_g1_batch(const uint64_t* commitments, const uint64_t
  * e(out_g1[b], [1]_2) == e(proof[b], SecretG2[n] - [x^n]_2).  n > MaxWidth -> TOO_LARGE (the reference panics). */
 int b200_check_proof_multi_g1_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* xs, const uint64_t* ys, size_t n,
                                     size_t batch, uint64_t* out_g1, uint64_t* x_pow_n);
+
+/* KZGSettings.SecretG2 (kzg.go:14-16): host copy of the n first points, read only by the two checks below (SecretG2[1],
+ * SecretG2[len(ys)]).  Call once, before the handle is shared between threads.  Points off the twist -> B200_ERR_BAD_INPUT. */
+int b200_kzg_settings_set_secret_g2(b200_ks* ks, const uint64_t* secret_g2, size_t n);
+/* kzg_single_proofs.go:57-75 CheckProofSingle, complete: G1 side on the device, [s - x]_2 and the pairing check on the host.
+ * *ok / ok[i] = 1 if the proof verifies.  SecretG2 not set (fewer than 2 points) -> B200_ERR_TOO_SMALL. */
+int b200_check_proof_single(b200_ks* ks, const uint64_t commitment[18], const uint64_t proof[18], const uint64_t x[4],
+                            const uint64_t y[4], int* ok);
+int b200_check_proof_single_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                  const uint64_t* ys, size_t batch, uint8_t* ok);
+/* kzg_multi_proofs.go:47-88 CheckProofMulti, complete (n = len(ys), power of two; needs SecretG2[n]); the batch form takes
+ * `batch` samples (commitment, proof, x, ys[n]) and spreads the pairing checks over the host cores. */
+int b200_check_proof_multi(b200_ks* ks, const uint64_t commitment[18], const uint64_t proof[18], const uint64_t x[4],
+                           const uint64_t* ys, size_t n, int* ok);
+int b200_check_proof_multi_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                 const uint64_t* ys, size_t n, size_t batch, uint8_t* ok);
+
+/* Aggregated forms (not in the reference): all `batch` proofs with ONE pairing.  With caller-supplied unpredictable non-zero
+ * scalars rs[i] (canonical Fr, from a CSPRNG), the per-proof equations are folded into
+ *   e(sum r_i A_i + sum r_i c_i proof_i, [1]_2) == e(sum r_i proof_i, [t]_2)   (A_i, c_i, t as in the functions above):
+ * three device MSMs of `batch` terms and one host pairing.  *ok = 1 iff the folded equation holds (a forged proof passes with
+ * probability ~ batch / r).  Use the per-proof forms to find WHICH proof of a failing batch is bad. */
+int b200_check_proof_single_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                      const uint64_t* ys, const uint64_t* rs, size_t batch, int* ok);
+int b200_check_proof_multi_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
+                                     const uint64_t* ys, size_t n, const uint64_t* rs, size_t batch, int* ok);
 
 /* ------------------------------------------------------------------ FK20 ------------------- */
 /* kzg.go:43-64 NewFK20SingleSettings(ks, n2) */

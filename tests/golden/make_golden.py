@@ -64,6 +64,12 @@ def main():
     g["trusted_setup"] = {"src": "eth/trusted_setup.json", "n": len(ts["setup_G1"]),
                           "roots_of_unity_first4": [str(v) for v in ts["roots_of_unity"][:4]],
                           "secret_verified": "1337"}
+    # G2: generator (bls/bls_hbls.go:27-30, decimal) and the head of setup_G2 (compressed, = 1337^i * GenG2) plus the
+    # entries CheckProofMulti reads for n = 8, 16 -- pins G2 compression / decompression / scalar multiplication
+    g["g2_generator"] = {"src": "bls/bls_hbls.go:27-30", "x0x1y0y1": re.findall(r'D\[[01]\]\.SetString\("(\d{100,})", 10\)', h)[:4]}
+    assert len(g["g2_generator"]["x0x1y0y1"]) == 4
+    g["trusted_setup_g2"] = {"src": "eth/trusted_setup.json setup_G2", "n": len(ts["setup_G2"]),
+                             "entries": {str(i): ts["setup_G2"][i] for i in (0, 1, 2, 3, 8, 16, 4095)}}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
         json.dump(g, f, indent=1)
     with open(os.path.join(HERE, "trusted_setup_g1.bin"), "wb") as f:
