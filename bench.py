@@ -200,6 +200,29 @@ def run_components(kzg, L, fk, fs, torch, dist, rank, world, max_over_ranks, bar
     out["fk20_single_concurrent_callers"] = {("%d_threads_polys_per_s" % t): round(world * max_over_ranks(-concurrent(t, 2)) * -1, 2) for t in (1, 8, 32)}
     out["one_polynomial_note"] = "host-buffer call per polynomial, n = %d (b200_fk20_single / b200_da_using_fk20), wall clock, max over ranks" % N_COEFFS
     if N_COEFFS == 4096:
+        # ---- verification: all 4096 FK20Single proofs of one blob against its commitment.  Aggregated: random linear
+        # combination, three device MSMs + ONE host pairing; per proof: the reference's CheckProofSingle, pairing per proof
+        # spread over the host cores (a 64-proof sample).  Both must say "valid".
+        s2 = kzg.generate_testing_setup_g2(SECRET, 2)
+        rc = L.b200_kzg_settings_set_secret_g2(fk.ks.h, s2.ctypes.data, 2)
+        assert rc == 0, L.b200_strerror(rc)
+        commits, proofs = fk.commit_fk20_batch(poly.reshape(1, N_COEFFS, 4))
+        w = int(kzg.fr_to_ints(kzg.FFTSettings(12).expanded_roots_of_unity()[1:2])[0])
+        xs_i, acc = [], 1
+        for _ in range(N_COEFFS):
+            xs_i.append(acc)
+            acc = acc * w % kzg.R_MOD
+        xs = kzg.fr_from_ints(xs_i)
+        ys = kzg.FFTSettings(12).fft(poly)
+        cs = np.repeat(commits[0].reshape(1, 18), N_COEFFS, axis=0)
+        agg_ok = []
+        t_agg = wall(lambda: agg_ok.append(fk.ks.check_proof_single_aggregate(cs, proofs[0], xs, ys)), 2)
+        one_ok = []
+        t_one = wall(lambda: one_ok.append(bool(fk.ks.check_proof_single_batch(cs[:64], proofs[0][:64], xs[:64], ys[:64]).all())), 1)
+        out["verification"] = {"aggregate_4096_proofs_ms": round(t_agg * 1e3, 2), "aggregate_proofs_per_s": round(world * N_COEFFS / t_agg, 1),
+                               "per_proof_checks_per_s": round(64 / t_one, 1), "host_cores": os.cpu_count(), "all_valid": bool(all(agg_ok) and all(one_ok)),
+                               "note": "b200_check_proof_single_aggregate (3 bucket MSMs of 4096 terms on the device + 1 pairing on the host) vs "
+                                       "b200_check_proof_single_batch (one host pairing check per proof, all host cores); host buffers, wall clock"}
         # ---- config 4
         scale, batch = 14, 64
         n = 1 << scale

@@ -225,6 +225,24 @@ extern "C" int b200_g2_from_compressed(uint64_t* out, const uint8_t* in) {
     g2_to_abi(out, p);
     return B200_OK;
 }
+// affine coordinates (canonical, x then y; zeros for infinity) -- StrG1 / StrG2 print them (bls/bls_kilic.go:55-61,96-102)
+extern "C" void b200_g1_to_affine(const uint64_t* p, uint64_t* xy) {
+    memset(xy, 0, 96);
+    const G1J a = g1_from_abi(p);
+    if (a.is_inf()) return;
+    Fp x, y;
+    g1_affine_canon(a, x, y);
+    memcpy(xy, x.l, 48); memcpy(xy + 6, y.l, 48);
+}
+extern "C" void b200_g2_to_affine(const uint64_t* p, uint64_t* xy) {
+    memset(xy, 0, 192);
+    const G2J a = g2_from_abi(p);
+    if (a.is_inf()) return;
+    Fp2 x, y;
+    g2_affine(a, x, y);
+    const Fp c[4] = {fe_from_mont(x.c0), fe_from_mont(x.c1), fe_from_mont(y.c0), fe_from_mont(y.c1)};
+    for (int i = 0; i < 4; i++) memcpy(xy + 6 * i, c[i].l, 48);
+}
 // setup.go:9-26 GenerateTestingSetup, G2 half: out[i] = secret^i * GenG2 (host: ~n scalar multiplications)
 extern "C" int b200_generate_testing_setup_g2(const uint64_t* secret, size_t n, uint64_t* out) {
     const Fr s = fr_from_abi_mont(secret);
@@ -898,7 +916,8 @@ struct b200_ks {
     int fb_w = 8;                 // its window bits
     size_t fb_n = 0;
     std::vector<G1A*> retired;    // smaller tables superseded by d_fb_table (freed with the settings)
-    std::vector<G2J> h_secret_g2; // SecretG2 (kzg.go:16), host copy: only the verification entry points read it
+    std::vector<uint64_t> h_secret_g2;   // SecretG2 (kzg.go:16) as handed in (36 x u64 per point): only the verification entry points read it
+    size_t n_secret_g2() const { return h_secret_g2.size() / 36; }
 };
 
 // Fixed-base window tables.  Window bits: 8 by default (384 KiB per base: 1.5 GiB for the 4096 commitment bases,
@@ -1075,15 +1094,18 @@ extern "C" int b200_check_proof_multi_g1_batch(b200_ks* ks, const uint64_t* comm
 // host; call once, before the handle is shared between threads.  n may be smaller than the G1 half (e.g. only the entries the
 // verifier needs); every point must be on the twist.
 extern "C" int b200_kzg_settings_set_secret_g2(b200_ks* ks, const uint64_t* secret_g2, size_t n) {
-    std::vector<G2J> pts(n);
-    for (size_t i = 0; i < n; i++) {
-        if (!abi_coords_canonical(secret_g2 + 36 * i, 6)) return B200_ERR_BAD_INPUT;
-        pts[i] = g2_from_abi(secret_g2 + 36 * i);
-        if (!g2_on_curve(pts[i])) return B200_ERR_BAD_INPUT;
-    }
+    std::vector<uint64_t> pts(secret_g2, secret_g2 + 36 * n);
     std::lock_guard<std::mutex> lk(ks->mu);
     ks->h_secret_g2.swap(pts);
     return B200_OK;
+}
+// SecretG2[i], validated when it is read (a setup can hold millions of points of which a verifier reads one or two)
+static int ks_secret_g2(const b200_ks* ks, size_t i, G2J* out) {
+    if (i >= ks->n_secret_g2()) return B200_ERR_TOO_SMALL;
+    const uint64_t* p = ks->h_secret_g2.data() + 36 * i;
+    if (!abi_coords_canonical(p, 6)) return B200_ERR_BAD_INPUT;
+    *out = g2_from_abi(p);
+    return g2_on_curve(*out) ? B200_OK : B200_ERR_BAD_INPUT;
 }
 
 // ok[i] = e(lhs[i], [1]_2) == e(proofs[i], rhs[i]) on the host cores, one pairing check per item
@@ -1110,11 +1132,12 @@ static int pairing_checks(const uint64_t* lhs, const uint64_t* proofs, const std
 // (b200_check_proof_single_g1_batch), [s - x]_2 = SecretG2[1] - x GenG2 (:59-62) and the pairing check (:74) on the host.
 extern "C" int b200_check_proof_single_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
                                              const uint64_t* ys, size_t batch, uint8_t* ok) {
-    if (ks->h_secret_g2.size() < 2) return B200_ERR_TOO_SMALL;          // SecretG2[1]
+    G2J s2;
+    CKS(ks_secret_g2(ks, 1, &s2));                                      // SecretG2[1]
     if (batch == 0) return B200_OK;
     std::vector<uint64_t> lhs(batch * 18);
     CKS(b200_check_proof_single_g1_batch(commitments, ys, batch, lhs.data()));
-    const G2J gen = g2_generator(), s2 = ks->h_secret_g2[1];
+    const G2J gen = g2_generator();
     std::vector<G2J> rhs(batch);
     for (size_t i = 0; i < batch; i++) {
         if (!fr_canon_valid(xs + 4 * i)) return B200_ERR_BAD_INPUT;
@@ -1134,11 +1157,12 @@ extern "C" int b200_check_proof_single(b200_ks* ks, const uint64_t* commitment, 
 // (b200_check_proof_multi_g1_batch), [s^n - x^n]_2 = SecretG2[n] - x^n GenG2 (:71-76) and the pairing check (:87) on the host.
 extern "C" int b200_check_proof_multi_batch(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
                                             const uint64_t* ys, size_t n, size_t batch, uint8_t* ok) {
-    if (ks->h_secret_g2.size() <= n) return B200_ERR_TOO_SMALL;         // SecretG2[len(ys)]
+    G2J sn;
+    CKS(ks_secret_g2(ks, n, &sn));                                      // SecretG2[len(ys)]
     if (batch == 0) return B200_OK;
     std::vector<uint64_t> lhs(batch * 18), xn(batch * 4);
     CKS(b200_check_proof_multi_g1_batch(ks, commitments, xs, ys, n, batch, lhs.data(), xn.data()));
-    const G2J gen = g2_generator(), sn = ks->h_secret_g2[n];
+    const G2J gen = g2_generator();
     std::vector<G2J> rhs(batch);
     for (size_t i = 0; i < batch; i++) rhs[i] = g2_sub(sn, g2_mul(gen, fr_load_canon(xn.data() + 4 * i)));
     return pairing_checks(lhs.data(), proofs, rhs, batch, ok);
@@ -1180,20 +1204,22 @@ static int aggregate_check(const uint64_t* a_pts, const uint64_t* proofs, const 
 extern "C" int b200_check_proof_single_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
                                                  const uint64_t* ys, const uint64_t* rs, size_t batch, int* ok) {
     *ok = 0;
-    if (ks->h_secret_g2.size() < 2) return B200_ERR_TOO_SMALL;
+    G2J s2;
+    CKS(ks_secret_g2(ks, 1, &s2));
     if (batch == 0) { *ok = 1; return B200_OK; }
     std::vector<uint64_t> a(batch * 18);
     CKS(b200_check_proof_single_g1_batch(commitments, ys, batch, a.data()));
-    return aggregate_check(a.data(), proofs, xs, rs, batch, ks->h_secret_g2[1], ok);
+    return aggregate_check(a.data(), proofs, xs, rs, batch, s2, ok);
 }
 extern "C" int b200_check_proof_multi_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
                                                 const uint64_t* ys, size_t n, const uint64_t* rs, size_t batch, int* ok) {
     *ok = 0;
-    if (ks->h_secret_g2.size() <= n) return B200_ERR_TOO_SMALL;
+    G2J sn;
+    CKS(ks_secret_g2(ks, n, &sn));
     if (batch == 0) { *ok = 1; return B200_OK; }
     std::vector<uint64_t> a(batch * 18), xn(batch * 4);
     CKS(b200_check_proof_multi_g1_batch(ks, commitments, xs, ys, n, batch, a.data(), xn.data()));
-    return aggregate_check(a.data(), proofs, xn.data(), rs, batch, ks->h_secret_g2[n], ok);
+    return aggregate_check(a.data(), proofs, xn.data(), rs, batch, sn, ok);
 }
 
 // ------------------------------------------------------------------------------ FK20

@@ -93,6 +93,10 @@ def lib():
     for name in ("b200_g2_add", "b200_g2_sub", "b200_g2_mul", "b200_g2_to_compressed"):
         getattr(L, name).argtypes = [vp, vp, vp] if name != "b200_g2_to_compressed" else [vp, vp]
         getattr(L, name).restype = None
+    L.b200_g1_to_affine.argtypes = [vp, vp]
+    L.b200_g1_to_affine.restype = None
+    L.b200_g2_to_affine.argtypes = [vp, vp]
+    L.b200_g2_to_affine.restype = None
     L.b200_g2_generator.argtypes = [vp]
     L.b200_g2_generator.restype = None
     L.b200_g2_neg.argtypes = [vp]

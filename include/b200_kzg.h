@@ -91,6 +91,10 @@ int b200_g2_equal(const uint64_t a[36], const uint64_t b[36]);                  
 void b200_g2_to_compressed(uint8_t out[96], const uint64_t p[36]);                  /* bls/bls_kilic.go:123 ToCompressedG2 */
 /* bls/bls_kilic.go:127 FromCompressedG2: flags, coordinates < p, curve equation, prime-order subgroup; else B200_ERR_BAD_INPUT */
 int b200_g2_from_compressed(uint64_t out[36], const uint8_t in[96]);
+/* Affine coordinates, canonical limbs (G1: x, y; G2: x.c0, x.c1, y.c0, y.c1; all zero for infinity): what StrG1 / StrG2 print
+ * (bls/bls_kilic.go:55-61, 96-102). */
+void b200_g1_to_affine(const uint64_t p[18], uint64_t xy[12]);
+void b200_g2_to_affine(const uint64_t p[36], uint64_t xy[24]);
 /* setup.go:9-26 GenerateTestingSetup, G2 half: out[i] = secret^i * GenG2 (host, one scalar multiplication per entry) */
 int b200_generate_testing_setup_g2(const uint64_t secret[4], size_t n, uint64_t* out);
 /* bls/bls_kilic.go:152-158 PairingsVerify: *ok = (e(a1, a2) == e(b1, b2)).  Non-canonical coordinates or points off their
@@ -180,7 +184,8 @@ int b200_check_proof_multi_g1_batch(b200_ks* ks, const uint64_t* commitments, co
                                     size_t batch, uint64_t* out_g1, uint64_t* x_pow_n);
 
 /* KZGSettings.SecretG2 (kzg.go:14-16): host copy of the n first points, read only by the two checks below (SecretG2[1],
- * SecretG2[len(ys)]).  Call once, before the handle is shared between threads.  Points off the twist -> B200_ERR_BAD_INPUT. */
+ * SecretG2[len(ys)]).  Call once, before the handle is shared between threads.  A point is validated when a check reads it
+ * (non-canonical coordinates or off the twist -> B200_ERR_BAD_INPUT from that check). */
 int b200_kzg_settings_set_secret_g2(b200_ks* ks, const uint64_t* secret_g2, size_t n);
 /* kzg_single_proofs.go:57-75 CheckProofSingle, complete: G1 side on the device, [s - x]_2 and the pairing check on the host.
  * *ok / ok[i] = 1 if the proof verifies.  SecretG2 not set (fewer than 2 points) -> B200_ERR_TOO_SMALL. */

@@ -3,8 +3,8 @@
 
 // Package bls, group half of the `bignum_b200` backend.  G1 lives in libb200kzg.so (Jacobian,
 // canonical limbs, Z == 0 <=> infinity, so the Go zero value is the point at infinity as
-// bls/bls_kilic.go:136 and kzg_multi_proofs.go:20 rely on).  G2 and the pairing are
-// verification-only and stay on kilic inside this tag (SURVEY.md section 8b).
+// bls/bls_kilic.go:136 and kzg_multi_proofs.go:20 rely on).  G2 and the pairing are the library's
+// host code (go_kzg_b200/csrc/pairing.h): this tag does not import kilic at all.
 // Drop-in sibling of bls/bls_kilic.go.  NOT COMPILED in this repository's build image.
 package bls
 
@@ -19,8 +19,6 @@ import (
 	"math/big"
 	"strings"
 	"unsafe"
-
-	kbls "github.com/kilic/bls12-381"
 )
 
 var ZERO_G1 G1Point
@@ -33,9 +31,9 @@ var ZeroG2 G2Point
 
 func initG1G2() {
 	C.b200_g1_generator(g1p(&GenG1))
-	GenG2 = G2Point(*kbls.NewG2().One())
+	C.b200_g2_generator(g2p(&GenG2))
 	ZeroG1 = G1Point{}
-	ZeroG2 = G2Point(*kbls.NewG2().Zero())
+	ZeroG2 = G2Point{}
 }
 
 // G1Point: Jacobian X, Y, Z, each six little-endian 64-bit limbs of a canonical residue mod p.
@@ -98,13 +96,21 @@ func FromCompressedG1Batch(v []byte) ([]G1Point, error) {
 	return out, nil
 }
 
+// limbsToBig: six little-endian 64-bit limbs -> integer
+func limbsToBig(l []uint64) *big.Int {
+	var be [48]byte
+	for i, w := range l {
+		for j := 0; j < 8; j++ {
+			be[47-8*i-j] = byte(w >> (8 * uint(j)))
+		}
+	}
+	return new(big.Int).SetBytes(be[:])
+}
+
 func StrG1(v *G1Point) string {
-	k := toKilicG1(v)
-	data := kbls.NewG1().ToUncompressed(k)
-	var a, b big.Int
-	a.SetBytes(data[:48])
-	b.SetBytes(data[48:])
-	return a.String() + "\n" + b.String()
+	var xy [12]uint64
+	C.b200_g1_to_affine(g1p(v), (*C.uint64_t)(unsafe.Pointer(&xy[0])))
+	return limbsToBig(xy[:6]).String() + "\n" + limbsToBig(xy[6:]).String()
 }
 
 // LinCombG1: device MSM (Pippenger bucket method).  Panics on a length mismatch, empty input gives
@@ -121,71 +127,60 @@ func LinCombG1(numbers []G1Point, factors []Fr) *G1Point {
 	return &out
 }
 
-// ---- G2 and the pairing: kilic, unchanged from bls/bls_kilic.go:67-157 ------------------------
+// ---- G2 and the pairing: host code of the library (bls/bls_kilic.go:67-157) -------------------
 
-type G2Point kbls.PointG2
+// G2Point: Jacobian X, Y, Z over Fp2, each coordinate (c0, c1) of six little-endian 64-bit limbs; the zero value is infinity.
+type G2Point struct{ X, Y, Z [2][6]uint64 }
 
-func ClearG2(x *G2Point) { (*kbls.PointG2)(x).Zero() }
+func g2p(p *G2Point) *C.uint64_t { return (*C.uint64_t)(unsafe.Pointer(p)) }
+
+func ClearG2(x *G2Point) { *x = G2Point{} }
 
 func CopyG2(dst *G2Point, v *G2Point) { *dst = *v }
 
-func kilicFr(b *Fr) *kbls.Fr {
-	be := FrTo32(b)
-	for i := 0; i < 16; i++ {
-		be[i], be[31-i] = be[31-i], be[i]
-	}
-	return new(kbls.Fr).FromBytes(be[:])
-}
+func MulG2(dst *G2Point, a *G2Point, b *Fr) { C.b200_g2_mul(g2p(dst), g2p(a), frp(b)) }
 
-func MulG2(dst *G2Point, a *G2Point, b *Fr) {
-	kbls.NewG2().MulScalar((*kbls.PointG2)(dst), (*kbls.PointG2)(a), kilicFr(b))
-}
+func AddG2(dst *G2Point, a *G2Point, b *G2Point) { C.b200_g2_add(g2p(dst), g2p(a), g2p(b)) }
 
-func AddG2(dst *G2Point, a *G2Point, b *G2Point) {
-	kbls.NewG2().Add((*kbls.PointG2)(dst), (*kbls.PointG2)(a), (*kbls.PointG2)(b))
-}
+func SubG2(dst *G2Point, a *G2Point, b *G2Point) { C.b200_g2_sub(g2p(dst), g2p(a), g2p(b)) }
 
-func SubG2(dst *G2Point, a *G2Point, b *G2Point) {
-	kbls.NewG2().Sub((*kbls.PointG2)(dst), (*kbls.PointG2)(a), (*kbls.PointG2)(b))
-}
-
-func NegG2(dst *G2Point) { kbls.NewG2().Neg((*kbls.PointG2)(dst), (*kbls.PointG2)(dst)) }
+func NegG2(dst *G2Point) { C.b200_g2_neg(g2p(dst)) }
 
 func StrG2(v *G2Point) string {
-	data := kbls.NewG2().ToUncompressed((*kbls.PointG2)(v))
-	var a, b big.Int
-	a.SetBytes(data[:96])
-	b.SetBytes(data[96:])
-	return a.String() + "\n" + b.String()
+	// kilic's ToUncompressed lays a G2 point out as x.c1 || x.c0 || y.c1 || y.c0; StrG2 prints the two 96-byte halves
+	var xy [24]uint64
+	C.b200_g2_to_affine(g2p(v), (*C.uint64_t)(unsafe.Pointer(&xy[0])))
+	join := func(c1, c0 []uint64) *big.Int {
+		hi := limbsToBig(c1)
+		return hi.Lsh(hi, 384).Or(hi, limbsToBig(c0))
+	}
+	return join(xy[6:12], xy[0:6]).String() + "\n" + join(xy[18:24], xy[12:18]).String()
 }
 
-func EqualG2(a *G2Point, b *G2Point) bool {
-	return kbls.NewG2().Equal((*kbls.PointG2)(a), (*kbls.PointG2)(b))
-}
+func EqualG2(a *G2Point, b *G2Point) bool { return C.b200_g2_equal(g2p(a), g2p(b)) == 1 }
 
-func ToCompressedG2(p *G2Point) []byte { return kbls.NewG2().ToCompressed((*kbls.PointG2)(p)) }
+func ToCompressedG2(p *G2Point) []byte {
+	out := make([]byte, 96)
+	C.b200_g2_to_compressed((*C.uint8_t)(unsafe.Pointer(&out[0])), g2p(p))
+	return out
+}
 
 func FromCompressedG2(v []byte) (*G2Point, error) {
-	p, err := kbls.NewG2().FromCompressed(v)
-	return (*G2Point)(p), err
-}
-
-// toKilicG1 crosses into kilic's representation through the compressed encoding (verification and
-// printing only, off the hot path).
-func toKilicG1(p *G1Point) *kbls.PointG1 {
-	k, err := kbls.NewG1().FromCompressed(ToCompressedG1(p))
-	if err != nil {
-		panic(err)
+	if len(v) != 96 {
+		return nil, errors.New("input string should be equal or larger than 96")
 	}
-	return k
+	var p G2Point
+	if C.b200_g2_from_compressed(g2p(&p), (*C.uint8_t)(unsafe.Pointer(&v[0]))) != C.B200_OK {
+		return nil, errors.New("invalid compressed G2 point") // flags, coordinate >= p, off the curve or outside the subgroup
+	}
+	return &p, nil
 }
 
 // e(a1^(-1), a2) * e(b1,  b2) = 1_T
 func PairingsVerify(a1 *G1Point, a2 *G2Point, b1 *G1Point, b2 *G2Point) bool {
-	pairingEngine := kbls.NewEngine()
-	pairingEngine.AddPairInv(toKilicG1(a1), (*kbls.PointG2)(a2))
-	pairingEngine.AddPair(toKilicG1(b1), (*kbls.PointG2)(b2))
-	return pairingEngine.Check()
+	var ok C.int
+	must(C.b200_pairings_verify(g1p(a1), g2p(a2), g1p(b1), g2p(b2), &ok))
+	return ok == 1
 }
 
 func DebugG1s(msg string, values []G1Point) {

@@ -13,6 +13,7 @@ import "C"
 import (
 	"fmt"
 	"runtime"
+	"unsafe"
 
 	"github.com/protolambda/go-kzg/bls"
 )
@@ -38,6 +39,9 @@ func NewKZGSettings(fs *FFTSettings, secretG1 []bls.G1Point, secretG2 []bls.G2Po
 	}
 	ks := &KZGSettings{FFTSettings: fs, SecretG1: secretG1, SecretG2: secretG2}
 	mustB200(C.b200_kzg_settings_new(fs.handle, g1s(secretG1), C.size_t(len(secretG1)), C.size_t(len(secretG2)), &ks.handle))
+	if len(secretG2) > 0 { // the verification entry points read SecretG2[1] and SecretG2[len(ys)] from the handle
+		mustB200(C.b200_kzg_settings_set_secret_g2(ks.handle, (*C.uint64_t)(unsafe.Pointer(&secretG2[0])), C.size_t(len(secretG2))))
+	}
 	runtime.SetFinalizer(ks, func(s *KZGSettings) { C.b200_kzg_settings_free(s.handle) })
 	return ks
 }

@@ -177,3 +177,27 @@ def test_kzg_equation_with_the_known_secret():
     assert kzg.pairings_verify(lhs, g2, proof, s_minus_x)
     wrong = g1_abi(pr.g1_mul(pr.G1, (ps - y + 1) % R))
     assert not kzg.pairings_verify(wrong, g2, proof, s_minus_x)
+
+
+def test_affine_coordinates_for_str():
+    """StrG1 / StrG2 (bls/bls_kilic.go:55-61,96-102) print the affine coordinates: b200_g1_to_affine / b200_g2_to_affine"""
+    L = kzg.lib()
+    k = 0xFEDCBA9876543210
+    p, q = pr.g1_mul(pr.G1, k), pr.g2_mul(pr.G2, k)
+    # hand the library projectively scaled points: (X, Y, Z) = (x z^2, y z^3, z)
+    z = 0x123456789
+    pj = np.zeros(18, dtype=np.uint64)
+    for c, v in enumerate((p[0] * z * z % P, p[1] * z ** 3 % P, z)):
+        for j in range(6):
+            pj[6 * c + j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    xy = np.zeros(12, dtype=np.uint64)
+    L.b200_g1_to_affine(pj.ctypes.data, xy.ctypes.data)
+    got = [sum(int(v) << (64 * j) for j, v in enumerate(xy[6 * c:6 * c + 6])) for c in range(2)]
+    assert got == [p[0], p[1]]
+    q2 = kzg.g2_add(kzg.g2_mul(kzg.g2_generator(), k - 1), kzg.g2_generator())     # Z != 1
+    xy2 = np.zeros(24, dtype=np.uint64)
+    L.b200_g2_to_affine(np.ascontiguousarray(q2).ctypes.data, xy2.ctypes.data)
+    got2 = [sum(int(v) << (64 * j) for j, v in enumerate(xy2[6 * c:6 * c + 6])) for c in range(4)]
+    assert got2 == [q[0][0], q[0][1], q[1][0], q[1][1]]
+    L.b200_g2_to_affine(np.zeros(36, dtype=np.uint64).ctypes.data, xy2.ctypes.data)
+    assert not xy2.any()
