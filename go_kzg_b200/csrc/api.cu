@@ -1111,7 +1111,7 @@ static int ks_secret_g2(const b200_ks* ks, size_t i, G2J* out) {
 // ok[i] = e(lhs[i], [1]_2) == e(proofs[i], rhs[i]) on the host cores, one pairing check per item
 static int pairing_checks(const uint64_t* lhs, const uint64_t* proofs, const std::vector<G2J>& rhs, size_t batch, uint8_t* ok) {
     for (size_t i = 0; i < batch; i++)
-        if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
+        if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi_h(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
     const G2J gen = g2_generator();
     unsigned nt = std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
@@ -1191,7 +1191,7 @@ static int aggregate_check(const uint64_t* a_pts, const uint64_t* proofs, const 
         const Fr r = fr_load_canon(rs + 4 * i);
         if (r.is_zero()) return B200_ERR_BAD_INPUT;
         fr_store_canon(rc.data() + 4 * i, fe_mul(fe_to_mont(r), fr_load_canon(cs + 4 * i)));
-        if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
+        if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi_h(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
     }
     uint64_t sa[18], sb[18], sp[18];
     CKS(b200_g1_lincomb(a_pts, rs, batch, sa));

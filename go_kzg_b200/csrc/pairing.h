@@ -177,6 +177,14 @@ inline bool f2_sqrt(Fp2& out, const Fp2& a) {
     out = r; return true;
 }
 
+// ABI point -> Montgomery Jacobian with the 64-bit product (g1_from_abi's fe_to_mont is the 32-bit emulation)
+inline G1J g1_from_abi_h(const uint64_t* p) {
+    G1J r;
+    memcpy(r.x.l, p, 48); memcpy(r.y.l, p + 6, 48); memcpy(r.z.l, p + 12, 48);
+    const Fp r2 = Fp::r2();
+    r.x = hmul(r.x, r2); r.y = hmul(r.y, r2); r.z = hmul(r.z, r2);
+    return r;
+}
 inline bool g1_on_curve(const G1J& p) {      // Y^2 = X^3 + 4 Z^6
     if (p.is_inf()) return true;
     Fp z2 = hsqr(p.z), z6 = hmul(hsqr(z2), z2);
