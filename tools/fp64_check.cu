@@ -20,6 +20,12 @@ int main() {
         Fp a = rnd_fp(it < 36 ? it % 6 : 0), b = rnd_fp(it < 36 ? it / 6 : 0);
         Fp w = fe_mul(a, b), g = fe_mul_fp64(a, b);
         if (w != g) { bad++; if (bad < 5) printf("mul mismatch it=%d\n", it); }
+        Fp h3m = fe_mul_hyb3(a, b), h3s = fe_sqr_hyb3(a);
+        if (w != h3m) { bad++; if (bad < 5) printf("hybrid3 mul mismatch it=%d\n", it); }
+        if (fe_sqr(a) != h3s) { bad++; if (bad < 5) printf("hybrid3 sqr mismatch it=%d\n", it); }
+        Fp h2m = fe_mul_hyb2(a, b), h2s = fe_sqr_hyb2(a);
+        if (w != h2m) { bad++; if (bad < 5) printf("hybrid2 mul mismatch it=%d\n", it); }
+        if (fe_sqr(a) != h2s) { bad++; if (bad < 5) printf("hybrid2 sqr mismatch it=%d\n", it); }
         Fp hm = fe_mul_hyb(a, b), hs = fe_sqr_hyb(a);
         if (w != hm) { bad++; if (bad < 5) printf("hybrid mul mismatch it=%d\n", it); }
         if (fe_sqr(a) != hs) { bad++; if (bad < 5) printf("hybrid sqr mismatch it=%d\n", it); }

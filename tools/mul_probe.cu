@@ -12,6 +12,10 @@ static __device__ __noinline__ Fp sqr_int(const Fp* a) { Fp x = *a; return fe_sq
 static __device__ __noinline__ Fp sqr_fp(const Fp* a) { Fp x = *a; return fe_sqr_fp64(x); }
 static __device__ __noinline__ Fp mul_hy(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul_hyb(x, y); }
 static __device__ __noinline__ Fp sqr_hy(const Fp* a) { Fp x = *a; return fe_sqr_hyb(x); }
+static __device__ __noinline__ Fp mul_h3(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul_hyb3(x, y); }
+static __device__ __noinline__ Fp sqr_h3(const Fp* a) { Fp x = *a; return fe_sqr_hyb3(x); }
+static __device__ __noinline__ Fp mul_h2(const Fp* a, const Fp* b) { Fp x = *a, y = *b; return fe_mul_hyb2(x, y); }
+static __device__ __noinline__ Fp sqr_h2(const Fp* a) { Fp x = *a; return fe_sqr_hyb2(x); }
 
 __device__ __forceinline__ unsigned hw_warp_slot() { unsigned w; asm volatile("mov.u32 %0, %%warpid;" : "=r"(w)); return w; }
 
@@ -22,7 +26,13 @@ __global__ void __launch_bounds__(128, 4) k_probe(uint32_t* buf, int iters, int 
     for (int k = 0; k < 12; k++) { x.l[k] = buf[k] + (uint32_t)i; y.l[k] = buf[12 + k] ^ (uint32_t)i; }
     x.l[11] &= 0x0fffffffu; y.l[11] &= 0x0fffffffu;
     bool fp = ((hw_warp_slot() >> 2) % den) < num;
-    if (den < 0) {      // hybrid product (FP64 product half, integer reduction half), every warp; den == -2: every other warp slot
+    if (den == -4) {    // interleaved hybrid, instruction order pinned by data dependences
+        if (sqr) for (int k = 0; k < iters; k++) { x = sqr_h3(&x); y = sqr_h3(&y); }
+        else for (int k = 0; k < iters; k++) { x = mul_h3(&x, &y); y = mul_h3(&y, &x); }
+    } else if (den == -3) {    // interleaved hybrid (rows of the reduction issued between the product columns)
+        if (sqr) for (int k = 0; k < iters; k++) { x = sqr_h2(&x); y = sqr_h2(&y); }
+        else for (int k = 0; k < iters; k++) { x = mul_h2(&x, &y); y = mul_h2(&y, &x); }
+    } else if (den < 0) {      // hybrid product (FP64 product half, integer reduction half), every warp; den == -2: every other warp slot
         bool hy = den == -1 || (hw_warp_slot() & 1);
         if (sqr) { if (hy) for (int k = 0; k < iters; k++) { x = sqr_hy(&x); y = sqr_hy(&y); } else for (int k = 0; k < iters; k++) { x = sqr_int(&x); y = sqr_int(&y); } }
         else { if (hy) for (int k = 0; k < iters; k++) { x = mul_hy(&x, &y); y = mul_hy(&y, &x); } else for (int k = 0; k < iters; k++) { x = mul_int(&x, &y); y = mul_int(&y, &x); } }
@@ -47,7 +57,7 @@ int main() {
     unsigned long long *c0, *c1; cudaMalloc(&c0, threads * 8); cudaMalloc(&c1, threads * 8);
     const int iters = 1000;
     struct { const char* name; int num, den; } modes[] = {{"integer pipe only", 0, 1}, {"FP64 pipe only", 1, 1}, {"2 of 4 warp slots on FP64", 1, 2},
-                                                          {"hybrid (FP64 product + int reduction)", 1, -1}, {"hybrid on odd warp slots", 1, -2}};
+                                                          {"hybrid (FP64 product + int reduction)", 1, -1}, {"hybrid on odd warp slots", 1, -2}, {"hybrid, interleaved rows", 1, -3}, {"hybrid, interleaved + pinned order", 1, -4}};
     unsigned long long* href = (unsigned long long*)malloc(threads * 8);
     unsigned long long* hgot = (unsigned long long*)malloc(threads * 8);
     for (int sqr = 0; sqr < 2; sqr++) {
