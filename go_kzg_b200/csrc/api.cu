@@ -93,9 +93,23 @@ static void keep_pool_memory() {
 // Host-buffer entry points run on a pooled non-blocking stream leased for the duration of the call (one pool per
 // device): callers on different threads (goroutines migrate across OS threads) overlap instead of serialising on
 // the legacy default stream.  Streams are never destroyed; a lease taken after cudaSetDevice belongs to that device.
+// Calls in flight (host-buffer entry points).  A call that finds the device to itself may spend lanes on latency (a quad of
+// lanes per butterfly in small G1 transforms, kernels_g1.cu); with several callers in flight the SMs are busy anyway and the
+// one-lane-per-butterfly kernels give more throughput.  Decided once per call, on the calling thread.
+static std::atomic<int> g_active_calls{0};
+static std::atomic<int> g_latency_mode{1};      // b200_set_latency_mode: 1 = automatic (default), 0 = never
+static const int kQuadMaxCallers = 2;
+extern "C" int b200_set_latency_mode(int mode) {
+    if (mode != 0 && mode != 1) return B200_ERR_BAD_INPUT;
+    g_latency_mode = mode;
+    return B200_OK;
+}
+
 struct StreamLease {
     cudaStream_t st = nullptr;
     int dev = -1;
+    bool counted = false;
+    void count() { counted = true; g1_set_quad_allowed(++g_active_calls <= kQuadMaxCallers && g_latency_mode.load() == 1); }
     static std::mutex& mu() { static std::mutex m; return m; }
     static std::vector<cudaStream_t>& pool(int d) { static std::vector<cudaStream_t> p[64]; return p[d]; }
     int acquire() {
@@ -104,12 +118,14 @@ struct StreamLease {
         {
             std::lock_guard<std::mutex> lk(mu());
             auto& p = pool(dev);
-            if (!p.empty()) { st = p.back(); p.pop_back(); return B200_OK; }
+            if (!p.empty()) { st = p.back(); p.pop_back(); count(); return B200_OK; }
         }
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        count();
         return B200_OK;
     }
     ~StreamLease() {
+        if (counted) --g_active_calls;
         if (!st) return;
         std::lock_guard<std::mutex> lk(mu());
         pool(dev).push_back(st);

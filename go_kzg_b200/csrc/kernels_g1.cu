@@ -314,14 +314,19 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage_quad(G1J* da
     }
     if (valid && (threadIdx.x & 3u) == 0) { st_vec(p0, s); st_vec(p1, x1); }
 }
-// Butterflies per launch up to which a quad per butterfly is used.  OFF by default (0): measured on one polynomial
-// (n = 4096, 2048 butterflies per stage) the quad stage is 2 % faster per call (fft_g1 20.3 -> 20.0 ms) but occupies 4 x the
-// warps, and the aggregate rate of concurrent one-polynomial callers drops by a third (32 callers: 136 -> 91 polynomials/s).
-// Build with -DB200_QUAD_STAGE_MAX=4096 to get it back.
+// Butterflies per launch up to which a quad of lanes per butterfly is used (quad.cuh): a point doubling in 3 dependent
+// products instead of 7, an addition in 5 instead of 11-16.  One polynomial at n = 4096 (2048 / 4096 butterflies per stage):
+// FFTG1 18.8 -> 11.6 ms, FK20Single 37.4 -> 24.5 ms, DAUsingFK20 41.9 -> 26.3 ms (profiles/r02_quad_stage.txt).  It spends
+// 4 x the warps and ~1.7 x the multiplier cycles per butterfly, so it only pays while the launch leaves the machine mostly
+// idle: above ~2 quad warps per SM sub-partition the multiplier pipe is the limit again (hence 8192), and with several
+// callers in flight the one-lane kernels give more aggregate throughput (8 concurrent callers: 103 against 80
+// polynomials/s), which is what g1_set_quad_allowed carries in from the API layer, once per call.
 #ifndef B200_QUAD_STAGE_MAX
-#define B200_QUAD_STAGE_MAX 0
+#define B200_QUAD_STAGE_MAX 8192
 #endif
-bool g1_stage_uses_quads(size_t n_half, size_t batch) { return batch < 16 && n_half * batch <= B200_QUAD_STAGE_MAX; }
+static thread_local bool t_quad_allowed = true;
+void g1_set_quad_allowed(bool allowed) { t_quad_allowed = allowed; }
+bool g1_stage_uses_quads(size_t n_half, size_t batch) { return t_quad_allowed && batch < 16 && n_half * batch <= B200_QUAD_STAGE_MAX; }
 
 static void stage_smem_opt_in() {
 #ifdef B200_STAGE_SMEM_TABLE

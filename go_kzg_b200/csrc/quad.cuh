@@ -24,10 +24,31 @@ namespace b200 {
 #define QUAD_FULL 0xffffffffu
 __device__ __forceinline__ unsigned quad_role() { return threadIdx.x & 3u; }
 
-__device__ __forceinline__ Fp quad_pick(unsigned role, const Fp& v0, const Fp& v1, const Fp& v2, const Fp& v3) {
+// Operand selection by lane role WITHOUT branches: ternaries over 12-word structs that live in local memory compile to
+// divergent branches (BSSY / BRA / BSYNC around the loads; the first form of this file had 98 such regions in one point
+// addition, each serialising the four lanes of every quad).  Masks and LOP3 instead.
+__device__ __forceinline__ Fp quad_pick2(unsigned sel, const Fp& v0, const Fp& v1) {            // sel ? v1 : v0
+    const uint32_t m = 0u - (sel & 1u);
     Fp r;
 #pragma unroll
-    for (int i = 0; i < 12; i++) r.l[i] = role == 0 ? v0.l[i] : (role == 1 ? v1.l[i] : (role == 2 ? v2.l[i] : v3.l[i]));
+    for (int i = 0; i < 12; i++) r.l[i] = (v0.l[i] & ~m) | (v1.l[i] & m);
+    return r;
+}
+__device__ __forceinline__ Fp quad_pick3(unsigned role, const Fp& v0, const Fp& v1, const Fp& v2) {   // role 3 -> v2 as well
+    const uint32_t m1 = 0u - (uint32_t)(role == 1), m2 = 0u - (uint32_t)(role >= 2);
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = (v0.l[i] & ~(m1 | m2)) | (v1.l[i] & m1) | (v2.l[i] & m2);
+    return r;
+}
+__device__ __forceinline__ Fp quad_pick(unsigned role, const Fp& v0, const Fp& v1, const Fp& v2, const Fp& v3) {
+    const uint32_t lo = 0u - (role & 1u), hi = 0u - ((role >> 1) & 1u);
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint32_t a = (v0.l[i] & ~lo) | (v1.l[i] & lo), b = (v2.l[i] & ~lo) | (v3.l[i] & lo);
+        r.l[i] = (a & ~hi) | (b & hi);
+    }
     return r;
 }
 __device__ __forceinline__ Fp quad_bcast(const Fp& v, int src) {
@@ -36,46 +57,56 @@ __device__ __forceinline__ Fp quad_bcast(const Fp& v, int src) {
     for (int i = 0; i < 12; i++) r.l[i] = __shfl_sync(QUAD_FULL, v.l[i], src, 4);
     return r;
 }
-__device__ __forceinline__ G1J g1_select(bool c, const G1J& a, const G1J& b) {   // c ? a : b, word by word
+__device__ __forceinline__ G1J g1_select(bool c, const G1J& a, const G1J& b) {   // c ? a : b, word by word, no branch
+    const uint32_t m = 0u - (uint32_t)c;
     G1J r;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        r.x.l[i] = c ? a.x.l[i] : b.x.l[i];
-        r.y.l[i] = c ? a.y.l[i] : b.y.l[i];
-        r.z.l[i] = c ? a.z.l[i] : b.z.l[i];
+        r.x.l[i] = (a.x.l[i] & m) | (b.x.l[i] & ~m);
+        r.y.l[i] = (a.y.l[i] & m) | (b.y.l[i] & ~m);
+        r.z.l[i] = (a.z.l[i] & m) | (b.z.l[i] & ~m);
     }
     return r;
 }
-// one level: r_j = a_j * b_j for j < 4, lane j of the quad computing product j (unused slots: pass any operands)
-__device__ __forceinline__ void quad_mul(const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2, const Fp& a3,
-                                         const Fp& b3, Fp& r0, Fp& r1, Fp& r2, Fp& r3) {
+// one level of K distinct products: lane j of the quad computes product min(j, K - 1) (K = 2: lanes 0, 2 the first and 1, 3
+// the second), only the K results are gathered (12 shuffles each).  A level whose lanes would all compute the SAME
+// product is a plain fp_mul in every lane: no selection, no shuffles.
+__device__ __forceinline__ void quad_mul4(const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2, const Fp& a3,
+                                          const Fp& b3, Fp& r0, Fp& r1, Fp& r2, Fp& r3) {
     const unsigned role = quad_role();
-    const Fp a = quad_pick(role, a0, a1, a2, a3), b = quad_pick(role, b0, b1, b2, b3);
-    const Fp p = fp_mul(a, b);
+    const Fp p = fp_mul(quad_pick(role, a0, a1, a2, a3), quad_pick(role, b0, b1, b2, b3));
     r0 = quad_bcast(p, 0); r1 = quad_bcast(p, 1); r2 = quad_bcast(p, 2); r3 = quad_bcast(p, 3);
 }
-// one level of squares
-__device__ __forceinline__ void quad_sqr(const Fp& a0, const Fp& a1, const Fp& a2, const Fp& a3, Fp& r0, Fp& r1, Fp& r2, Fp& r3) {
-    const Fp p = fp_sqr(quad_pick(quad_role(), a0, a1, a2, a3));
-    r0 = quad_bcast(p, 0); r1 = quad_bcast(p, 1); r2 = quad_bcast(p, 2); r3 = quad_bcast(p, 3);
+__device__ __forceinline__ void quad_mul3(const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2, Fp& r0, Fp& r1,
+                                          Fp& r2) {
+    const unsigned role = quad_role();
+    const Fp p = fp_mul(quad_pick3(role, a0, a1, a2), quad_pick3(role, b0, b1, b2));
+    r0 = quad_bcast(p, 0); r1 = quad_bcast(p, 1); r2 = quad_bcast(p, 2);
+}
+__device__ __forceinline__ void quad_mul2(const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, Fp& r0, Fp& r1) {
+    const unsigned role = quad_role();
+    const Fp p = fp_mul(quad_pick2(role, a0, a1), quad_pick2(role, b0, b1));
+    r0 = quad_bcast(p, 0); r1 = quad_bcast(p, 1);
+}
+__device__ __forceinline__ void quad_sqr3(const Fp& a0, const Fp& a1, const Fp& a2, Fp& r0, Fp& r1, Fp& r2) {
+    const Fp p = fp_sqr(quad_pick3(quad_role(), a0, a1, a2));
+    r0 = quad_bcast(p, 0); r1 = quad_bcast(p, 1); r2 = quad_bcast(p, 2);
 }
 
 // *p = 2 * *p where active, in 3 levels (formulas of g1_dbl: 2M + 5S; they map infinity to infinity by themselves)
 static __device__ __noinline__ void quad_dbl(G1J* p_io, bool active) {
     const G1J p = *p_io;
-    Fp a, b, yz, u0, c, t, f;
-    quad_mul(p.x, p.x, p.y, p.y, p.y, p.z, p.x, p.x, a, b, yz, u0);
+    Fp a, b, yz, c, t, f;
+    quad_mul3(p.x, p.x, p.y, p.y, p.y, p.z, a, b, yz);
     const Fp e = fe_add(fe_dbl(a), a);
-    quad_sqr(b, fe_add(p.x, b), e, e, c, t, f, u0);
+    quad_sqr3(b, fe_add(p.x, b), e, c, t, f);
     const Fp d = fe_dbl(fe_sub(fe_sub(t, a), c));
     G1J o;
     o.z = fe_dbl(yz);
     o.x = fe_sub(f, fe_dbl(d));
-    const Fp w = fe_sub(d, o.x);
-    Fp ew, u1, u2;
-    quad_mul(e, w, e, w, e, w, e, w, ew, u0, u1, u2);
+    const Fp ew = fp_mul(e, fe_sub(d, o.x));                  // the same product in every lane
     o.y = fe_sub(ew, fe_dbl(fe_dbl(fe_dbl(c))));
-    if (active) *p_io = o;
+    *p_io = g1_select(active, o, p);
 }
 
 // *p = *p + *q where active; both Jacobian; 5 levels.  Cases of g1_add by selection: an infinite operand returns the
@@ -84,16 +115,16 @@ static __device__ __noinline__ void quad_dbl(G1J* p_io, bool active) {
 static __device__ __noinline__ void quad_add(G1J* p_io, const G1J* q_in, bool active) {
     const G1J p = *p_io, q = *q_in;
     Fp z1z1, z2z2, a, b, u1, u2, s1, s2;
-    quad_mul(p.z, p.z, q.z, q.z, p.y, q.z, q.y, p.z, z1z1, z2z2, a, b);
-    quad_mul(p.x, z2z2, q.x, z1z1, a, z2z2, b, z1z1, u1, u2, s1, s2);
+    quad_mul4(p.z, p.z, q.z, q.z, p.y, q.z, q.y, p.z, z1z1, z2z2, a, b);
+    quad_mul4(p.x, z2z2, q.x, z1z1, a, z2z2, b, z1z1, u1, u2, s1, s2);
     const Fp h = fe_sub(u2, u1), rr = fe_sub(s2, s1);
     Fp hh, zz, r2, t0, hhh, v, z3, t1;
-    quad_mul(h, h, p.z, q.z, rr, rr, h, h, hh, zz, r2, t0);
-    quad_mul(h, hh, u1, hh, zz, h, h, hh, hhh, v, z3, t0);
+    quad_mul3(h, h, p.z, q.z, rr, rr, hh, zz, r2);
+    quad_mul3(h, hh, u1, hh, zz, h, hhh, v, z3);
     G1J o;
     o.x = fe_sub(fe_sub(r2, hhh), fe_dbl(v));
     const Fp w = fe_sub(v, o.x);
-    quad_mul(rr, w, s1, hhh, rr, w, s1, hhh, t0, t1, hh, zz);
+    quad_mul2(rr, w, s1, hhh, t0, t1);
     o.y = fe_sub(t0, t1);
     o.z = z3;
     const bool pinf = p.is_inf(), qinf = q.is_inf();
@@ -105,7 +136,7 @@ static __device__ __noinline__ void quad_add(G1J* p_io, const G1J* q_in, bool ac
     }
     o = g1_select(qinf, p, o);
     o = g1_select(pinf, q, o);
-    if (active) *p_io = o;
+    *p_io = g1_select(active, o, p);
 }
 
 // *p = *p + *q where active, Q affine (finite, or (0, 0) for infinity); 5 levels
@@ -113,16 +144,16 @@ static __device__ __noinline__ void quad_add_mixed(G1J* p_io, const G1A* q_in, b
     const G1J p = *p_io;
     const G1A q = *q_in;
     Fp z1z1, t, u2, s2, t0, t1;
-    quad_mul(p.z, p.z, q.y, p.z, p.z, p.z, q.y, p.z, z1z1, t, t0, t1);
-    quad_mul(q.x, z1z1, t, z1z1, q.x, z1z1, t, z1z1, u2, s2, t0, t1);
+    quad_mul2(p.z, p.z, q.y, p.z, z1z1, t);
+    quad_mul2(q.x, z1z1, t, z1z1, u2, s2);
     const Fp h = fe_sub(u2, p.x), rr = fe_sub(s2, p.y);
     Fp hh, r2, z3, hhh, v;
-    quad_mul(h, h, rr, rr, p.z, h, h, h, hh, r2, z3, t0);
-    quad_mul(h, hh, p.x, hh, h, hh, p.x, hh, hhh, v, t0, t1);
+    quad_mul3(h, h, rr, rr, p.z, h, hh, r2, z3);
+    quad_mul2(h, hh, p.x, hh, hhh, v);
     G1J o;
     o.x = fe_sub(fe_sub(r2, hhh), fe_dbl(v));
     const Fp w = fe_sub(v, o.x);
-    quad_mul(rr, w, p.y, hhh, rr, w, p.y, hhh, t0, t1, hh, r2);
+    quad_mul2(rr, w, p.y, hhh, t0, t1);
     o.y = fe_sub(t0, t1);
     o.z = z3;
     const bool pinf = p.is_inf(), qinf = q.is_inf();
@@ -135,7 +166,7 @@ static __device__ __noinline__ void quad_add_mixed(G1J* p_io, const G1A* q_in, b
     G1J qj; qj.x = q.x; qj.y = q.y; qj.z = Fp::one();
     o = g1_select(qinf, p, o);
     o = g1_select(pinf && !qinf, qj, o);
-    if (active) *p_io = o;
+    *p_io = g1_select(active, o, p);
 }
 
 // *out = m * *p where active, for a small m (at most 16 bits); warp-collective like everything here
@@ -154,18 +185,18 @@ __device__ __forceinline__ void quad_small_mul(G1J* out, const G1J* p, unsigned 
 static __device__ __noinline__ void quad_add_sub(G1J* sum, G1J* diff, const G1J* x_in, const G1J* t_in) {
     const G1J x = *x_in, t = *t_in;
     Fp z1z1, z2z2, a, b, u1, u2, s1, s2;
-    quad_mul(x.z, x.z, t.z, t.z, x.y, t.z, t.y, x.z, z1z1, z2z2, a, b);
-    quad_mul(x.x, z2z2, t.x, z1z1, a, z2z2, b, z1z1, u1, u2, s1, s2);
+    quad_mul4(x.z, x.z, t.z, t.z, x.y, t.z, t.y, x.z, z1z1, z2z2, a, b);
+    quad_mul4(x.x, z2z2, t.x, z1z1, a, z2z2, b, z1z1, u1, u2, s1, s2);
     const Fp h = fe_sub(u2, u1), rp = fe_sub(s2, s1), rm = fe_sub(fe_neg(s2), s1);
-    Fp hh, zz, rp2, rm2, hhh, v, z3, t0;
-    quad_mul(h, h, x.z, t.z, rp, rp, rm, rm, hh, zz, rp2, rm2);
-    quad_mul(h, hh, u1, hh, zz, h, h, hh, hhh, v, z3, t0);
+    Fp hh, zz, rp2, rm2, hhh, v, z3;
+    quad_mul4(h, h, x.z, t.z, rp, rp, rm, rm, hh, zz, rp2, rm2);
+    quad_mul3(h, hh, u1, hh, zz, h, hhh, v, z3);
     const Fp v2 = fe_dbl(v);
     G1J sp, dm;
     sp.x = fe_sub(fe_sub(rp2, hhh), v2);
     dm.x = fe_sub(fe_sub(rm2, hhh), v2);
     Fp yp, ym, sh;
-    quad_mul(rp, fe_sub(v, sp.x), rm, fe_sub(v, dm.x), s1, hhh, s1, hhh, yp, ym, sh, t0);
+    quad_mul3(rp, fe_sub(v, sp.x), rm, fe_sub(v, dm.x), s1, hhh, yp, ym, sh);
     sp.y = fe_sub(yp, sh); dm.y = fe_sub(ym, sh);
     sp.z = z3; dm.z = z3;
     const bool xinf = x.is_inf(), tinf = t.is_inf();
@@ -207,8 +238,8 @@ static __device__ __noinline__ void quad_mul_digits(G1J* out, const G1J* p_in, c
         for (int i = 1; i < 8; i++) { tab[i] = tab[i - 1]; quad_add(&tab[i], &p2, true); }
     }
     const Fp beta = fp_const_beta();
-    quad_mul(tab[0].x, beta, tab[1].x, beta, tab[2].x, beta, tab[3].x, beta, bx[0], bx[1], bx[2], bx[3]);
-    quad_mul(tab[4].x, beta, tab[5].x, beta, tab[6].x, beta, tab[7].x, beta, bx[4], bx[5], bx[6], bx[7]);
+    quad_mul4(tab[0].x, beta, tab[1].x, beta, tab[2].x, beta, tab[3].x, beta, bx[0], bx[1], bx[2], bx[3]);
+    quad_mul4(tab[4].x, beta, tab[5].x, beta, tab[6].x, beta, tab[7].x, beta, bx[4], bx[5], bx[6], bx[7]);
     G1J acc = G1J::infinity();
     const int wtop = __reduce_max_sync(QUAD_FULL, top);
     for (int i = wtop; i >= 0; i--) {

@@ -172,6 +172,7 @@ def lib():
     L.b200_fk20_last_launch_count.restype = u64
     L.b200_last_launch_count.restype = u64
     L.b200_set_fixed_base_window.argtypes = [i32]
+    L.b200_set_latency_mode.argtypes = [i32]
     L.b200_selftest_field.argtypes = [sz, u64, C.POINTER(u64)]
     L.b200_probe_fp_mul.argtypes = [sz, i32, C.POINTER(C.c_float)]
     L.b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(u64)]

@@ -425,19 +425,51 @@ def test_fk20_multi_settings_sharded_by_offset():
         last.da_using_fk20_multi(poly)
 
 
-def test_single_transform_lane_mappings_agree():
-    """One transform uses three lane mappings over its stages (across blocks with sparse programs while a stage has
-    at least 32 blocks, per-lane fixed windows for the rest); batches of 16+ use whole-warp lanes.  Same input through
-    batch 1, 3 (below the whole-warp switch) and 16 must give identical bytes, at a size with many across-block stages."""
+@pytest.mark.parametrize("latency_mode", [1, 0])
+def test_single_transform_lane_mappings_agree(latency_mode):
+    """One transform uses several lane mappings over its stages: a quad of lanes per butterfly while the call has the
+    device to itself (latency mode 1, small launches), else one lane per butterfly -- across blocks with sparse programs
+    while a stage has enough blocks, per-lane fixed windows for the rest; batches of 16+ use whole-warp lanes.  Same input
+    through batch 1, 3 (below the whole-warp switch) and 16, with and without the quad kernels, must give identical bytes,
+    at a size with many across-block stages."""
     n, scale = 2048, 11
     ks, pts = _random_points(n, 2048, False)
     fs, fo = kzg.FFTSettings(scale), cref.FFTSettings(scale)
-    for inv in (False, True):
-        want = cref.g1_compress(cref.g1_mul_gen(cref.limbs_to_fr(fo.fft(cref.fr_to_limbs(ks), inv))))
-        assert np.array_equal(kzg.g1_to_compressed(fs.fft_g1(pts, inv)), want)
-        for batch in (3, 16):
-            out = fs.fft_g1_batch(np.stack([pts] * batch), inv)
-            assert np.array_equal(kzg.g1_to_compressed(out[batch - 1]), want)
+    assert kzg.lib().b200_set_latency_mode(latency_mode) == 0
+    try:
+        for inv in (False, True):
+            want = cref.g1_compress(cref.g1_mul_gen(cref.limbs_to_fr(fo.fft(cref.fr_to_limbs(ks), inv))))
+            assert np.array_equal(kzg.g1_to_compressed(fs.fft_g1(pts, inv)), want)
+            for batch in (3, 16):
+                out = fs.fft_g1_batch(np.stack([pts] * batch), inv)
+                assert np.array_equal(kzg.g1_to_compressed(out[batch - 1]), want)
+    finally:
+        kzg.lib().b200_set_latency_mode(1)
+    assert kzg.lib().b200_set_latency_mode(7) != 0
+
+
+def test_one_polynomial_calls_same_bytes_in_both_latency_modes(fk4096):
+    """FK20Single / DAUsingFK20 of ONE polynomial at n = 4096: the quad-per-butterfly stage kernels (latency mode 1, default)
+    and the one-lane kernels (mode 0, also what concurrent callers get) must produce identical proofs; spot-checked against
+    the closed form."""
+    rng = random.Random(31337)
+    poly = [rng.randrange(R) for _ in range(4096)]
+    p = kzg.fr_from_ints(poly)
+    L = kzg.lib()
+    out = {}
+    try:
+        for mode in (1, 0):
+            assert L.b200_set_latency_mode(mode) == 0
+            out[mode] = (kzg.g1_to_compressed(fk4096.fk20_single(p)), kzg.g1_to_compressed(fk4096.da_using_fk20(p)))
+    finally:
+        L.b200_set_latency_mode(1)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    ps = pyref.eval_poly(poly, SECRET)
+    w = pyref.scale2_root_of_unity(12)
+    for i in (0, 1, 2047, 4095):
+        x = pow(w, i, R)
+        q = (ps - pyref.eval_poly(poly, x)) * pow((SECRET - x) % R, -1, R) % R
+        assert bytes(out[1][0][i]) == bytes(cref.g1_compress(cref.g1_mul_gen([q]))[0])
 
 
 @pytest.mark.parametrize("scale", [2, 5, 8, 12])
