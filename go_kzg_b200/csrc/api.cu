@@ -102,6 +102,7 @@ static const int kQuadMaxCallers = 2;
 extern "C" int b200_set_latency_mode(int mode) {
     if (mode != 0 && mode != 1) return B200_ERR_BAD_INPUT;
     g_latency_mode = mode;
+    g1_set_quad_enabled(mode == 1);
     return B200_OK;
 }
 

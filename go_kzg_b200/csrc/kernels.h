@@ -108,6 +108,7 @@ void launch_g1_fft_stage(G1J* data, size_t n_half, size_t batch, size_t m, size_
 // whether launch_g1_fft_stage runs one butterfly per quad of lanes for this shape (then across_blocks needs n_half / m to be a
 // multiple of 8 only, instead of 32)
 bool g1_stage_uses_quads(size_t n_half, size_t batch);
+void g1_set_quad_enabled(bool enabled);   // process wide (b200_set_latency_mode)
 void g1_set_quad_allowed(bool allowed);   // per calling thread; the API layer clears it when several calls are in flight
 // dst[(a B + b) C + k] = src[(b A + a) C + k]
 void launch_g1_swap_digits(G1J* dst, const G1J* src, size_t A, size_t B, size_t C, cudaStream_t st);

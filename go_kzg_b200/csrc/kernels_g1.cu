@@ -9,6 +9,7 @@
 // (out-of-line point operations, tables in local memory).
 #include "g1_dev.cuh"
 #include "kernels.h"
+#include <atomic>
 #include "quad.cuh"
 
 namespace b200 {
@@ -324,9 +325,13 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_fft_stage_quad(G1J* da
 #ifndef B200_QUAD_STAGE_MAX
 #define B200_QUAD_STAGE_MAX 8192
 #endif
-static thread_local bool t_quad_allowed = true;
+static thread_local bool t_quad_allowed = true;     // per call (API layer: concurrency at the start of the call)
+static std::atomic<bool> g_quad_enabled{true};      // process wide (b200_set_latency_mode), also seen by the device-pointer entry points
 void g1_set_quad_allowed(bool allowed) { t_quad_allowed = allowed; }
-bool g1_stage_uses_quads(size_t n_half, size_t batch) { return t_quad_allowed && batch < 16 && n_half * batch <= B200_QUAD_STAGE_MAX; }
+void g1_set_quad_enabled(bool enabled) { g_quad_enabled = enabled; }
+bool g1_stage_uses_quads(size_t n_half, size_t batch) {
+    return t_quad_allowed && g_quad_enabled.load() && batch < 16 && n_half * batch <= B200_QUAD_STAGE_MAX;
+}
 
 static void stage_smem_opt_in() {
 #ifdef B200_STAGE_SMEM_TABLE

@@ -4,7 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I go_kzg_b200/csrc -I include -o tools/lat_probe tools/lat_probe.cu
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "g1_dev.cuh"
+#include "quad.cuh"
 using namespace b200;
 
 __device__ __forceinline__ G1J g1_dbl_inl(const G1J& p) {      // g1_dbl with the products inlined (ILP across them)
@@ -36,6 +36,13 @@ __global__ void __launch_bounds__(32) k_lat(uint32_t* buf, int iters, long long*
     if (MODE == 6) for (int k = 0; k < iters; k++) p = g1_dbl_inl(p);
     if (MODE == 7) for (int k = 0; k < iters; k++) x = fe_mul_k(x, y);                      // product then word-serial reduction
     if (MODE == 8) for (int k = 0; k < iters; k++) x = fp_sqr(x);
+    if (MODE == 9) for (int k = 0; k < iters; k++) quad_dbl(&p, true);                      // quad operations (quad.cuh)
+    if (MODE == 10) { G1J q = p; q.x = y; for (int k = 0; k < iters; k++) quad_add(&p, &q, true); }
+    if (MODE == 11) { G1A q; q.x = y; q.y = z; for (int k = 0; k < iters; k++) quad_add_mixed(&p, &q, true); }
+    if (MODE == 12) for (int k = 0; k < iters; k++) x = fe_add(x, y);                       // one linear operation, dependent
+    if (MODE == 13) for (int k = 0; k < iters; k++) x = quad_bcast(x, (k + threadIdx.x) & 3); // one gather of 12 words
+    if (MODE == 14) for (int k = 0; k < iters; k++) x = quad_pick3(quad_role(), x, y, z);
+    if (MODE == 15) { G1J q = p; q.x = y; for (int k = 0; k < iters; k++) g1_add_ni(&p, &p, &q); }   // one-lane general addition
     long long t1 = clock64();
     unsigned long long acc = 0;
     for (int k = 0; k < 12; k++) acc = acc * 1000003ull + x.l[k] + 31ull * y.l[k] + 17ull * z.l[k] + p.x.l[k] + p.y.l[k] + p.z.l[k];
@@ -51,8 +58,9 @@ int main() {
     const int iters = 200;
     const char* names[] = {"fe_mul inline, dependent", "fe_sqr inline, dependent", "fp_mul out-of-line call", "2 independent fe_mul per iteration",
                            "3 independent fe_sqr per iteration", "g1_dbl_ni (out-of-line products)", "g1_dbl inlined products",
-                           "fe_mul_k (product + serial reduction)", "fp_sqr out-of-line call"};
-    for (int mode = 0; mode < 9; mode++) {
+                           "fe_mul_k (product + serial reduction)", "fp_sqr out-of-line call", "quad_dbl", "quad_add", "quad_add_mixed",
+                           "fe_add, dependent", "quad_bcast (12 SHFL)", "quad_pick3", "g1_add_ni (one lane)"};
+    for (int mode = 0; mode < 16; mode++) {
         for (int rep = 0; rep < 2; rep++) {
             switch (mode) {
                 case 0: k_lat<0><<<1, 32>>>(d, iters, cyc, chk); break;
@@ -64,6 +72,13 @@ int main() {
                 case 6: k_lat<6><<<1, 32>>>(d, iters, cyc, chk); break;
                 case 7: k_lat<7><<<1, 32>>>(d, iters, cyc, chk); break;
                 case 8: k_lat<8><<<1, 32>>>(d, iters, cyc, chk); break;
+                case 9: k_lat<9><<<1, 32>>>(d, iters, cyc, chk); break;
+                case 10: k_lat<10><<<1, 32>>>(d, iters, cyc, chk); break;
+                case 11: k_lat<11><<<1, 32>>>(d, iters, cyc, chk); break;
+                case 12: k_lat<12><<<1, 32>>>(d, iters, cyc, chk); break;
+                case 13: k_lat<13><<<1, 32>>>(d, iters, cyc, chk); break;
+                case 14: k_lat<14><<<1, 32>>>(d, iters, cyc, chk); break;
+                case 15: k_lat<15><<<1, 32>>>(d, iters, cyc, chk); break;
             }
             cudaDeviceSynchronize();
         }
