@@ -171,6 +171,48 @@ __global__ void __launch_bounds__(MSM_WINDOWS_THREADS) k_msm_windows(MsmPlan p, 
 }
 static_assert(MSM_WINDOWS_THREADS == 256, "warp 0 holds one quad per warp of the CTA");
 
+// ---- steps 5 + 6 for windows of up to 512 buckets: one CTA per window, Q = min(B, 64) quads, L = B / Q buckets each ----------
+// sum_b b Bucket[b] with b = q L + j + 1:   sum_q A_q + L sum_(k >= 1) Suf_k,   A_q = sum_j (j + 1) Bucket[q L + j + 1] (running
+// sums, 2 L additions), R_q = sum_j Bucket[..], Suf_k = sum_(q >= k) R_q by a Hillis-Steele suffix scan over the quads (log2 Q
+// levels through shared memory), L Suf by log2 L doublings, then one tree over the quads.  Depth: 2 L + 2 log2 Q + 1 quad
+// additions + log2 L doublings (n = 4096: 15 additions, ~0.1 ms) where the segment + window kernels above take ~0.4 ms because of
+// their one-lane additions and the small multiplication by the segment's base index.
+#define MSM_SCAN_QUADS 64      // two warps per SM sub-partition: with 128 the four warps of a sub-partition share its multiplier and every level takes twice as long
+__global__ void __launch_bounds__(4 * MSM_SCAN_QUADS) k_msm_window_scan(MsmPlan p, const G1J* __restrict__ buckets, G1J* __restrict__ wsums) {
+    __shared__ G1J sh[MSM_SCAN_QUADS];
+    __shared__ G1J part[MSM_SCAN_QUADS / 8];
+    static_assert(MSM_SCAN_QUADS <= 64, "warp 0 holds one quad per warp of the CTA");
+    const unsigned w = blockIdx.x, tid = threadIdx.x, q = tid >> 2, Q = blockDim.x >> 2, L = p.B / Q;
+    const G1J* bkt = buckets + (size_t)w * p.B + (size_t)q * L;
+    G1J run = ld_vec(bkt + (L - 1)), acc = run;
+    for (int j = (int)L - 2; j >= 0; j--) {
+        G1J v = ld_vec(bkt + j);
+        quad_add(&run, &v, true);
+        quad_add(&acc, &run, true);
+    }
+    G1J suf = run;
+    for (unsigned d = 1; d < Q; d <<= 1) {
+        if ((tid & 3u) == 0) sh[q] = suf;
+        __syncthreads();
+        const bool act = q + d < Q;
+        G1J other = act ? sh[q + d] : G1J::infinity();
+        __syncthreads();
+        quad_add(&suf, &other, act);
+    }
+    for (unsigned l = L; l > 1; l >>= 1) quad_dbl(&suf, true);           // L Suf_q
+    quad_add(&acc, &suf, q >= 1);                                         // quad 0 has base index 0
+    quad_warp_sum(acc);
+    const unsigned nwarp = blockDim.x >> 5;
+    if ((tid & 31u) == 0) part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid < 32) {                                  // warp 0: quad j takes the sum of warp j (at most 8 warps), then a shuffle tree
+        const unsigned j = tid >> 2;
+        G1J v = j < nwarp ? part[j] : G1J::infinity();
+        quad_warp_sum(v);
+        if (tid == 0) st_vec(wsums + w, v);
+    }
+}
+
 // ---- step 7: one CTA, quad w doubles the sum of window w  c w  times; then the sum over the windows -------------
 __global__ void __launch_bounds__(160) k_msm_horner(MsmPlan p, const G1J* __restrict__ wsums, G1J* __restrict__ out) {
     __shared__ G1J part[5];
@@ -249,10 +291,16 @@ void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* w
     // 64-thread CTAs: a launch below one wave then spreads evenly over the SMs (CTAs of 128 leave some SMs with 3 and others with 2)
     if (quad_ok) k_msm_accumulate<true><<<grid_for(units * 4, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
     else k_msm_accumulate<false><<<grid_for(units, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
-    k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L), 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
-    k_msm_windows<<<p.W, MSM_WINDOWS_THREADS, 0, st>>>(p, ws.segs, ws.wsums);
+    if (p.B <= 8 * MSM_SCAN_QUADS) {                 // up to 512 buckets per window (n up to ~2^13): scan form, one kernel
+        const unsigned quads = p.B < MSM_SCAN_QUADS ? p.B : MSM_SCAN_QUADS;
+        k_msm_window_scan<<<p.W, 4 * quads, 0, st>>>(p, ws.buckets, ws.wsums);
+        g_launch_count += 6;
+    } else {
+        k_msm_segments<<<grid_for((size_t)p.W * (p.B / p.L), 128), 128, 0, st>>>(p, ws.buckets, ws.segs);
+        k_msm_windows<<<p.W, MSM_WINDOWS_THREADS, 0, st>>>(p, ws.segs, ws.wsums);
+        g_launch_count += 7;
+    }
     k_msm_horner<<<1, (unsigned)((p.W * 4 + 31) / 32 * 32), 0, st>>>(p, ws.wsums, out);
-    g_launch_count += 7;
 }
 
 }  // namespace b200
