@@ -5,6 +5,7 @@
 #include "kernels.h"
 #include "msm.cuh"
 #include "quad.cuh"
+#include <cooperative_groups.h>
 
 namespace b200 {
 
@@ -213,6 +214,63 @@ __global__ void __launch_bounds__(4 * MSM_SCAN_QUADS) k_msm_window_scan(MsmPlan 
     }
 }
 
+// The same reduction for windows of 128 .. 1024 buckets over a CLUSTER of four CTAs (4 x 32 quads = 128 quads, one quad warp
+// per SM sub-partition on four SMs, so no two warps share a multiplier): the suffix scan reads the neighbouring CTAs' values
+// through distributed shared memory.  n = 4096 (512 buckets, L = 4): 23 quad additions + 2 doublings deep.
+#define MSM_CL_CTAS 4
+#define MSM_CL_QUADS 32
+__global__ void __cluster_dims__(MSM_CL_CTAS, 1, 1) __launch_bounds__(4 * MSM_CL_QUADS)
+k_msm_window_scan_cluster(MsmPlan p, const G1J* __restrict__ buckets, G1J* __restrict__ wsums) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ G1J sh[MSM_CL_QUADS];
+    __shared__ G1J part[MSM_CL_QUADS / 8];
+    __shared__ G1J cta_total;
+    const unsigned rank = cluster.block_rank(), w = blockIdx.x / MSM_CL_CTAS, tid = threadIdx.x, q = tid >> 2;
+    const unsigned Q = MSM_CL_CTAS * MSM_CL_QUADS, gq = rank * MSM_CL_QUADS + q, L = p.B / Q;
+    const G1J* bkt = buckets + (size_t)w * p.B + (size_t)gq * L;
+    G1J run = ld_vec(bkt + (L - 1)), acc = run;
+    for (int j = (int)L - 2; j >= 0; j--) {
+        G1J v = ld_vec(bkt + j);
+        quad_add(&run, &v, true);
+        quad_add(&acc, &run, true);
+    }
+    G1J suf = run;
+    for (unsigned d = 1; d < Q; d <<= 1) {
+        if ((tid & 3u) == 0) sh[q] = suf;
+        cluster.sync();
+        const unsigned src = gq + d;
+        const bool act = src < Q;
+        G1J other = G1J::infinity();
+        if (act) {
+            const G1J* remote = cluster.map_shared_rank(sh, src / MSM_CL_QUADS);
+            other = remote[src % MSM_CL_QUADS];
+        }
+        cluster.sync();
+        quad_add(&suf, &other, act);
+    }
+    for (unsigned l = L; l > 1; l >>= 1) quad_dbl(&suf, true);
+    quad_add(&acc, &suf, gq >= 1);
+    quad_warp_sum(acc);
+    if ((tid & 31u) == 0) part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned j = tid >> 2;
+        G1J v = j < MSM_CL_QUADS / 8 ? part[j] : G1J::infinity();
+        quad_warp_sum(v);
+        if (tid == 0) cta_total = v;
+    }
+    cluster.sync();
+    if (rank == 0 && tid < 32) {
+        const unsigned j = tid >> 2;
+        G1J v = G1J::infinity();
+        if (j < MSM_CL_CTAS) v = *cluster.map_shared_rank(&cta_total, j);
+        quad_warp_sum(v);
+        if (tid == 0) st_vec(wsums + w, v);
+    }
+    cluster.sync();                                  // keep every CTA's shared memory alive until rank 0 has read it
+}
+
 // ---- step 7: one CTA, quad w doubles the sum of window w  c w  times; then the sum over the windows -------------
 __global__ void __launch_bounds__(160) k_msm_horner(MsmPlan p, const G1J* __restrict__ wsums, G1J* __restrict__ out) {
     __shared__ G1J part[5];
@@ -291,7 +349,10 @@ void launch_g1_msm(const G1J* pts, const Fr* k, int k_is_mont, size_t n, void* w
     // 64-thread CTAs: a launch below one wave then spreads evenly over the SMs (CTAs of 128 leave some SMs with 3 and others with 2)
     if (quad_ok) k_msm_accumulate<true><<<grid_for(units * 4, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
     else k_msm_accumulate<false><<<grid_for(units, 64), 64, 0, st>>>(p, pts, ws.bx, ws.sorted, ws.counts, ws.offsets, ws.flag, ws.buckets);
-    if (p.B <= 8 * MSM_SCAN_QUADS) {                 // up to 512 buckets per window (n up to ~2^13): scan form, one kernel
+    if (p.B >= MSM_CL_CTAS * MSM_CL_QUADS && p.B <= 8 * MSM_CL_CTAS * MSM_CL_QUADS) {   // 128 .. 1024 buckets: cluster of four CTAs per window
+        k_msm_window_scan_cluster<<<p.W * MSM_CL_CTAS, 4 * MSM_CL_QUADS, 0, st>>>(p, ws.buckets, ws.wsums);
+        g_launch_count += 6;
+    } else if (p.B <= 8 * MSM_SCAN_QUADS) {          // fewer buckets (n below ~1000): one CTA per window
         const unsigned quads = p.B < MSM_SCAN_QUADS ? p.B : MSM_SCAN_QUADS;
         k_msm_window_scan<<<p.W, 4 * quads, 0, st>>>(p, ws.buckets, ws.wsums);
         g_launch_count += 6;

@@ -14,8 +14,8 @@
 //               in adjacent lanes and are combined with a warp-shuffle tree
 //   5 segments  unit = L consecutive buckets: sum_j (b0 + j) Bucket[b0 + j] with a running sum
 //   6 windows   one CTA per window: tree sum of its segments
-//     (windows of up to 512 buckets: 5 + 6 are one kernel, k_msm_window_scan -- running sums per quad, suffix scan over the
-//      quads, one tree; no small multiplication by the segment's base index)
+//     (windows of up to 1024 buckets: 5 + 6 are one kernel, k_msm_window_scan(_cluster) -- running sums per quad, suffix scan
+//      over the quads (of a cluster of four CTAs from 128 buckets on), one tree; no small multiplication by a base index)
 //   7 horner    window w doubled c w times, then the sum of the W weighted window sums
 // Steps 5-7 (and step 4 when the problem is too small to fill the chip) run one unit per QUAD of lanes (quad.cuh):
 // they are waited for because of the depth of their chains of point operations, and a quad walks a chain 2-3x faster.

@@ -120,7 +120,7 @@ def _random_points(n, seed, affine):
     return ks, pts
 
 
-@pytest.mark.parametrize("n,affine", [(32, True), (33, False), (257, False), (4096, True), (4096, False), (65536, True)])
+@pytest.mark.parametrize("n,affine", [(32, True), (33, False), (257, False), (600, True), (1024, False), (4096, True), (4096, False), (8192, True), (65536, True)])
 def test_lincomb_bucket_msm(n, affine):
     """generic b200_g1_lincomb (no settings, no fixed-base table) over arbitrary points: the Pippenger path from 32
     terms on; affine inputs take mixed additions, Jacobian inputs (Z != 1) general ones.  Structured cases: zero
