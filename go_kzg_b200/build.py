@@ -55,14 +55,30 @@ def _compile(unit: str, verbose: bool, defines=(), tag: str = "") -> str:
     return obj
 
 
+def _source_digest() -> str:
+    """SHA-256 over the names and contents of every source the library is built from (mtimes do not survive a copy of the
+    tree to another machine in any useful order, contents do)."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(_deps()):
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    newest = max(os.path.getmtime(p) for p in _deps())
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+    stamp = LIB + ".srchash"
+    digest = _source_digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     with ThreadPoolExecutor(len(UNITS)) as ex:
         objs = list(ex.map(lambda u: _compile(u, verbose), UNITS))
     subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+    with open(stamp, "w") as f:
+        f.write(digest + "\n")
     return LIB
 
 
