@@ -113,16 +113,16 @@ struct StreamLease {
     void count() { counted = true; g1_set_quad_allowed(++g_active_calls <= kQuadMaxCallers && g_latency_mode.load() == 1); }
     static std::mutex& mu() { static std::mutex m; return m; }
     static std::vector<cudaStream_t>& pool(int d) { static std::vector<cudaStream_t> p[64]; return p[d]; }
-    int acquire() {
+    int acquire(bool counted_call = true) {      // counted_call = false: an extra stream of a call that already holds one
         CK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64) return B200_ERR_BAD_INPUT;
         {
             std::lock_guard<std::mutex> lk(mu());
             auto& p = pool(dev);
-            if (!p.empty()) { st = p.back(); p.pop_back(); count(); return B200_OK; }
+            if (!p.empty()) { st = p.back(); p.pop_back(); if (counted_call) count(); return B200_OK; }
         }
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        count();
+        if (counted_call) count();
         return B200_OK;
     }
     ~StreamLease() {
@@ -449,6 +449,8 @@ extern "C" int b200_das_fft_extension_batch(b200_fs* fs, uint64_t* vals, size_t 
     if (batch == 0) return B200_OK;
     if (batch > 65535) return B200_ERR_TOO_LARGE;           // the batch rides on grid.y
     CK(cudaSetDevice(fs->device));
+    // (cutting the batch into chunks on several streams to overlap the copies was measured SLOWER: 55 k against 69 k
+    // polynomials/s at n = 8192, batch 64 -- the per-chunk allocations and launches cost more than the overlap returns)
     StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
     DevBuf raw, buf;
     CKS(raw.alloc(batch * n * 32, st)); CKS(buf.alloc(batch * n * sizeof(Fr), st));
@@ -497,30 +499,38 @@ static bool zero_poly_sizes_ok(size_t nmiss, size_t length) {
 }
 
 // device side: zero_eval[b] and zero_poly[b] (Montgomery) for `batch` missing lists
-static int dev_zero_poly(b200_fs* fs, const std::vector<uint32_t>& h_missing, const std::vector<uint32_t>& h_nmiss, size_t pitch,
-                         size_t n, size_t batch, Fr* d_zero_eval, Fr* d_zero_poly, cudaStream_t st) {
-    size_t max_missing = 0;
-    for (size_t b = 0; b < batch; b++) if (h_nmiss[b] > max_missing) max_missing = h_nmiss[b];
-    DevBuf miss, cnt, partial;
-    CKS(miss.alloc(h_missing.size() * 4, st)); CKS(cnt.alloc(batch * 4, st));
-    CK(cudaMemcpyAsync(miss.p, h_missing.data(), h_missing.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(cnt.p, h_nmiss.data(), batch * 4, cudaMemcpyHostToDevice, st));
+// zero polynomial of `batch` index sets that already sit on the device (d_missing: pitch entries per set, d_nmiss: their
+// sizes; max_missing: the largest size, known to the host)
+static int dev_zero_poly_lists(b200_fs* fs, const uint32_t* d_missing, const uint32_t* d_nmiss, size_t max_missing, size_t pitch,
+                               size_t n, size_t batch, Fr* d_zero_eval, Fr* d_zero_poly, cudaStream_t st) {
     const size_t mp = zero_poly_tree_size(max_missing);
     if (max_missing >= 256 && mp <= n && max_missing < n) {
         // large sets: coefficients through the product tree, evaluations with one forward NTT
         DevBuf ca, cb, padded, tmp;
         CKS(ca.alloc(batch * mp * sizeof(Fr), st)); CKS(cb.alloc(batch * mp * sizeof(Fr), st));
         CKS(padded.alloc(batch * 2 * mp * sizeof(Fr), st)); CKS(tmp.alloc(batch * 2 * mp * sizeof(Fr), st));
-        launch_zero_poly_tree(fs->dom, n, batch, miss.as<uint32_t>(), cnt.as<uint32_t>(), pitch, mp, ca.as<Fr>(), cb.as<Fr>(),
+        launch_zero_poly_tree(fs->dom, n, batch, d_missing, d_nmiss, pitch, mp, ca.as<Fr>(), cb.as<Fr>(),
                               padded.as<Fr>(), tmp.as<Fr>(), d_zero_poly, st);
         CKS(check_launches());
         CKS(dev_fr_fft(fs, d_zero_poly, d_zero_eval, log2u(n), batch, false, st));
     } else {
+        DevBuf partial;
         CKS(partial.alloc(batch * zero_eval_segments(max_missing) * n * sizeof(Fr), st));
-        launch_zero_eval(fs->dom, n, batch, miss.as<uint32_t>(), cnt.as<uint32_t>(), pitch, max_missing, partial.as<Fr>(), d_zero_eval, st);
+        launch_zero_eval(fs->dom, n, batch, d_missing, d_nmiss, pitch, max_missing, partial.as<Fr>(), d_zero_eval, st);
         CKS(check_launches());
         CKS(dev_fr_fft(fs, d_zero_eval, d_zero_poly, log2u(n), batch, true, st));
     }
+    return B200_OK;
+}
+static int dev_zero_poly(b200_fs* fs, const std::vector<uint32_t>& h_missing, const std::vector<uint32_t>& h_nmiss, size_t pitch,
+                         size_t n, size_t batch, Fr* d_zero_eval, Fr* d_zero_poly, cudaStream_t st) {
+    size_t max_missing = 0;
+    for (size_t b = 0; b < batch; b++) if (h_nmiss[b] > max_missing) max_missing = h_nmiss[b];
+    DevBuf miss, cnt;
+    CKS(miss.alloc(h_missing.size() * 4, st)); CKS(cnt.alloc(batch * 4, st));
+    CK(cudaMemcpyAsync(miss.p, h_missing.data(), h_missing.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cnt.p, h_nmiss.data(), batch * 4, cudaMemcpyHostToDevice, st));
+    CKS(dev_zero_poly_lists(fs, miss.as<uint32_t>(), cnt.as<uint32_t>(), max_missing, pitch, n, batch, d_zero_eval, d_zero_poly, st));
     CK(cudaStreamSynchronize(st));   // h_missing / h_nmiss are the caller's stack vectors
     return B200_OK;
 }
@@ -574,16 +584,33 @@ static int fs_shift_tables(b200_fs* fs, const Fr** inv_pows, const Fr** pows) {
     return B200_OK;
 }
 
+// number of zero bytes among n (present[i] == 0 <=> samples[i] == nil), eight at a time
+static uint32_t count_zero_bytes(const uint8_t* p, size_t n) {
+    uint32_t c = 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t v;
+        memcpy(&v, p + i, 8);
+        const uint64_t k = 0x7f7f7f7f7f7f7f7full;
+        const uint64_t t = ~(((v & k) + k) | v | k);                // 0x80 in every byte of v that is zero
+        c += (uint32_t)__builtin_popcountll(t);
+    }
+    for (; i < n; i++) c += p[i] == 0;
+    return c;
+}
+
+// recover_from_samples.go:42-109 for a batch.  The host only counts the missing samples (every size check of the reference
+// depends on the counts alone); the index lists are compacted on the device from the presence mask -- built on the host they
+// cost more than the whole device pipeline.  On an error return the contents of `out` are unspecified.
 extern "C" int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t* samples, const uint8_t* present, size_t n,
                                                     size_t batch, uint64_t* out) {
     if (batch == 0) return B200_OK;
     if (batch > 65535) return B200_ERR_TOO_LARGE;                  // the batch rides on grid.y / grid.z
-    // missing index lists (recover_from_samples.go:45-50)
-    std::vector<uint32_t> miss(batch * n), cnt(batch);
+    std::vector<uint32_t> cnt(batch);
+    size_t max_missing = 0;
     for (size_t b = 0; b < batch; b++) {
-        uint32_t c = 0;
-        for (size_t i = 0; i < n; i++) if (!present[b * n + i]) miss[b * n + c++] = (uint32_t)i;
-        cnt[b] = c;
+        cnt[b] = count_zero_bytes(present + b * n, n);
+        if (cnt[b] > max_missing) max_missing = cnt[b];
     }
     for (size_t b = 0; b < batch; b++) {
         // nothing missing: zeroPolyFn returns all zeros and the sanity loop panics (recover_from_samples.go:54-58)
@@ -598,15 +625,16 @@ extern "C" int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t*
     const unsigned logn = log2u(n);
     const size_t total = batch * n;
     StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
-    DevBuf raw, s, ze, zp, a, c, pres, flags;
+    DevBuf raw, s, ze, zp, a, c, pres, flags, miss, dcnt;
     CKS(raw.alloc(total * 32, st)); CKS(s.alloc(total * sizeof(Fr), st)); CKS(ze.alloc(total * sizeof(Fr), st));
     CKS(zp.alloc(total * sizeof(Fr), st)); CKS(a.alloc(total * sizeof(Fr), st)); CKS(c.alloc(total * sizeof(Fr), st));
-    CKS(pres.alloc(total, st)); CKS(flags.alloc(batch * 4, st));
-    CK(cudaMemcpyAsync(raw.p, samples, total * 32, cudaMemcpyHostToDevice, st));
+    CKS(pres.alloc(total, st)); CKS(flags.alloc(batch * 4, st)); CKS(miss.alloc(total * 4, st)); CKS(dcnt.alloc(batch * 4, st));
     CK(cudaMemcpyAsync(pres.p, present, total, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(raw.p, samples, total * 32, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(flags.p, 0, batch * 4, st));
+    launch_missing_lists(pres.as<uint8_t>(), n, batch, miss.as<uint32_t>(), n, dcnt.as<uint32_t>(), st);   // :45-50
     launch_fr_to_mont(raw.as<uint64_t>(), s.as<Fr>(), total, st);
-    CKS(dev_zero_poly(fs, miss, cnt, n, n, batch, ze.as<Fr>(), zp.as<Fr>(), st));
+    CKS(dev_zero_poly_lists(fs, miss.as<uint32_t>(), dcnt.as<uint32_t>(), max_missing, n, n, batch, ze.as<Fr>(), zp.as<Fr>(), st));
     launch_fr_mul_masked(a.as<Fr>(), s.as<Fr>(), ze.as<Fr>(), pres.as<uint8_t>(), total, st);   // E = samples (.) zeroEval
     CKS(dev_fr_fft(fs, a.as<Fr>(), a.as<Fr>(), logn, batch, true, st));                            // polyWithZero
     launch_fr_mul_table(a.as<Fr>(), shift_inv, n, batch, st);                                      // ShiftPoly
@@ -620,6 +648,7 @@ extern "C" int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t*
     launch_recover_check(a.as<Fr>(), s.as<Fr>(), ze.as<Fr>(), pres.as<uint8_t>(), n, batch, flags.as<uint32_t>(), st);
     launch_fr_from_mont(a.as<Fr>(), raw.as<uint64_t>(), total, st);
     CKS(check_launches());
+    CK(cudaMemcpyAsync(out, raw.p, total * 32, cudaMemcpyDeviceToHost, st));
     std::vector<uint32_t> h_flags(batch);
     CK(cudaMemcpyAsync(h_flags.data(), flags.p, batch * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -627,8 +656,6 @@ extern "C" int b200_recover_poly_from_samples_batch(b200_fs* fs, const uint64_t*
         if (h_flags[b] & 2) return B200_ERR_ZERO_EVAL;             // recover_from_samples.go:54-58 (panic)
         if (h_flags[b] & 1) return B200_ERR_RECOVERY;              // recover_from_samples.go:103-107 (error)
     }
-    CK(cudaMemcpyAsync(out, raw.p, total * 32, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     return B200_OK;
 }
 extern "C" int b200_recover_poly_from_samples(b200_fs* fs, const uint64_t* s, const uint8_t* p, size_t n, uint64_t* out) {

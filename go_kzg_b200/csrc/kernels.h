@@ -56,6 +56,7 @@ size_t zero_eval_segments(size_t max_missing);
 // product-tree route for large missing sets: zero_poly[b][0..n) (Montgomery coefficients); mp = zero_poly_tree_size(max
 // missing) <= n padded roots per list; coef_a, coef_b: batch * mp scratch each, padded, ntt_tmp: batch * 2 mp each
 size_t zero_poly_tree_size(size_t max_missing);
+void launch_missing_lists(const uint8_t* present, size_t n, size_t batch, uint32_t* missing, size_t pitch, uint32_t* nmiss, cudaStream_t st);
 void launch_zero_poly_tree(const FrDomain& dom, size_t n, size_t batch, const uint32_t* d_missing, const uint32_t* d_nmiss,
                            size_t miss_pitch, size_t mp, Fr* coef_a, Fr* coef_b, Fr* padded, Fr* ntt_tmp, Fr* zero_poly,
                            cudaStream_t st);

@@ -618,6 +618,41 @@ void launch_recover_check(const Fr* rec, const Fr* samples, const Fr* zero_eval,
     k_recover_check<<<grid_for(n * batch, 256), 256, 0, st>>>(rec, samples, zero_eval, present, n, n * batch, flags); g_launch_count++;
 }
 
+// ------------------------------------------------------------------------------ missing index lists
+// recover_from_samples.go:45-50 on the device: for every polynomial the ascending list of indices i with present[i] == 0
+// (stream compaction: one CTA per polynomial, every thread owns n / blockDim consecutive entries; block-wide exclusive scan
+// of the per-thread counts).  On the host this loop cost more than the whole device pipeline of a batch (config 4).
+__global__ void __launch_bounds__(1024) k_missing_lists(const uint8_t* __restrict__ present, size_t n, uint32_t* __restrict__ missing,
+                                                        size_t pitch, uint32_t* __restrict__ nmiss) {
+    __shared__ uint32_t warp_tot[32];
+    const size_t b = blockIdx.x;
+    const uint8_t* pr = present + b * n;
+    const unsigned nt = blockDim.x, tid = threadIdx.x;
+    const size_t per = (n + nt - 1) / nt, lo = (size_t)tid * per, hi = lo + per < n ? lo + per : n;
+    uint32_t c = 0;
+    for (size_t i = lo; i < hi; i++) c += pr[i] == 0;
+    // inclusive scan inside the warp, then over the warp totals
+    uint32_t incl = c;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= (unsigned)d) incl += v; }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t t = tid < (nt + 31) / 32 ? warp_tot[tid] : 0u, ti = t;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, ti, d); if (tid >= (unsigned)d) ti += v; }
+        warp_tot[tid] = ti - t;                                   // exclusive prefix of the warp totals
+        if (tid == 31) nmiss[b] = ti;
+    }
+    __syncthreads();
+    uint32_t pos = warp_tot[tid >> 5] + incl - c;
+    uint32_t* out = missing + b * pitch;
+    for (size_t i = lo; i < hi; i++) if (pr[i] == 0) out[pos++] = (uint32_t)i;
+}
+void launch_missing_lists(const uint8_t* present, size_t n, size_t batch, uint32_t* missing, size_t pitch, uint32_t* nmiss, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n || !batch) return;
+    k_missing_lists<<<(unsigned)batch, 1024, 0, st>>>(present, n, missing, pitch, nmiss); g_launch_count++;
+}
+
 // ------------------------------------------------------------------------------ powers
 // out[i] = s^i (canonical), i < n, by square-and-multiply over the bits of i; sq[j] = s^(2^j) (Montgomery)
 __global__ void k_fr_powers(const Fr* __restrict__ sq, Fr* __restrict__ out, size_t n) {
