@@ -528,21 +528,21 @@ def test_recover_batch_and_errors():
 
 
 @pytest.mark.parametrize("batch", [16, 18, 37])
-def test_chunked_batches_of_recovery_and_extension(batch):
-    """Batches of 16+ polynomials run as four chunks on up to three streams (uploads, kernels and downloads overlapping):
-    ragged chunk sizes, different missing ratios per polynomial, every output against its own single call / the data."""
+def test_larger_batches_of_recovery_and_extension(batch):
+    """Batches with a different missing ratio per polynomial: the index lists are compacted on the device from the presence
+    masks (ragged counts inside one launch); every output against the data / its own single call."""
     scale = 8
     fs = kzg.FFTSettings(scale)
     cases = [_recovery_case(scale, 0.5 + 0.02 * (b % 20), 900 + b) for b in range(batch)]
     out = fs.recover_poly_from_samples_batch(np.stack([c[1] for c in cases]), np.stack([c[2] for c in cases]))
     for b in range(batch):
         assert kzg.fr_to_ints(out[b]) == cases[b][0]
-    # the extension: chunked batch == one call per polynomial
+    # the extension: batch == one call per polynomial
     evens = np.stack([kzg.fr_from_ints(random_fr_ints(1 << (scale - 1), 7000 + b)) for b in range(batch)])
     odds = fs.das_fft_extension_batch(evens)
     for b in (0, 1, batch // 2, batch - 1):
         assert np.array_equal(odds[b], fs.das_fft_extension(evens[b]))
-    # a polynomial with nothing missing in the LAST chunk: the whole call fails the way the single call does (:54-58)
+    # a polynomial with nothing missing at the end of the batch: the whole call fails the way the single call does (:54-58)
     pres = np.stack([c[2] for c in cases])
     pres[batch - 1] = 1
     with pytest.raises(kzg.KZGPanic):
