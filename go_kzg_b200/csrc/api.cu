@@ -1152,18 +1152,23 @@ static int ks_secret_g2(const b200_ks* ks, size_t i, G2J* out) {
     return g2_on_curve(*out) ? B200_OK : B200_ERR_BAD_INPUT;
 }
 
-// ok[i] = e(lhs[i], [1]_2) == e(proofs[i], rhs[i]) on the host cores, one pairing check per item
-static int pairing_checks(const uint64_t* lhs, const uint64_t* proofs, const std::vector<G2J>& rhs, size_t batch, uint8_t* ok) {
-    for (size_t i = 0; i < batch; i++)
+// ok[i] = e(lhs[i], [1]_2) == e(proofs[i], t2 - cs[i] [1]_2) on the host cores: one G2 scalar multiplication and one pairing
+// check per item, both inside the worker threads
+static int pairing_checks(const uint64_t* lhs, const uint64_t* proofs, const G2J& t2, const uint64_t* cs, size_t batch, uint8_t* ok) {
+    for (size_t i = 0; i < batch; i++) {
+        if (!fr_canon_valid(cs + 4 * i)) return B200_ERR_BAD_INPUT;
         if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi_h(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
+    }
     const G2J gen = g2_generator();
     unsigned nt = std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
     if (nt > batch) nt = (unsigned)batch;
     std::atomic<size_t> next{0};
     auto work = [&]() {
-        for (size_t i; (i = next.fetch_add(1)) < batch;)
-            ok[i] = pairings_verify(g1_from_abi(lhs + 18 * i), gen, g1_from_abi(proofs + 18 * i), rhs[i]) ? 1 : 0;
+        for (size_t i; (i = next.fetch_add(1)) < batch;) {
+            const G2J rhs = g2_sub(t2, g2_mul(gen, fr_load_canon(cs + 4 * i)));
+            ok[i] = pairings_verify(g1_from_abi_h(lhs + 18 * i), gen, g1_from_abi_h(proofs + 18 * i), rhs) ? 1 : 0;
+        }
     };
     std::vector<std::thread> th;
     for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
@@ -1181,13 +1186,7 @@ extern "C" int b200_check_proof_single_batch(b200_ks* ks, const uint64_t* commit
     if (batch == 0) return B200_OK;
     std::vector<uint64_t> lhs(batch * 18);
     CKS(b200_check_proof_single_g1_batch(commitments, ys, batch, lhs.data()));
-    const G2J gen = g2_generator();
-    std::vector<G2J> rhs(batch);
-    for (size_t i = 0; i < batch; i++) {
-        if (!fr_canon_valid(xs + 4 * i)) return B200_ERR_BAD_INPUT;
-        rhs[i] = g2_sub(s2, g2_mul(gen, fr_load_canon(xs + 4 * i)));
-    }
-    return pairing_checks(lhs.data(), proofs, rhs, batch, ok);
+    return pairing_checks(lhs.data(), proofs, s2, xs, batch, ok);
 }
 extern "C" int b200_check_proof_single(b200_ks* ks, const uint64_t* commitment, const uint64_t* proof, const uint64_t* x, const uint64_t* y,
                                        int* ok) {
@@ -1206,10 +1205,7 @@ extern "C" int b200_check_proof_multi_batch(b200_ks* ks, const uint64_t* commitm
     if (batch == 0) return B200_OK;
     std::vector<uint64_t> lhs(batch * 18), xn(batch * 4);
     CKS(b200_check_proof_multi_g1_batch(ks, commitments, xs, ys, n, batch, lhs.data(), xn.data()));
-    const G2J gen = g2_generator();
-    std::vector<G2J> rhs(batch);
-    for (size_t i = 0; i < batch; i++) rhs[i] = g2_sub(sn, g2_mul(gen, fr_load_canon(xn.data() + 4 * i)));
-    return pairing_checks(lhs.data(), proofs, rhs, batch, ok);
+    return pairing_checks(lhs.data(), proofs, sn, xn.data(), batch, ok);
 }
 extern "C" int b200_check_proof_multi(b200_ks* ks, const uint64_t* commitment, const uint64_t* proof, const uint64_t* x, const uint64_t* ys,
                                       size_t n, int* ok) {
