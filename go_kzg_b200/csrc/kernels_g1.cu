@@ -418,11 +418,31 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_programs(G1J* data
     g1_mul_program(&r, &x, progs + pi * prog_stride);
     st_vec(p, r);
 }
+// the same with a quad of lanes per product (latency mode, small launches: see g1_stage_uses_quads)
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_programs_quad(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride,
+                                                                            const ScalarProgram* __restrict__ progs, size_t prog_stride,
+                                                                            int bitrev, unsigned logn) {
+    const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool valid = t < n * batch;                  // quads past the end idle through the collective operations
+    const size_t tc = valid ? t : 0;
+    const size_t b = tc % batch, i = tc / batch;
+    const size_t pi = bitrev ? bitrev_u32((uint32_t)i, logn) : i;
+    G1J* p = data + b * bstride + i * estride;
+    G1J x = G1J::infinity(), r;
+    if (valid) x = ld_vec(p);
+    quad_mul_program(&r, &x, progs + pi * prog_stride);
+    if (valid && (threadIdx.x & 3u) == 0) st_vec(p, r);
+}
 void launch_g1_mul_programs(G1J* data, size_t n, size_t batch, size_t estride, size_t bstride, const ScalarProgram* progs,
                             size_t prog_stride, int bitrev, unsigned logn, cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_MUL, st);
     if (!n || !batch) return;
-    k_g1_mul_programs<<<grid_for(n * g1_lanes_for_batch(batch), G1_BLOCK), G1_BLOCK, 0, st>>>(data, n, batch, estride, bstride, progs, prog_stride, bitrev, logn);
+    if (g1_stage_uses_quads(n, batch)) {
+        const size_t lanes = (n * batch * 4 + 31) / 32 * 32;
+        k_g1_mul_programs_quad<<<grid_for(lanes, G1_BLOCK), G1_BLOCK, 0, st>>>(data, n, batch, estride, bstride, progs, prog_stride, bitrev, logn);
+    } else {
+        k_g1_mul_programs<<<grid_for(n * g1_lanes_for_batch(batch), G1_BLOCK), G1_BLOCK, 0, st>>>(data, n, batch, estride, bstride, progs, prog_stride, bitrev, logn);
+    }
     g_launch_count++;
 }
 
@@ -517,6 +537,73 @@ __device__ __forceinline__ void fb_accumulate(G1J* acc, const G1A* __restrict__ 
         }
     }
 }
+// Latency form of the look-ups (small launches): the windows of one product are spread over FB_SPLIT adjacent lanes, each
+// lane adds its share (windows w = lane, lane + FB_SPLIT, ..), and the partial sums are combined with a shuffle tree:
+// 32 dependent additions become 4 + 3 tree levels (W = 8).  The digit recoding carries from window to window, so every lane
+// walks all the windows and adds only at its own.
+#define FB_SPLIT 8
+template <int W>
+__device__ __forceinline__ void fb_accumulate_strided(G1J* acc, const G1A* __restrict__ row, const Fr& s, unsigned first) {
+    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1), MASK = (1u << W) - 1u, PER = (NW + FB_SPLIT - 1) / FB_SPLIT;
+    // pass 1: the signed digits of this lane's windows (the recoding carries from window to window: all of them are walked)
+    int mine[PER];
+#pragma unroll
+    for (unsigned j = 0; j < PER; j++) mine[j] = 0;
+    unsigned carry = 0;
+#pragma unroll
+    for (unsigned w = 0; w < NW; w++) {
+        const unsigned off = w * W, li = off >> 5, sh = off & 31u;
+        unsigned bits = s.l[li] >> sh;
+        if (sh + W > 32 && li + 1 < 8) bits |= s.l[li + 1] << (32 - sh);
+        unsigned d = (bits & MASK) + carry;
+        const bool neg = d > D;
+        if (neg) { d = (1u << W) - d; carry = 1; } else carry = 0;
+        if ((w % FB_SPLIT) == first) mine[w / FB_SPLIT] = neg ? -(int)d : (int)d;
+    }
+    // pass 2: the j-th addition of every lane in the same iteration (lanes that diverge serialise: one addition per window
+    // and warp would cost what the unsplit loop costs)
+#pragma unroll
+    for (unsigned j = 0; j < PER; j++) {
+        const int dg = mine[j];
+        const unsigned w = j * FB_SPLIT + first;
+        if (dg != 0 && w < NW) {
+            const unsigned d = dg < 0 ? (unsigned)(-dg) : (unsigned)dg;
+            G1A p = ld_vec(row + w * D + (d - 1));
+            if (dg < 0) p.y = fe_neg(p.y);
+            g1_add_mixed_ni(acc, acc, &p);
+        }
+    }
+}
+__device__ __forceinline__ void g1_split_sum(G1J& acc) {          // sum over FB_SPLIT adjacent lanes (whole warps only)
+    for (unsigned off = FB_SPLIT >> 1; off >= 1; off >>= 1) {
+        G1J other;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            other.x.l[i] = __shfl_xor_sync(0xffffffffu, acc.x.l[i], off);
+            other.y.l[i] = __shfl_xor_sync(0xffffffffu, acc.y.l[i], off);
+            other.z.l[i] = __shfl_xor_sync(0xffffffffu, acc.z.l[i], off);
+        }
+        g1_add_ni(&acc, &acc, &other);
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base_split(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
+                                                                               G1J* out, size_t out_bstride, size_t n, size_t batch) {
+    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, t = tid / FB_SPLIT;
+    const unsigned lane = (unsigned)(tid % FB_SPLIT);
+    const bool valid = t < n * batch;                              // the grid is whole warps: idle groups walk the tree with infinity
+    G1J acc = G1J::infinity();
+    size_t b = 0, i = 0;
+    if (valid) {
+        b = t % batch; i = t / batch;
+        Fr s = ld_vec(k + b * n + i);
+        if (k_is_mont) s = fe_from_mont(s);
+        fb_accumulate_strided<W>(&acc, table + i * (size_t)(NW * D), s, lane);
+    }
+    g1_split_sum(acc);
+    if (valid && lane == 0) st_vec(out + b * out_bstride + i, acc);
+}
 template <int W>
 __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_g1_mul_fixed_base(const G1A* __restrict__ table, const Fr* __restrict__ k, int k_is_mont,
                                                                          G1J* out, size_t out_bstride, size_t n, size_t batch) {
@@ -571,10 +658,58 @@ __global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_fk20_part2_fold2(const G1
     }
     st_vec(out + b * out_bstride + i, acc);
 }
+// latency form of k_fk20_part2_fold2: FB_SPLIT lanes per output slot (the 4 x 32 additions of an odd slot become 16 + 3 tree levels)
+template <int W>
+__global__ void __launch_bounds__(G1_BLOCK, G1_MINB) k_fk20_part2_fold2_split(const G1A* __restrict__ table, const Fr* __restrict__ c,
+                                                                              const Fr* __restrict__ rev, size_t rstride, G1J* out,
+                                                                              size_t out_bstride, size_t k, size_t batch) {
+    constexpr unsigned NW = (256 + W - 1) / W, D = 1u << (W - 1);
+    constexpr size_t ROW = (size_t)NW * D;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, t = tid / FB_SPLIT;
+    const unsigned lane = (unsigned)(tid % FB_SPLIT);
+    const bool valid = t < 2 * k * batch;
+    G1J acc = G1J::infinity();
+    size_t b = 0, i = 0;
+    if (valid) {
+        b = t % batch;
+        const size_t ii = t / batch;
+        i = ii < k ? 2 * ii + 1 : 2 * (ii - k);
+        const Fr* cb = c + b * 2 * k;
+        if (!(i & 1)) {
+            fb_accumulate_strided<W>(&acc, table + i * ROW, fe_from_mont(ld_vec(cb + i)), lane);
+        } else {
+            const size_t q = k / 4, m = i >> 1, o = m / q, p = m % q;
+            Fr u = ld_vec(rev + 2 * p * rstride), v = ld_vec(rev + p * rstride), v2 = ld_vec(rev + (p + q) * rstride);
+            for (unsigned tt = 0; tt < 4; tt++) {
+                const size_t src = 2 * (p + tt * q) + 1;
+                Fr s = ld_vec(cb + src);
+                bool neg = false;
+                if (o == 1) { s = fe_mul(s, u); neg = tt & 1; }
+                else if (o == 2) { s = fe_mul(s, (tt & 1) ? v2 : v); neg = tt >= 2; }
+                else if (o == 3) { s = fe_mul(fe_mul(s, (tt & 1) ? v2 : v), u); neg = (tt == 1 || tt == 2); }
+                if (neg) s = fe_neg(s);
+                fb_accumulate_strided<W>(&acc, table + src * ROW, fe_from_mont(s), lane);
+            }
+        }
+    }
+    g1_split_sum(acc);
+    if (valid && lane == 0) st_vec(out + b * out_bstride + i, acc);
+}
+// look-ups of a launch this small are waited for because of the DEPTH of their chains of additions
+static bool fb_uses_split(size_t products) { return g1_stage_uses_quads(products / 2, 1); }
 void launch_fk20_part2_fold2(const G1A* table, int W, const Fr* c, const Fr* rev, size_t rstride, G1J* out, size_t out_bstride,
                              size_t k, size_t batch, cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_LOOKUP, st);
     if (!k || !batch) return;
+    if (fb_uses_split(2 * k * batch)) {
+        const unsigned g = grid_for(2 * k * batch * FB_SPLIT, G1_BLOCK);
+        if (W == 12) k_fk20_part2_fold2_split<12><<<g, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+        else if (W == 10) k_fk20_part2_fold2_split<10><<<g, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+        else if (W == 8) k_fk20_part2_fold2_split<8><<<g, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+        else k_fk20_part2_fold2_split<4><<<g, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
+        g_launch_count++;
+        return;
+    }
     const unsigned grid = grid_for(2 * k * batch, G1_BLOCK);
     if (W == 12) k_fk20_part2_fold2<12><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
     else if (W == 10) k_fk20_part2_fold2<10><<<grid, G1_BLOCK, 0, st>>>(table, c, rev, rstride, out, out_bstride, k, batch);
@@ -586,6 +721,15 @@ void launch_g1_mul_fixed_base(const G1A* table, int W, const Fr* k, int k_is_mon
                               cudaStream_t st) {
     ProfScope prof_scope(PROF_G1_LOOKUP, st);
     if (!n || !batch) return;
+    if (fb_uses_split(n * batch)) {
+        const unsigned g = grid_for(n * batch * FB_SPLIT, G1_BLOCK);
+        if (W == 12) k_g1_mul_fixed_base_split<12><<<g, G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+        else if (W == 10) k_g1_mul_fixed_base_split<10><<<g, G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+        else if (W == 8) k_g1_mul_fixed_base_split<8><<<g, G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+        else k_g1_mul_fixed_base_split<4><<<g, G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
+        g_launch_count++;
+        return;
+    }
     if (W == 12) k_g1_mul_fixed_base<12><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     else if (W == 10) k_g1_mul_fixed_base<10><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);
     else if (W == 8) k_g1_mul_fixed_base<8><<<grid_for(n * batch, G1_BLOCK), G1_BLOCK, 0, st>>>(table, k, k_is_mont, out, out_bstride, n, batch);

@@ -51,7 +51,7 @@ const char* b200_strerror(int status);
 const char* b200_last_cuda_error(void);
 int b200_device_count(void);
 /* Latency mode of small G1 transforms (one polynomial per call): 1 (default) = automatic -- a call that finds at most one other
- * call in flight spends four lanes per butterfly (FK20Single of one n = 4096 polynomial: 37 -> 24 ms); 0 = never (servers
+ * call in flight spends four lanes per butterfly (FK20Single of one n = 4096 polynomial: 37 -> 23 ms); 0 = never (servers
  * that always run many callers and want the aggregate rate).  Results are identical either way. */
 int b200_set_latency_mode(int mode);
 /* Selects the CUDA device used by handles created afterwards on this thread (default 0). */
