@@ -196,7 +196,7 @@ def run_components(kzg, L, fk, fs, torch, dist, rank, world, max_over_ranks, bar
         if errs:
             raise errs[0]
         return nthreads * reps / dt
-    concurrent(8, 2)
+    concurrent(32, 1)          # creates the pooled streams and grows the memory pool outside the timed passes
     out["fk20_single_concurrent_callers"] = {("%d_threads_polys_per_s" % t): round(world * max_over_ranks(-concurrent(t, 6)) * -1, 2) for t in (1, 2, 8, 32)}
     out["one_polynomial_note"] = "host-buffer call per polynomial, n = %d (b200_fk20_single / b200_da_using_fk20), wall clock, max over ranks" % N_COEFFS
     if N_COEFFS == 4096:
