@@ -1223,22 +1223,59 @@ extern "C" int b200_check_proof_multi(b200_ks* ks, const uint64_t* commitment, c
 // three MSMs of `batch` terms on the device (bucket MSM from 32 terms on) and one pairing on the host.  rs: batch canonical
 // scalars from the caller's CSPRNG (the Go shim uses crypto/rand); a single r_i == 0 would drop proof i from the check,
 // so zeros are rejected.
+// a_pts, proofs, cs, rs: host arrays of `batch` entries; g_scalar (may be null): an extra term g_scalar * G on the left.
+// Device-resident: both point arrays go up once, are checked to be on the curve there, and feed the three MSMs; three
+// points come back.  The scalars r_i c_i are formed on the host (Fr products).
 static int aggregate_check(const uint64_t* a_pts, const uint64_t* proofs, const uint64_t* cs, const uint64_t* rs, size_t batch,
-                           const G2J& t2, int* ok) {
-    std::vector<uint64_t> rc(batch * 4);
+                           const G2J& t2, const Fr* g_scalar_canon, int* ok) {
+    if (b200_device_count() == 0) return B200_ERR_NO_DEVICE;
+    const size_t na = batch + (g_scalar_canon ? 1 : 0);
+    std::vector<uint64_t> rc(batch * 4), ra(na * 4), apts(na * 18);
     for (size_t i = 0; i < batch; i++) {
         if (!fr_canon_valid(rs + 4 * i) || !fr_canon_valid(cs + 4 * i)) return B200_ERR_BAD_INPUT;
         const Fr r = fr_load_canon(rs + 4 * i);
         if (r.is_zero()) return B200_ERR_BAD_INPUT;
         fr_store_canon(rc.data() + 4 * i, fe_mul(fe_to_mont(r), fr_load_canon(cs + 4 * i)));
-        if (!abi_coords_canonical(proofs + 18 * i, 3) || !g1_on_curve(g1_from_abi_h(proofs + 18 * i))) return B200_ERR_BAD_INPUT;
+        if (!abi_coords_canonical(proofs + 18 * i, 3) || !abi_coords_canonical(a_pts + 18 * i, 3)) return B200_ERR_BAD_INPUT;
     }
-    uint64_t sa[18], sb[18], sp[18];
-    CKS(b200_g1_lincomb(a_pts, rs, batch, sa));
-    CKS(b200_g1_lincomb(proofs, rc.data(), batch, sb));
-    CKS(b200_g1_lincomb(proofs, rs, batch, sp));
-    const G1J lhs = g1_add(g1_from_abi(sa), g1_from_abi(sb));
-    *ok = pairings_verify(lhs, g2_generator(), g1_from_abi(sp), t2) ? 1 : 0;
+    memcpy(ra.data(), rs, batch * 32);
+    memcpy(apts.data(), a_pts, batch * 144);
+    if (g_scalar_canon) {
+        fr_store_canon(ra.data() + 4 * batch, *g_scalar_canon);
+        g1_to_abi(apts.data() + 18 * batch, g1_generator());
+    }
+    CK(cudaSetDevice(g_device));
+    StreamLease lease; CKS(lease.acquire()); cudaStream_t st = lease.st;
+    DevBuf raw_a, raw_p, da, dp, k_a, k_rc, k_r, work, res, flag;
+    CKS(raw_a.alloc(na * 144, st)); CKS(raw_p.alloc(batch * 144, st)); CKS(da.alloc(na * sizeof(G1J), st)); CKS(dp.alloc(batch * sizeof(G1J), st));
+    CKS(k_a.alloc(na * 32, st)); CKS(k_rc.alloc(batch * 32, st)); CKS(k_r.alloc(batch * 32, st));
+    CKS(work.alloc(3 * na * sizeof(G1J), st)); CKS(res.alloc(3 * 144, st)); CKS(flag.alloc(4, st));
+    CK(cudaMemcpyAsync(raw_a.p, apts.data(), na * 144, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(raw_p.p, proofs, batch * 144, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k_a.p, ra.data(), na * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k_rc.p, rc.data(), batch * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k_r.p, rs, batch * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(flag.p, 0, 4, st));
+    launch_g1_from_abi(raw_a.as<uint64_t>(), da.as<G1J>(), na, st);
+    launch_g1_from_abi(raw_p.as<uint64_t>(), dp.as<G1J>(), batch, st);
+    launch_g1_on_curve(da.as<G1J>(), na, flag.as<uint32_t>(), st);
+    launch_g1_on_curve(dp.as<G1J>(), batch, flag.as<uint32_t>(), st);
+    G1J* w = work.as<G1J>();
+    CKS(dev_lincomb(da.as<G1J>(), 0, k_a.as<Fr>(), 0, w, na, 1, st));                   // sum r_i A_i (+ g G)
+    CKS(dev_lincomb(dp.as<G1J>(), 0, k_rc.as<Fr>(), 0, w + na, batch, 1, st));          // sum r_i c_i proof_i
+    CKS(dev_lincomb(dp.as<G1J>(), 0, k_r.as<Fr>(), 0, w + 2 * na, batch, 1, st));       // sum r_i proof_i
+    launch_g1_to_abi(w, res.as<uint64_t>(), 1, 1, 1, 1, 0, 0, st);
+    launch_g1_to_abi(w + na, res.as<uint64_t>() + 18, 1, 1, 1, 1, 0, 0, st);
+    launch_g1_to_abi(w + 2 * na, res.as<uint64_t>() + 36, 1, 1, 1, 1, 0, 0, st);
+    CKS(check_launches());
+    uint64_t h_res[54];
+    uint32_t h_flag = 0;
+    CK(cudaMemcpyAsync(h_res, res.p, sizeof h_res, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_flag, flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_flag) return B200_ERR_BAD_INPUT;                                              // a point off the curve
+    const G1J lhs = g1_add(g1_from_abi(h_res), g1_from_abi(h_res + 18));
+    *ok = pairings_verify(lhs, g2_generator(), g1_from_abi(h_res + 36), t2) ? 1 : 0;
     return B200_OK;
 }
 extern "C" int b200_check_proof_single_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
@@ -1247,9 +1284,14 @@ extern "C" int b200_check_proof_single_aggregate(b200_ks* ks, const uint64_t* co
     G2J s2;
     CKS(ks_secret_g2(ks, 1, &s2));
     if (batch == 0) { *ok = 1; return B200_OK; }
-    std::vector<uint64_t> a(batch * 18);
-    CKS(b200_check_proof_single_g1_batch(commitments, ys, batch, a.data()));
-    return aggregate_check(a.data(), proofs, xs, rs, batch, s2, ok);
+    // sum r_i (commitment_i - y_i G) = sum r_i commitment_i - (sum r_i y_i) G: one extra term instead of a product per proof
+    Fr ry = Fr::zero();
+    for (size_t i = 0; i < batch; i++) {
+        if (!fr_canon_valid(ys + 4 * i) || !fr_canon_valid(rs + 4 * i)) return B200_ERR_BAD_INPUT;
+        ry = fe_add(ry, fe_mul(fe_to_mont(fr_load_canon(rs + 4 * i)), fr_load_canon(ys + 4 * i)));
+    }
+    const Fr neg_ry = fe_neg(ry);
+    return aggregate_check(commitments, proofs, xs, rs, batch, s2, &neg_ry, ok);
 }
 extern "C" int b200_check_proof_multi_aggregate(b200_ks* ks, const uint64_t* commitments, const uint64_t* proofs, const uint64_t* xs,
                                                 const uint64_t* ys, size_t n, const uint64_t* rs, size_t batch, int* ok) {
@@ -1259,7 +1301,7 @@ extern "C" int b200_check_proof_multi_aggregate(b200_ks* ks, const uint64_t* com
     if (batch == 0) { *ok = 1; return B200_OK; }
     std::vector<uint64_t> a(batch * 18), xn(batch * 4);
     CKS(b200_check_proof_multi_g1_batch(ks, commitments, xs, ys, n, batch, a.data(), xn.data()));
-    return aggregate_check(a.data(), proofs, xn.data(), rs, batch, sn, ok);
+    return aggregate_check(a.data(), proofs, xn.data(), rs, batch, sn, nullptr, ok);
 }
 
 // ------------------------------------------------------------------------------ FK20

@@ -140,6 +140,7 @@ void launch_g1_add_arrays(G1J* dst, size_t dst_estride, size_t dst_bstride, cons
                           size_t src_bstride, size_t n, size_t batch, cudaStream_t st);
 // dst[i] -= src[i * src_stride]   (contiguous dst; src_stride in points)
 void launch_g1_sub_arrays(G1J* dst, const G1J* src, size_t src_stride, size_t n, cudaStream_t st);
+void launch_g1_on_curve(const G1J* pts, size_t n, uint32_t* flag, cudaStream_t st);   // flag |= 1 if a point is off the curve
 // bls/bls_kilic.go:118-121 FromCompressedG1 over an array: flags, x < p, curve equation, prime-order subgroup;
 // out[i] = ABI point (canonical, Z = 1; all zero for infinity and for rejected encodings), status[i] = 0 ok / 1 / 2 / 3
 void launch_g1_decompress(const uint8_t* in48, uint64_t* out_abi, uint32_t* status, size_t n, cudaStream_t st);

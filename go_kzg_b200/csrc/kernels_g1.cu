@@ -776,6 +776,23 @@ void launch_g1_add_arrays(G1J* dst, size_t dst_estride, size_t dst_bstride, cons
     g_launch_count++;
 }
 
+// flag |= 1 if any of the n points is off the curve Y^2 = X^3 + 4 Z^6 (infinity, Z == 0, is on it): the aggregated checks feed
+// caller-supplied points into MSMs, whose results mean nothing for points outside the group
+__global__ void __launch_bounds__(128) k_g1_on_curve(const G1J* __restrict__ pts, size_t n, uint32_t* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const G1J p = ld_vec(pts + i);
+    if (p.is_inf()) return;
+    const Fp z2 = fp_sqr(p.z), z6 = fp_mul(fp_sqr(z2), z2);
+    const Fp rhs = fe_add(fp_mul(fp_sqr(p.x), p.x), fp_mul(fp_const_four(), z6));
+    if (fp_sqr(p.y) != rhs) atomicOr(flag, 1u);
+}
+void launch_g1_on_curve(const G1J* pts, size_t n, uint32_t* flag, cudaStream_t st) {
+    ProfScope prof_scope(PROF_MISC, st);
+    if (!n) return;
+    k_g1_on_curve<<<grid_for(n, 128), 128, 0, st>>>(pts, n, flag); g_launch_count++;
+}
+
 __global__ void __launch_bounds__(128) k_g1_sub_arrays(G1J* dst, const G1J* src, size_t src_stride, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

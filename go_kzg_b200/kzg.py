@@ -693,8 +693,12 @@ class KZGSettings:
 
     @staticmethod
     def _random_scalars(batch: int) -> np.ndarray:
+        """`batch` non-zero scalars below 2^248 (< r) from the OS CSPRNG, as (batch, 4) uint64 limbs"""
         import secrets
-        return fr_from_ints([secrets.randbelow(R_MOD - 1) + 1 for _ in range(batch)])
+        raw = np.frombuffer(secrets.token_bytes(batch * 32), dtype=np.uint8).reshape(batch, 32).copy()
+        raw[:, 31] = 0
+        raw[:, 0] |= 1
+        return raw.view(np.uint64).reshape(batch, 4)
 
     def check_proof_single_aggregate(self, commitments, proofs, xs, ys, rs=None) -> bool:
         """All proofs of the batch with one pairing (random linear combination; three device MSMs).  rs: non-zero
